@@ -1,0 +1,153 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference and pin the oracle.
+
+Run in the build container only (needs /root/reference):
+
+    python oracle/gen_golden.py
+
+It imports the reference's vendored HQQ (amq/kernel/hqq) with a stub
+``termcolor`` module (its only missing import), runs the reference's
+Quantizer / BitPack / GPTQLinear / pack_intweight on seeded inputs, asserts
+that every oracle function in oracle/amq_oracle.py reproduces the reference
+output (bit-exact for integer work, exact equality for the fp16 torch path),
+and stores inputs + reference outputs as small fixtures.  The fixtures are
+committed; the reference is not needed to run the tests.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = "/root/reference/amq/kernel/hqq"
+sys.path.insert(0, ROOT)
+
+
+def import_reference():
+    if "termcolor" not in sys.modules:
+        tc = types.ModuleType("termcolor")
+        tc.colored = lambda s, *a, **k: s
+        sys.modules["termcolor"] = tc
+    sys.path.insert(0, REF)
+    from hqq.core.bitpack import BitPack
+    from hqq.core.quantize import Quantizer, BaseQuantizeConfig
+    from hqq.backends.autogptq import GPTQLinear
+    from hqq.backends.ft import pack_intweight
+    return BitPack, Quantizer, BaseQuantizeConfig, GPTQLinear, pack_intweight
+
+
+def main():
+    from oracle import amq_oracle as O
+    BitPack, Quantizer, BaseQuantizeConfig, GPTQLinear, pack_intweight = import_reference()
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    G = 128
+    report = []
+
+    # ---- 1. BitPack round trips (the reference's tests/test_bitpack.py property)
+    rng = np.random.RandomState(42)
+    for nbits, pack, unpack in [(4, BitPack.pack_4bit_u8, BitPack.unpack_4bit_u8),
+                                (2, BitPack.pack_2bit_u8, BitPack.unpack_2bit_u8),
+                                (3, BitPack.pack_3bit_32, BitPack.unpack_3bit_32)]:
+        for R in (40, 64, 130):
+            if nbits != 3 and R % {4: 2, 2: 4}[nbits]:
+                continue
+            codes = rng.randint(0, 2 ** nbits, size=(R, G)).astype(np.uint8)
+            ref_p = pack(torch.from_numpy(codes)).numpy()
+            assert np.array_equal(O.hqq_pack(codes, nbits), ref_p), ("hqq_pack", nbits, R)
+            ref_u = unpack(torch.from_numpy(ref_p)).numpy()
+            assert np.array_equal(O.hqq_unpack(ref_p, nbits), ref_u), ("hqq_unpack", nbits, R)
+            assert np.array_equal(O.hqq_unpack(ref_p, nbits, rows=R), codes)
+            if R == 130 or (R == 64 and nbits != 3):
+                np.savez_compressed(os.path.join(out_dir, f"bitpack_{nbits}bit_R{R}.npz"),
+                                    codes=codes, packed=ref_p)
+    report.append("bitpack ok")
+
+    # ---- 2. Quantizer.quantize / dequantize -> GPTQLinear.pack -> forward (torch path)
+    for (N, K) in [(64, 256), (256, 512)]:
+        for nbits in (2, 3, 4):
+            torch.manual_seed(1000 * nbits + N)
+            W = (torch.randn(N, K) * 0.02).half()
+            cfg = BaseQuantizeConfig(nbits=nbits, group_size=G)["weight_quant_params"]
+            W_q, meta = Quantizer.quantize(W, device="cpu", compute_dtype=torch.float16, **cfg)
+            meta["compute_dtype"] = torch.float16
+            # the reference moves meta to fp16 on .cuda() (quantize.py:202-217)
+            scale16 = meta["scale"].half()
+            zero16 = meta["zero"].half()
+            meta16 = dict(meta, scale=scale16, zero=zero16)
+            W_deq = Quantizer.dequantize(W_q, meta16)
+
+            # oracle: quantize
+            codes, o_scale, o_zero, n_it = O.hqq_quantize(W, nbits, G)
+            ref_codes = O.hqq_unpack(W_q.numpy(), nbits, rows=N * K // G)
+            assert np.array_equal(codes, ref_codes), ("quantize codes", nbits)
+            assert torch.equal(o_scale, meta["scale"]) and torch.equal(o_zero, meta["zero"]), ("meta", nbits)
+            assert np.array_equal(O.hqq_pack(codes, nbits), W_q.numpy())
+            o_deq = O.hqq_dequantize(codes, scale16, zero16, (N, K))
+            assert torch.equal(o_deq, W_deq), ("dequant", nbits)
+
+            # GPTQ pack
+            layer = GPTQLinear(nbits, G, K, N, bias=False, kernel_switch_threshold=0)
+            s2 = scale16.reshape(N, -1)
+            z2 = zero16.reshape(N, -1)
+            layer.pack(W_deq, s2, z2)
+            q_codes = O.gptq_codes_from_weight(W_deq, s2, z2, G)
+            assert np.array_equal(q_codes.astype(np.uint8), codes.reshape(N, K)), ("codes survive dequant", nbits)
+            assert np.array_equal(O.gptq_pack_codes(q_codes, nbits), layer.qweight.numpy()), ("gptq pack", nbits)
+            assert np.array_equal(O.gptq_unpack(layer.qweight.numpy(), nbits), q_codes.T.astype(np.uint8))
+            assert np.array_equal(O.gptq_unpack_fast(layer.qweight.numpy(), nbits), q_codes.T.astype(np.uint8))
+
+            # forward (torch dequant+matmul branch), M in {1, 5}
+            fx = {}
+            for M in (1, 5):
+                torch.manual_seed(7 + M)
+                x = torch.randn(M, K).half()
+                y_ref = layer(x)
+                y_or = O.gptq_forward_torch(x, layer.qweight.numpy(), layer.scales, layer.zeros, nbits, G)
+                assert torch.equal(y_ref, y_or), ("gptq fwd", nbits, M)
+                y32 = O.gptq_forward_fp32(x, layer.qweight.numpy(), layer.scales, layer.zeros, nbits, G)
+                fx[f"x{M}"] = x.numpy()
+                fx[f"y{M}_ref_fp16"] = y_ref.numpy()
+                fx[f"y{M}_fp32"] = y32.numpy()
+                report.append(f"N{N} K{K} b{nbits} M{M}: ref-fp16 vs fp32 max-rel {O.max_rel(y_ref, y32):.2e}")
+
+            extra = {}
+            if nbits == 4:
+                ft_q = pack_intweight(torch.from_numpy(q_codes.astype(np.int32)), interleave=4, kstride=64).numpy()
+                assert np.array_equal(O.ft_pack_intweight(q_codes), ft_q), "ft pack"
+                assert np.array_equal(O.ft_unpack(ft_q), q_codes.astype(np.uint8)), "ft unpack"
+                extra["ft_qweight"] = ft_q
+            np.savez_compressed(
+                os.path.join(out_dir, f"linear_{nbits}bit_N{N}_K{K}.npz"),
+                W=W.numpy(), hqq_Wq=W_q.numpy(), hqq_scale=meta["scale"].numpy(),
+                hqq_zero=meta["zero"].numpy(), codes=codes, W_deq=W_deq.numpy(),
+                gptq_qweight=layer.qweight.numpy(), gptq_scales=layer.scales.numpy(),
+                gptq_zeros=layer.zeros.numpy(), solver_iters=np.int32(n_it), **fx, **extra)
+    report.append("quantize/dequant/gptq/ft ok")
+
+    # ---- 3. arch selection rule (amq_speed_benchmark.py:209-229) on a synthetic stats file
+    import json
+    rs = np.random.RandomState(0)
+    names = ["self_attn.q_proj", "self_attn.k_proj", "self_attn.v_proj", "self_attn.o_proj",
+             "mlp.gate_proj", "mlp.up_proj", "mlp.down_proj"]
+    entries = []
+    for i in range(12):
+        arch = {"linear": {n: rs.choice([2, 3, 4], size=4).tolist() for n in names}}
+        entries.append([arch, float(rs.rand()), float(2.9 + 0.02 * i)])
+    stats = {"archive": entries[:8], "candidates": entries[8:]}
+    # reference rule, executed verbatim in spirit: filter, count 4-bit, argmax
+    cands = [a for a in stats["archive"] + stats["candidates"] if abs(a[-1] - 3.0) < 0.05]
+    cb = [np.concatenate([b for b in a[0]["linear"].values()]) for a in cands]
+    pick = cands[int(np.argmax([(b == 4.0).sum() for b in cb]))][0]["linear"]
+    assert O.select_arch(stats, 3.0) == pick
+    with open(os.path.join(out_dir, "arch_stats.json"), "w") as f:
+        json.dump({"stats": stats, "target_bits": 3.0, "expected": pick}, f)
+    report.append("arch selection ok")
+
+    print("\n".join(report))
+
+
+if __name__ == "__main__":
+    main()
