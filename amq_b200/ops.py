@@ -1,0 +1,235 @@
+"""Python shims over the C ABI (include/amqb.h).  The shims own all allocations (torch tensors)
+and pass raw device pointers + the current CUDA stream; the library allocates nothing."""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import GemvProblem, check, cur_stream, lib, ptr
+
+GROUP = 128
+_workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
+
+
+def native_supported(bits: int, N: int, K: int, G: int) -> bool:
+    return bits in (2, 3, 4) and G == GROUP and N % 32 == 0 and K % GROUP == 0 and N > 0 and K > 0
+
+
+def native_bytes(bits: int, N: int, K: int) -> int:
+    return int(lib().amqb_native_bytes(bits, N, K))
+
+
+def workspace(device: torch.device, max_N: int = 1 << 17, max_K: int = 1 << 15, max_M: int = 16) -> torch.Tensor:
+    """Zero-filled split-K workspace, one per (device, stream).  The decode kernels leave the
+    arrival counters zeroed, so it is allocated and cleared exactly once."""
+    dev = device.index if device.index is not None else torch.cuda.current_device()
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _workspaces.get(key)
+    need = int(lib().amqb_workspace_bytes(max_N, max_K, max_M))
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(need, dtype=torch.uint8, device=torch.device("cuda", dev))
+        _workspaces[key] = ws
+    return ws
+
+
+def _req_cuda(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("amq_b200: CUDA tensors required (no CPU fallback on this path)")
+
+
+# ------------------------------------------------------------------ layout transcoders
+def unpack_codes(packed: torch.Tensor, bits: int, layout: int, N: int, K: int, G: int = GROUP) -> torch.Tensor:
+    _req_cuda(packed)
+    out = torch.empty((N, K), dtype=torch.uint8, device=packed.device)
+    check(lib().amqb_unpack_codes(bits, layout, ptr(packed), ptr(out), N, K, G, cur_stream()), "unpack_codes")
+    return out
+
+
+def repack_gptq(bits: int, qweight: torch.Tensor, scales: torch.Tensor, zeros: torch.Tensor,
+                N: int, K: int, G: int = GROUP) -> torch.Tensor:
+    _req_cuda(qweight, scales, zeros)
+    nat = torch.empty(native_bytes(bits, N, K), dtype=torch.uint8, device=qweight.device)
+    scratch = torch.empty((N, K), dtype=torch.uint8, device=qweight.device)
+    check(lib().amqb_repack_gptq(bits, ptr(qweight), ptr(scales.float().contiguous()), ptr(zeros.float().contiguous()),
+                                 ptr(nat), ptr(scratch), N, K, G, cur_stream()), "repack_gptq")
+    return nat
+
+
+def repack_ft(qweight: torch.Tensor, scales: torch.Tensor, scaled_zeros: torch.Tensor,
+              N: int, K: int, G: int = GROUP) -> torch.Tensor:
+    _req_cuda(qweight, scales, scaled_zeros)
+    nat = torch.empty(native_bytes(4, N, K), dtype=torch.uint8, device=qweight.device)
+    scratch = torch.empty((N, K), dtype=torch.uint8, device=qweight.device)
+    check(lib().amqb_repack_ft(ptr(qweight), ptr(scales.half().contiguous()), ptr(scaled_zeros.half().contiguous()),
+                               ptr(nat), ptr(scratch), N, K, G, cur_stream()), "repack_ft")
+    return nat
+
+
+def pack_native(bits: int, codes: torch.Tensor, scale: torch.Tensor, zero: torch.Tensor,
+                zero_is_scaled: bool = False, G: int = GROUP) -> torch.Tensor:
+    """codes u8 [N,K]; scale/zero fp16 [N, K/G] (HQQ meta; W = (q - zero) * scale)."""
+    _req_cuda(codes, scale, zero)
+    N, K = codes.shape
+    nat = torch.empty(native_bytes(bits, N, K), dtype=torch.uint8, device=codes.device)
+    check(lib().amqb_pack_native(bits, ptr(codes.contiguous()), ptr(scale.half().contiguous()),
+                                 ptr(zero.half().contiguous()), int(zero_is_scaled), ptr(nat), N, K, G, cur_stream()),
+          "pack_native")
+    return nat
+
+
+def gptq_pack(bits: int, W: torch.Tensor, scales: torch.Tensor, zeros: torch.Tensor, G: int):
+    """GPTQLinear.pack on the GPU. W fp16 [N,K]; scales/zeros [N,K/G] -> (qweight, scales_f32, zeros_f32)."""
+    _req_cuda(W, scales, zeros)
+    N, K = W.shape
+    qweight = torch.empty((K // 32 * bits, N), dtype=torch.int32, device=W.device)
+    s_out = torch.empty((K // G, N), dtype=torch.float32, device=W.device)
+    z_out = torch.empty((K // G, N), dtype=torch.float32, device=W.device)
+    check(lib().amqb_gptq_pack(bits, ptr(W.half().contiguous()), ptr(scales.half().contiguous()),
+                               ptr(zeros.half().contiguous()), ptr(qweight), ptr(s_out), ptr(z_out), N, K, G,
+                               cur_stream()), "gptq_pack")
+    return qweight, s_out, z_out
+
+
+def ft_pack(W: torch.Tensor, scales: torch.Tensor, zeros: torch.Tensor, G: int):
+    _req_cuda(W, scales, zeros)
+    N, K = W.shape
+    qweight = torch.empty((N // 4, K), dtype=torch.int16, device=W.device)
+    s_out = torch.empty((K // G, N), dtype=torch.float16, device=W.device)
+    z_out = torch.empty((K // G, N), dtype=torch.float16, device=W.device)
+    check(lib().amqb_ft_pack(ptr(W.half().contiguous()), ptr(scales.half().contiguous()), ptr(zeros.half().contiguous()),
+                             ptr(qweight), ptr(s_out), ptr(z_out), N, K, G, cur_stream()), "ft_pack")
+    return qweight, s_out, z_out
+
+
+# ------------------------------------------------------------------ decode
+def make_problem(bits: int, w_native: torch.Tensor, x: torch.Tensor, y: torch.Tensor, N: int, K: int,
+                 bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+                 prologue: int = _lib.PRO_NONE, gamma: Optional[torch.Tensor] = None, eps: float = 0.0,
+                 ldx: Optional[int] = None, ldy: Optional[int] = None) -> GemvProblem:
+    M = x.shape[0]
+    p = GemvProblem()
+    p.bits, p.M, p.N, p.K = bits, M, N, K
+    p.w_native = w_native.data_ptr()
+    p.x = x.data_ptr()
+    p.ldx = ldx if ldx is not None else x.stride(0)
+    p.y = y.data_ptr()
+    p.ldy = ldy if ldy is not None else y.stride(0)
+    p.bias = bias.data_ptr() if bias is not None else None
+    p.residual = residual.data_ptr() if residual is not None else None
+    p.prologue = prologue
+    p.gamma = gamma.data_ptr() if gamma is not None else None
+    p.eps = eps
+    return p
+
+
+def gemv_grouped(problems: Sequence[GemvProblem], ws: torch.Tensor, pdl: bool = False) -> None:
+    arr = (GemvProblem * len(problems))(*problems)
+    check(lib().amqb_gemv_grouped(arr, len(problems), ptr(ws), ctypes.c_size_t(ws.numel()), int(pdl), cur_stream()),
+          "gemv_grouped")
+
+
+def gemv(bits: int, w_native: torch.Tensor, x: torch.Tensor, N: int, K: int,
+         bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y fp16 [M,N] = x[M,K] @ dequant(W)^T (+bias), M <= 16, through amqb_gemv_w{2,3,4}."""
+    _req_cuda(w_native, x)
+    if x.dtype != torch.float16:
+        raise RuntimeError("amq_b200: fp16 activations required (as the reference kernels, autogptq.py:165-169, ft.py:62)")
+    x = x.contiguous()
+    M = x.shape[0]
+    y = out if out is not None else torch.empty((M, N), dtype=torch.float16, device=x.device)
+    ws = workspace(x.device)
+    fn = {2: lib().amqb_gemv_w2, 3: lib().amqb_gemv_w3, 4: lib().amqb_gemv_w4}[bits]
+    check(fn(ptr(w_native), ptr(x), ptr(y), ptr(bias), M, N, K, ptr(ws), ctypes.c_size_t(ws.numel()), cur_stream()),
+          f"gemv_w{bits}")
+    return y
+
+
+def gemv_gptq_layout(bits: int, qweight: torch.Tensor, scales: torch.Tensor, zeros: torch.Tensor, x: torch.Tensor,
+                     N: int, K: int, G: int, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req_cuda(qweight, scales, zeros, x)
+    x = x.contiguous()
+    M = x.shape[0]
+    y = torch.empty((M, N), dtype=torch.float16, device=x.device)
+    check(lib().amqb_gemv_gptq_layout(bits, ptr(qweight), ptr(scales), ptr(zeros), ptr(x), ptr(y), ptr(bias),
+                                      M, N, K, G, cur_stream()), "gemv_gptq_layout")
+    return y
+
+
+def linear_forward(bits: int, w_native: torch.Tensor, x2: torch.Tensor, N: int, K: int,
+                   bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """Dispatch on the row count like the reference modules do (autogptq.py:163, ft.py:129-142):
+    decode kernel for M <= 16, tensor-core prefill kernel above."""
+    M = x2.shape[0]
+    if M <= 16:
+        return gemv(bits, w_native, x2, N, K, bias)
+    return gemm_tc(bits, w_native, x2, N, K, bias)
+
+
+def gemm_tc(bits: int, w_native: torch.Tensor, x: torch.Tensor, N: int, K: int,
+            bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req_cuda(w_native, x)
+    x = x.contiguous()
+    M = x.shape[0]
+    y = torch.empty((M, N), dtype=torch.float16, device=x.device)
+    L = lib()
+    if not hasattr(L, "amqb_gemm_tc"):
+        raise RuntimeError("amq_b200: amqb_gemm_tc missing from libamqb.so")
+    need = int(L.amqb_gemm_workspace_bytes(M, K, bits))
+    wsb = torch.empty(max(need, 16), dtype=torch.uint8, device=x.device)
+    check(L.amqb_gemm_tc(bits, ptr(w_native), ptr(x), ptr(y), ptr(bias), M, N, K, ptr(wsb),
+                         ctypes.c_size_t(wsb.numel()), cur_stream()), "gemm_tc")
+    return y
+
+
+# ------------------------------------------------------------------ HQQ proxy ops
+def hqq_dequant(bits: int, W_q: torch.Tensor, scale: torch.Tensor, zero: torch.Tensor, N: int, K: int,
+                G: int = GROUP) -> torch.Tensor:
+    _req_cuda(W_q, scale, zero)
+    out = torch.empty((N, K), dtype=torch.float16, device=W_q.device)
+    check(lib().amqb_hqq_dequant(bits, ptr(W_q), ptr(scale.half().contiguous()), ptr(zero.half().contiguous()),
+                                 ptr(out), N, K, G, cur_stream()), "hqq_dequant")
+    return out
+
+
+def hqq_pack(bits: int, codes: torch.Tensor) -> torch.Tensor:
+    _req_cuda(codes)
+    R, G = codes.shape
+    if bits == 3:
+        out = torch.empty(((R + 9) // 10, G), dtype=torch.int32, device=codes.device)
+    else:
+        out = torch.empty((R // (2 if bits == 4 else 4), G), dtype=torch.uint8, device=codes.device)
+    check(lib().amqb_hqq_pack(bits, ptr(codes.to(torch.uint8).contiguous()), ptr(out), R, G, cur_stream()), "hqq_pack")
+    return out
+
+
+def hqq_unpack(bits: int, W_q: torch.Tensor, R: Optional[int] = None) -> torch.Tensor:
+    _req_cuda(W_q)
+    step, G = W_q.shape
+    p = {4: 2, 2: 4, 3: 10}[bits]
+    Rfull = step * p
+    out = torch.empty((Rfull, G), dtype=torch.uint8, device=W_q.device)
+    check(lib().amqb_hqq_unpack(bits, ptr(W_q.contiguous()), ptr(out), Rfull, G, cur_stream()), "hqq_unpack")
+    return out if R is None else out[:R]
+
+
+def hqq_quantize(W: torch.Tensor, bits: int, G: int = GROUP, round_zero: Optional[bool] = None):
+    """Quantizer.quantize (axis=1) -> (codes u8 [R,G], scale fp32 [R,1], zero fp32 [R,1], iters)."""
+    _req_cuda(W)
+    if round_zero is None:
+        round_zero = bits == 4
+    N, K = W.shape
+    R = N * K // G
+    L = lib()
+    codes = torch.empty((R, G), dtype=torch.uint8, device=W.device)
+    scale = torch.empty((R, 1), dtype=torch.float32, device=W.device)
+    zero = torch.empty((R, 1), dtype=torch.float32, device=W.device)
+    iters = torch.zeros(1, dtype=torch.int32, device=W.device)
+    need = int(L.amqb_hqq_quantize_workspace_bytes(N, K, G))
+    wsb = torch.zeros(max(need, 16), dtype=torch.uint8, device=W.device)
+    check(L.amqb_hqq_quantize(bits, ptr(W.half().contiguous()), ptr(codes), ptr(scale), ptr(zero), int(round_zero),
+                              N, K, G, ptr(wsb), ctypes.c_size_t(wsb.numel()), ptr(iters), cur_stream()), "hqq_quantize")
+    return codes, scale, zero, iters

@@ -1,0 +1,176 @@
+/*
+ * amqb.h — C ABI of the B200-native AMQ quantized-linear hot path.
+ *
+ * Drop-in boundary for the three pybind ops the reference binds for this path
+ * (paths relative to /root/reference/):
+ *   auto_gptq.vecquant{2,3,4}matmul_faster_old   amq/kernel/AutoGPTQ/auto_gptq_kernel.cu:443-475
+ *   faster_transformer.gemv_4bit                  amq/kernel/ft/quantization_new/gemv/gemv_cuda.cu:358-437
+ *   faster_transformer.gemm_4bit                  amq/kernel/ft/quantization_new/gemm/gemm_cuda.cu:929-1032
+ * plus the host-side packers they depend on
+ *   GPTQLinear.pack                               amq/kernel/hqq/hqq/backends/autogptq.py:111-156
+ *   pack_intweight                                amq/kernel/hqq/hqq/backends/ft.py:15-55
+ *   Quantizer.quantize / dequantize, BitPack      amq/kernel/hqq/hqq/core/quantize.py:75-199, core/bitpack.py:24-110
+ *
+ * Conventions: extern "C"; plain device pointers + sizes; every entry point
+ * returns an int status (0 = ok, negative = amqb_status); nothing allocates,
+ * nothing throws; every launch goes to the caller's cudaStream_t (passed as
+ * void*) so calls are CUDA-graph capturable.  All pointers are DEVICE
+ * pointers unless a parameter says "host".  There is no CPU fallback.
+ */
+#ifndef AMQB_H_
+#define AMQB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  AMQB_OK = 0,
+  AMQB_ERR_BAD_ARG = -1,          /* null pointer, bits not in {2,3,4}, M out of range ... */
+  AMQB_ERR_UNSUPPORTED_SHAPE = -2,/* shape precondition of the kernel not met (see each call) */
+  AMQB_ERR_LAUNCH = -3,           /* cudaGetLastError() after the launch was not cudaSuccess */
+  AMQB_ERR_WORKSPACE = -4         /* workspace too small / not zero-initialised */
+} amqb_status;
+
+/* Packed-code layouts understood by amqb_unpack_codes / amqb_repack_* */
+typedef enum {
+  AMQB_LAYOUT_HQQ = 0,    /* HQQLinear.W_q, axis=1 (bitpack.py): u8 [R/p, G] or int32 [ceil(R/10), G] */
+  AMQB_LAYOUT_GPTQ = 1,   /* GPTQLinear.qweight int32 [K*b/32, N] (autogptq.py:55-58) */
+  AMQB_LAYOUT_FT = 2,     /* FT_QuantLinear.qweight int16 [N/4, K], 4-bit only (ft.py:15-55) */
+  AMQB_LAYOUT_NATIVE = 3  /* this library's MMA-fragment-major layout */
+} amqb_layout;
+
+/* Fused prologues / epilogues of the decode kernel (decode-step glue) */
+typedef enum {
+  AMQB_PRO_NONE = 0,      /* x used as is */
+  AMQB_PRO_RMSNORM = 1,   /* x <- x * rsqrt(mean(x^2)+eps) * gamma   (fp32 math, fp16 result) */
+  AMQB_PRO_SILU_MUL = 2   /* x <- silu(x[:, :K]) * x[:, K:2K]  (x is the [M, 2K] gate|up buffer) */
+} amqb_prologue;
+
+const char* amqb_last_error_string(void);
+int amqb_version(void);
+
+/* ---- sizes ------------------------------------------------------------- */
+/* Bytes of the native weight buffer (codes + fp16 scale / zero*scale, interleaved
+ * per 32-row x 128-k record).  Requires N % 32 == 0, K % 128 == 0, G == 128.
+ * Returns 0 for an unsupported shape. */
+size_t amqb_native_bytes(int bits, int N, int K);
+/* Bytes of the split-K workspace a decode launch may touch (fp32 partials +
+ * int32 arrival counters).  The caller allocates it once, ZERO-FILLED, per
+ * stream; the kernels leave the counters zeroed again. */
+size_t amqb_workspace_bytes(int max_N, int max_K, int max_M);
+
+/* ---- bit-exactness probe ---------------------------------------------- */
+/* codes_out: u8 [N, K] row-major, code of output channel n / input channel k. */
+int amqb_unpack_codes(int bits, int layout, const void* packed, uint8_t* codes_out,
+                      int N, int K, int G, void* stream);
+
+/* ---- repack into the native layout (GPTQLinear.post_init / after load_state_dict) */
+/* scratch_codes: u8 [N, K] device scratch. */
+int amqb_repack_gptq(int bits, const int32_t* qweight, const float* scales, const float* zeros,
+                     void* w_native, uint8_t* scratch_codes, int N, int K, int G, void* stream);
+int amqb_repack_ft(const int16_t* qweight, const void* scales_f16, const void* scaled_zeros_f16,
+                   void* w_native, uint8_t* scratch_codes, int N, int K, int G, void* stream);
+/* From u8 codes [N, K] + fp16 scale [N, K/G] + fp16 zero [N, K/G] (HQQ meta: W=(q-zero)*scale). */
+int amqb_pack_native(int bits, const uint8_t* codes, const void* scale_f16, const void* zero_f16,
+                     int zero_is_scaled, void* w_native, int N, int K, int G, void* stream);
+
+/* ---- packers of the reference layouts (replace the CPU numpy loops) ---- */
+/* GPTQLinear.pack (autogptq.py:111-156): W_deq fp16 [N,K], scales/zeros fp16 [N,K/G]
+ * -> qweight int32 [K*b/32, N], scales_out/zeros_out fp32 [K/G, N]. */
+int amqb_gptq_pack(int bits, const void* W_f16, const void* scales_f16, const void* zeros_f16,
+                   int32_t* qweight, float* scales_out, float* zeros_out,
+                   int N, int K, int G, void* stream);
+/* FT_QuantLinear.pack (ft.py:103-126) -> qweight int16 [N/4,K], scales/scaled_zeros fp16 [K/G,N]. */
+int amqb_ft_pack(const void* W_f16, const void* scales_f16, const void* zeros_f16,
+                 int16_t* qweight, void* scales_out_f16, void* scaled_zeros_out_f16,
+                 int N, int K, int G, void* stream);
+
+/* ---- decode: fused dequant GEMV / skinny GEMM, M = 1..16 ---------------- */
+typedef struct {
+  int bits;                 /* 2, 3 or 4 */
+  int M, N, K;              /* rows of x, out features, in features */
+  const void* w_native;     /* amqb_native_bytes(bits, N, K) bytes */
+  const void* x;            /* fp16 [M, ldx] */
+  int ldx;
+  void* y;                  /* fp16 [M, ldy]; written, not accumulated into */
+  int ldy;
+  const void* bias;         /* fp16 [N] or NULL */
+  const void* residual;     /* fp16 [M, ldy] added to the result, or NULL (may alias y) */
+  int prologue;             /* amqb_prologue */
+  const void* gamma;        /* fp16 [K] RMSNorm weight (AMQB_PRO_RMSNORM) */
+  float eps;
+} amqb_gemv_problem;
+
+/* One launch over `count` independent problems sharing M (q/k/v or gate/up, mixed bit-widths
+ * allowed).  workspace: amqb_workspace_bytes() bytes, zero-filled once.  pdl != 0 launches with
+ * programmatic stream serialization (weights prefetch overlaps the previous kernel's tail). */
+int amqb_gemv_grouped(const amqb_gemv_problem* problems_host, int count,
+                      void* workspace, size_t workspace_bytes, int pdl, void* stream);
+/* Single-problem convenience wrappers, one per bit width (the three specialisations). */
+int amqb_gemv_w2(const void* w_native, const void* x, void* y, const void* bias,
+                 int M, int N, int K, void* workspace, size_t workspace_bytes, void* stream);
+int amqb_gemv_w3(const void* w_native, const void* x, void* y, const void* bias,
+                 int M, int N, int K, void* workspace, size_t workspace_bytes, void* stream);
+int amqb_gemv_w4(const void* w_native, const void* x, void* y, const void* bias,
+                 int M, int N, int K, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Direct replacement of vecquant{2,3,4}matmul_faster_old on the UNREPACKED GPTQLinear buffers
+ * (any N % 2 == 0, K % 32 == 0, K % G == 0): y fp16 [M,N] = x @ (scales*q - zeros) (+bias).
+ * SIMT, deterministic (no atomics).  Slower than the native path; used when the native shape
+ * preconditions do not hold and as an independent cross-check. */
+int amqb_gemv_gptq_layout(int bits, const int32_t* qweight, const float* scales, const float* zeros,
+                          const void* x, void* y, const void* bias,
+                          int M, int N, int K, int G, void* stream);
+
+/* ---- prefill: dequant-fused tensor-core GEMM (tcgen05 / TMEM), M >= 17 -- */
+/* workspace: amqb_gemm_workspace_bytes(M, K) bytes (permuted copy of x). */
+size_t amqb_gemm_workspace_bytes(int M, int K, int bits);
+int amqb_gemm_tc(int bits, const void* w_native, const void* x, void* y, const void* bias,
+                 int M, int N, int K, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- HQQ proxy ops (config 4) ------------------------------------------ */
+/* Quantizer.dequantize (quantize.py:183-199) on the HQQ layout: W_out fp16 [N,K] =
+ * (unpack(W_q) - zero) * scale with the reference's two fp16 roundings. */
+int amqb_hqq_dequant(int bits, const void* W_q, const void* scale_f16, const void* zero_f16,
+                     void* W_out_f16, int N, int K, int G, void* stream);
+/* BitPack.pack_* / unpack_* (bitpack.py:24-110): codes u8 [R, G] <-> packed. */
+int amqb_hqq_pack(int bits, const uint8_t* codes, void* W_q, int R, int G, void* stream);
+int amqb_hqq_unpack(int bits, const void* W_q, uint8_t* codes, int R, int G, void* stream);
+/* Quantizer.quantize (quantize.py:75-180 + optimize.py:201-255), axis=1.
+ * W fp16 [N,K] -> codes u8 [R,G] (R = N*K/G), scale/zero fp32 [R] (scale already inverted).
+ * workspace: amqb_hqq_quantize_workspace_bytes(N,K,G).  iters_run_out: device int. */
+size_t amqb_hqq_quantize_workspace_bytes(int N, int K, int G);
+int amqb_hqq_quantize(int bits, const void* W_f16, uint8_t* codes, float* scale, float* zero,
+                      int round_zero, int N, int K, int G, void* workspace, size_t workspace_bytes,
+                      int* iters_run_out, void* stream);
+
+/* ---- decode-step glue ----------------------------- */
+int amqb_embed(const int64_t* token_ids, const void* table_f16, void* out_f16,
+               int M, int hidden, void* stream);
+/* RoPE (HF rotate_half convention) on q,k of this step, append k,v to the static cache,
+ * single-query attention over positions [0, pos].  qkv: fp16 [B, (Hq+2*Hkv)*D].
+ * k_cache/v_cache: fp16 [B, Hkv, max_seq, D].  out: fp16 [B, Hq*D]. */
+int amqb_attn_decode(const void* qkv, void* k_cache, void* v_cache, void* out,
+                     const int* pos_dev, int B, int Hq, int Hkv, int D, int max_seq,
+                     float rope_theta, void* stream);
+/* fp16 GEMV for the unquantised lm_head with fused final RMSNorm prologue:
+ * logits fp32 [M, V] = rmsnorm(x) @ W^T. */
+int amqb_lm_head(const void* W_f16, const void* x, const void* gamma, float eps,
+                 float* logits, int M, int V, int K, void* stream);
+int amqb_argmax(const float* logits, int64_t* out_ids, int M, int V, void* stream);
+
+/* ---- tensor parallel (config 5): one-shot all-reduce over NVLink peer memory */
+/* peer_bufs_host[r] = device pointer of rank r's exchange buffer mapped into this process,
+ * each amqb_ar_buffer_bytes(max_elems, world) bytes, zero-filled at creation. */
+size_t amqb_ar_buffer_bytes(int max_elems, int world);
+int amqb_allreduce_f16(void* const* peer_bufs_host, int rank, int world, void* data_f16,
+                       const void* residual_f16, int n_elems, uint32_t epoch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMQB_H_ */

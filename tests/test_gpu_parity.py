@@ -1,0 +1,194 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the committed
+golden fixtures made from the unmodified reference.  Integer / layout work must be bit-exact;
+outputs must satisfy max|y - ref| / max|ref| <= 1e-3 against the exact-fp32 reference computed
+from the stored buffers."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import amq_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+G = 128
+TOL = 1e-3
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import amq_b200.ops as ops_
+    return ops_
+
+
+def _synthetic(N, K, bits, seed):
+    """Fast synthetic linear: random codes, realistic fp16 scale / fractional zero."""
+    rs = np.random.RandomState(seed)
+    codes = rs.randint(0, 2 ** bits, size=(N, K)).astype(np.uint8)
+    lo, hi = {2: (0.024, 0.054), 3: (0.010, 0.023), 4: (0.0047, 0.011)}[bits]
+    scale = torch.from_numpy(rs.uniform(lo, hi, size=(N, K // G)).astype(np.float32)).half()
+    zero = torch.from_numpy(rs.uniform(0.5, 2 ** bits - 1.5, size=(N, K // G)).astype(np.float32)).half()
+    return codes, scale, zero
+
+
+def _gptq_buffers(codes, scale, zero, bits):
+    qweight = O.gptq_pack_codes(codes.astype(np.int64), bits)
+    scales = scale.t().contiguous().float()
+    zeros = (zero * scale).t().contiguous().float()        # fp16 product, as autogptq.py:112
+    return qweight, scales, zeros
+
+
+# ------------------------------------------------------------------ codes: bit-exact
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "linear_*.npz"))))
+def test_unpack_all_layouts_golden(ops, path):
+    from amq_b200 import _lib
+    d = np.load(path)
+    bits = int(os.path.basename(path).split("_")[1][0])
+    N, K = d["W"].shape
+    codes = d["codes"].reshape(N, K)
+    dev = "cuda"
+    got = ops.unpack_codes(torch.from_numpy(d["hqq_Wq"]).to(dev), bits, _lib.LAYOUT_HQQ, N, K, G).cpu().numpy()
+    assert np.array_equal(got, codes)
+    got = ops.unpack_codes(torch.from_numpy(d["gptq_qweight"]).to(dev), bits, _lib.LAYOUT_GPTQ, N, K, G).cpu().numpy()
+    assert np.array_equal(got, codes)
+    if bits == 4:
+        got = ops.unpack_codes(torch.from_numpy(d["ft_qweight"]).to(dev), bits, _lib.LAYOUT_FT, N, K, G).cpu().numpy()
+        assert np.array_equal(got, codes)
+    nat = ops.repack_gptq(bits, torch.from_numpy(d["gptq_qweight"]).to(dev), torch.from_numpy(d["gptq_scales"]).to(dev),
+                          torch.from_numpy(d["gptq_zeros"]).to(dev), N, K, G)
+    got = ops.unpack_codes(nat, bits, _lib.LAYOUT_NATIVE, N, K, G).cpu().numpy()
+    assert np.array_equal(got, codes)
+
+
+@pytest.mark.parametrize("bits", [2, 3, 4])
+def test_packers_match_reference_golden(ops, bits):
+    """GPTQLinear.pack / FT pack / BitPack on the GPU reproduce the reference's packed tensors."""
+    d = np.load(os.path.join(GOLD, f"linear_{bits}bit_N256_K512.npz"))
+    N, K = d["W"].shape
+    dev = "cuda"
+    W_deq = torch.from_numpy(d["W_deq"]).to(dev)
+    s = torch.from_numpy(d["hqq_scale"]).half().reshape(N, -1).to(dev)
+    z = torch.from_numpy(d["hqq_zero"]).half().reshape(N, -1).to(dev)
+    q, so, zo = ops.gptq_pack(bits, W_deq, s, z, G)
+    assert np.array_equal(q.cpu().numpy(), d["gptq_qweight"])
+    assert np.array_equal(so.cpu().numpy(), d["gptq_scales"]) and np.array_equal(zo.cpu().numpy(), d["gptq_zeros"])
+    codes = torch.from_numpy(d["codes"]).to(dev)
+    assert np.array_equal(ops.hqq_pack(bits, codes).cpu().numpy(), d["hqq_Wq"])
+    assert np.array_equal(ops.hqq_unpack(bits, torch.from_numpy(d["hqq_Wq"]).to(dev), codes.shape[0]).cpu().numpy(), d["codes"])
+    deq = ops.hqq_dequant(bits, torch.from_numpy(d["hqq_Wq"]).to(dev), s.reshape(-1), z.reshape(-1), N, K, G)
+    assert np.array_equal(deq.cpu().numpy(), d["W_deq"])       # two fp16 roundings, bit-exact
+    if bits == 4:
+        fq, fs, fz = ops.ft_pack(W_deq, s, z, G)
+        assert np.array_equal(fq.cpu().numpy(), d["ft_qweight"])
+        assert np.array_equal(fs.cpu().numpy(), d["gptq_scales"].astype(np.float16))
+        assert np.array_equal(fz.cpu().numpy(), (-d["gptq_zeros"]).astype(np.float16))
+
+
+@pytest.mark.parametrize("R", [40, 130, 1310])
+def test_bitpack_roundtrip_property(ops, R):
+    """The reference's tests/test_bitpack.py property: unpack(pack(W)) == W, bit-exact, incl. 3-bit padding."""
+    torch.manual_seed(42)
+    for bits in (2, 3, 4):
+        if bits != 3 and R % (2 if bits == 4 else 4):
+            continue
+        codes = torch.randint(0, 2 ** bits, (R, G), dtype=torch.uint8, device="cuda")
+        packed = ops.hqq_pack(bits, codes)
+        assert np.array_equal(packed.cpu().numpy(), O.hqq_pack(codes.cpu().numpy(), bits))
+        assert torch.equal(ops.hqq_unpack(bits, packed, R), codes)
+
+
+# ------------------------------------------------------------------ outputs: <= 1e-3 max-rel vs fp32
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "linear_*.npz"))))
+@pytest.mark.parametrize("magic", ["0", "1"])
+def test_gemv_golden(ops, path, magic, monkeypatch):
+    monkeypatch.setenv("AMQB_GEMV_MAGIC", magic)
+    d = np.load(path)
+    bits = int(os.path.basename(path).split("_")[1][0])
+    N, K = d["W"].shape
+    dev = "cuda"
+    qw = torch.from_numpy(d["gptq_qweight"]).to(dev)
+    sc = torch.from_numpy(d["gptq_scales"]).to(dev)
+    ze = torch.from_numpy(d["gptq_zeros"]).to(dev)
+    nat = ops.repack_gptq(bits, qw, sc, ze, N, K, G)
+    for M in (1, 5):
+        x = torch.from_numpy(d[f"x{M}"]).to(dev)
+        ref = torch.from_numpy(d[f"y{M}_fp32"])
+        y = ops.gemv(bits, nat, x, N, K).cpu()
+        assert O.max_rel(y, ref) <= TOL, (bits, M, O.max_rel(y, ref))
+        y2 = ops.gemv_gptq_layout(bits, qw, sc, ze, x, N, K, G).cpu()
+        assert O.max_rel(y2, ref) <= TOL
+        # distance to the reference's own fp16 torch output, reported for context
+        assert O.max_rel(y, torch.from_numpy(d[f"y{M}_ref_fp16"])) <= 2e-3
+
+
+SHAPES = [(4096, 4096), (11008, 4096), (4096, 11008), (1024, 4096), (128, 8192), (512, 3584), (3584, 18944), (32, 128)]
+
+
+@pytest.mark.parametrize("N,K", SHAPES)
+@pytest.mark.parametrize("bits", [2, 3, 4])
+def test_gemv_model_shapes(ops, N, K, bits):
+    """Full model shapes (configs 1-3, 5 and the tp=8 shards): GPU fp32 torch reference from the same
+    codes (the CPU oracle is checked against it on the 4096x4096 case below)."""
+    from amq_b200 import _lib
+    dev = "cuda"
+    codes, scale, zero = _synthetic(N, K, bits, seed=N + K + bits)
+    cg = torch.from_numpy(codes).to(dev)
+    sg, zg = scale.to(dev), zero.to(dev)
+    nat = ops.pack_native(bits, cg, sg, zg)
+    assert torch.equal(ops.unpack_codes(nat, bits, _lib.LAYOUT_NATIVE, N, K, G), cg)
+    zs = (zg * sg)                                            # fp16 product
+    W = (cg.float().reshape(N, K // G, G) * sg.float()[..., None] - zs.float()[..., None]).reshape(N, K)
+    torch.manual_seed(bits)
+    bias = torch.randn(N, device=dev).half()
+    for M in (1, 2, 8, 16):
+        x = torch.randn(M, K, device=dev).half()
+        ref = x.float() @ W.t()
+        y = ops.gemv(bits, nat, x, N, K)
+        assert O.max_rel(y.cpu(), ref.cpu()) <= TOL, (N, K, bits, M, O.max_rel(y.cpu(), ref.cpu()))
+        if M in (1, 16):
+            yb = ops.gemv(bits, nat, x, N, K, bias)
+            assert O.max_rel(yb.cpu(), (ref + bias.float()).cpu()) <= TOL
+    # determinism: no atomics on data -> bitwise identical reruns
+    x = torch.randn(1, K, device=dev).half()
+    y1 = ops.gemv(bits, nat, x, N, K)
+    y2 = ops.gemv(bits, nat, x, N, K)
+    assert torch.equal(y1, y2)
+
+
+@pytest.mark.parametrize("bits", [2, 3, 4])
+def test_config1_vs_cpu_oracle(ops, bits):
+    """Config 1: 4096x4096 q_proj-shaped linear, batch-1, against the CPU oracle end to end
+    (oracle pack -> our repack -> our GEMV vs oracle fp32 and the oracle's fp16 torch path)."""
+    N = K = 4096
+    codes, scale, zero = _synthetic(N, K, bits, seed=bits)
+    qweight, scales, zeros = _gptq_buffers(codes, scale, zero, bits)
+    dev = "cuda"
+    nat = ops.repack_gptq(bits, torch.from_numpy(qweight).to(dev), scales.to(dev), zeros.to(dev), N, K, G)
+    torch.manual_seed(0)
+    x = torch.randn(1, K).half()
+    ref32 = O.gptq_forward_fp32(x, qweight, scales, zeros, bits, G)
+    y = ops.gemv(bits, nat, x.to(dev), N, K).cpu()
+    assert O.max_rel(y, ref32) <= TOL
+    ref16 = O.gptq_forward_torch(x, qweight, scales, zeros, bits, G)
+    assert O.max_rel(y, ref16) <= 2e-3
+
+
+def test_error_conventions(ops):
+    from amq_b200 import _lib
+    L = _lib.lib()
+    assert L.amqb_native_bytes(3, 100, 4096) == 0           # N % 32 != 0
+    x = torch.zeros(17, 128, device="cuda", dtype=torch.float16)
+    nat = torch.zeros(ops.native_bytes(3, 32, 128), dtype=torch.uint8, device="cuda")
+    ws = ops.workspace(x.device)
+    y = torch.zeros(17, 32, device="cuda", dtype=torch.float16)
+    rc = L.amqb_gemv_w3(_lib.ptr(nat), _lib.ptr(x), _lib.ptr(y), None, 17, 32, 128, _lib.ptr(ws), ws.numel(), None)
+    assert rc == -1 and b"M must be 1..16" in L.amqb_last_error_string()
+    rc = L.amqb_gemv_w3(_lib.ptr(nat), _lib.ptr(x), _lib.ptr(y), None, 1, 48, 128, _lib.ptr(ws), ws.numel(), None)
+    assert rc == -2
+    with pytest.raises(RuntimeError):
+        ops.gemv(3, nat.cpu(), x[:1], 32, 128)              # CPU tensor: loud failure, no fallback
