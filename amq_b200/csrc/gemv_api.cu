@@ -1,0 +1,163 @@
+// Host side of the decode GEMV: argument checks, launch geometry (cluster size, x' chunking,
+// pipeline depth) and dispatch to the per-bit-width kernels.  Entry points: include/amqb.h.
+#include <stdlib.h>
+
+#include "gemv_mma.cuh"
+
+namespace amqb {
+
+static int g_sm_count = 0;
+static long long* g_dbg = nullptr;
+
+static int sm_count() {
+  if (g_sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+
+// One launch: problems sharing M, bit width and prologue kind.
+static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, cudaStream_t st) {
+  GemvLaunch L{};
+  const int M = pr[0]->M, bits = pr[0]->bits, pro = pr[0]->prologue;
+  const int NB = M <= 8 ? 1 : 2;
+  L.count = count;
+  L.M = M;
+  L.dbg = g_dbg;
+  int max_rb = 0, min_g = 1 << 30;
+  const int B = sm_count();
+  for (int i = 0; i < count; ++i) {
+    const amqb_gemv_problem& q = *pr[i];
+    DevProblem& P = L.prob[i];
+    P.w = (const uint8_t*)q.w_native; P.x = (const __half*)q.x; P.y = (__half*)q.y;
+    P.bias = (const __half*)q.bias; P.residual = (const __half*)q.residual; P.gamma = (const __half*)q.gamma;
+    P.eps = q.eps; P.bits = q.bits; P.N = q.N; P.K = q.K; P.ldx = q.ldx; P.ldy = q.ldy; P.prologue = q.prologue;
+    P.n_rb = q.N / 32; P.n_g = q.K / kGroup;
+    if (P.n_rb > max_rb) max_rb = P.n_rb;
+    if (P.n_g < min_g) min_g = P.n_g;
+  }
+  // K split across a cluster only when N is too small to occupy the chip (each cluster then owns at
+  // most one row block per problem, which is what the DSMEM hand-off assumes)
+  int S = 1;
+  while (S < kMaxCluster && max_rb * S * 2 <= B && S * 2 <= min_g) S *= 2;
+  L.S = S;
+  int ncl = B / S;
+  if (ncl > max_rb) ncl = max_rb;
+  if (ncl < 1) ncl = 1;
+  // x' chunking along K when M * K is too large for shared memory
+  const int per_group = mmas_per_group(bits) * M * 32;
+  int max_kc = 0, acc_blocks = 0, max_slice = 0;
+  for (int i = 0; i < count; ++i) {
+    DevProblem& P = L.prob[i];
+    const int slice = (P.n_g + S - 1) / S;
+    int kc = kXprimeBudget / per_group;
+    if (kc >= slice) kc = slice;
+    else kc = (kc / kStageRecs) * kStageRecs;       // whole pipeline stages per chunk
+    if (kc < 1) return fail(AMQB_ERR_UNSUPPORTED_SHAPE, "gemv: x' chunk does not fit shared memory");
+    P.kc = kc;
+    if (kc > max_kc) max_kc = kc;
+    if (slice > max_slice) max_slice = slice;
+    if (kc < slice) {
+      const int blocks = (P.n_rb + ncl - 1) / ncl;
+      if (blocks > acc_blocks) acc_blocks = blocks;
+    }
+  }
+  L.accbuf_blocks = acc_blocks;
+  {
+    const char* e = getenv("AMQB_COPY_RECS");
+    L.copy_recs = e ? atoi(e) : 4;
+    if (L.copy_recs < 1) L.copy_recs = 1;
+  }
+  const int stage_recs = max_slice < kStageRecs ? max_slice : kStageRecs;
+  L.stage_bytes = stage_recs * rec_bytes(bits);
+  L.xprime_bytes = (max_kc * per_group + 127) & ~127;
+  L.xs_floats = (max_kc * NB * 8 + 31) & ~31;
+  const size_t fixed = 256 + (size_t)L.xs_floats * 4 + 16 * kCW * 4 + L.xprime_bytes +
+                       (size_t)2 * kCW * 2 * NB * 128 * 4 + (size_t)acc_blocks * 2 * NB * 128 * 4 +
+                       (S > 1 ? (size_t)count * S * 2 * NB * 128 * 4 : 0) + 128;
+  if (fixed + 2 * (size_t)L.stage_bytes > (size_t)kSmemTarget)
+    return fail(AMQB_ERR_UNSUPPORTED_SHAPE, "gemv: shared memory budget exceeded");
+  int ns = (int)(((size_t)kSmemTarget - fixed) / L.stage_bytes);
+  if (ns > 8) ns = 8;
+  L.n_stages = ns;
+  const size_t smem = fixed + (size_t)ns * L.stage_bytes;
+  const int grid = ncl * S;
+  if (bits == 2) return launch_w2(L, pro, grid, smem, pdl, st);
+  if (bits == 3) return launch_w3(L, pro, grid, smem, pdl, st);
+  return launch_w4(L, pro, grid, smem, pdl, st);
+}
+
+}  // namespace amqb
+
+using namespace amqb;
+
+extern "C" {
+
+/* debug: per-CTA globaltimer stamps (8 x int64 per CTA) written by the next decode launches */
+int amqb_debug_set_timeline(void* buf) {
+  g_dbg = (long long*)buf;
+  return AMQB_OK;
+}
+
+/* The decode kernels need no global workspace (all reductions stay on chip: shared memory within
+ * a CTA, distributed shared memory within a cluster); the entry points keep the parameter so the
+ * ABI stays stable.  A small non-zero size is returned so callers can keep one buffer per stream. */
+size_t amqb_workspace_bytes(int max_N, int max_K, int max_M) {
+  if (max_N <= 0 || max_K <= 0 || max_M <= 0) return 0;
+  return 256;
+}
+
+int amqb_gemv_grouped(const amqb_gemv_problem* pr, int count, void* workspace, size_t workspace_bytes, int pdl,
+                      void* stream) {
+  (void)workspace; (void)workspace_bytes;
+  if (!pr || count < 1 || count > kMaxProblems) return fail(AMQB_ERR_BAD_ARG, "gemv: bad argument");
+  const int M = pr[0].M;
+  if (M < 1 || M > 16) return fail(AMQB_ERR_BAD_ARG, "gemv: M must be 1..16 (use amqb_gemm_tc for prefill)");
+  for (int i = 0; i < count; ++i) {
+    const amqb_gemv_problem& q = pr[i];
+    if (q.M != M) return fail(AMQB_ERR_BAD_ARG, "gemv: all problems of a group must share M");
+    if (!(q.bits == 2 || q.bits == 3 || q.bits == 4) || !q.w_native || !q.x || !q.y)
+      return fail(AMQB_ERR_BAD_ARG, "gemv: bad problem");
+    if (q.N <= 0 || q.K <= 0 || q.N % 32 || q.K % kGroup)
+      return fail(AMQB_ERR_UNSUPPORTED_SHAPE, "gemv: needs N % 32 == 0 and K % 128 == 0");
+    if ((q.ldx % 4) || ((uintptr_t)q.x & 7) || ((uintptr_t)q.w_native & 15))
+      return fail(AMQB_ERR_BAD_ARG, "gemv: x must be 8-byte aligned with ldx % 4 == 0, w 16-byte aligned");
+    if (q.prologue < AMQB_PRO_NONE || q.prologue > AMQB_PRO_SILU_MUL) return fail(AMQB_ERR_BAD_ARG, "gemv: bad prologue");
+    if (q.prologue == AMQB_PRO_RMSNORM && !q.gamma) return fail(AMQB_ERR_BAD_ARG, "gemv: rmsnorm prologue needs gamma");
+  }
+  // one launch per (bit width, prologue) class present in the group, in first-appearance order
+  bool done[kMaxProblems] = {false, false, false, false};
+  for (int i = 0; i < count; ++i) {
+    if (done[i]) continue;
+    const amqb_gemv_problem* sub[kMaxProblems];
+    int n = 0;
+    for (int j = i; j < count; ++j)
+      if (!done[j] && pr[j].bits == pr[i].bits && pr[j].prologue == pr[i].prologue) { sub[n++] = &pr[j]; done[j] = true; }
+    const int rc = launch_group(sub, n, pdl, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return AMQB_OK;
+}
+
+static int gemv_single(int bits, const void* w, const void* x, void* y, const void* bias, int M, int N, int K,
+                       void* ws, size_t wsb, void* stream) {
+  amqb_gemv_problem p{};
+  p.bits = bits; p.M = M; p.N = N; p.K = K; p.w_native = w; p.x = x; p.ldx = K; p.y = y; p.ldy = N; p.bias = bias;
+  p.prologue = AMQB_PRO_NONE;
+  return amqb_gemv_grouped(&p, 1, ws, wsb, 0, stream);
+}
+
+int amqb_gemv_w2(const void* w, const void* x, void* y, const void* bias, int M, int N, int K, void* ws, size_t wsb, void* stream) {
+  return gemv_single(2, w, x, y, bias, M, N, K, ws, wsb, stream);
+}
+int amqb_gemv_w3(const void* w, const void* x, void* y, const void* bias, int M, int N, int K, void* ws, size_t wsb, void* stream) {
+  return gemv_single(3, w, x, y, bias, M, N, K, ws, wsb, stream);
+}
+int amqb_gemv_w4(const void* w, const void* x, void* y, const void* bias, int M, int N, int K, void* ws, size_t wsb, void* stream) {
+  return gemv_single(4, w, x, y, bias, M, N, K, ws, wsb, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,314 @@
+// Decode-step glue around the quantized linears: embedding gather,
+// RoPE + KV-cache append + single-query attention, the unquantised fp16 lm_head GEMV with the
+// final RMSNorm fused in, and greedy argmax.  (RMSNorm before q/k/v and gate/up, SiLU*up before
+// down_proj and the residual adds live inside the decode GEMV's prologue / epilogue.)
+//
+// Reference counterparts (not on the linear hot path; rebuilt here only because the metric of
+// record is model-level tok/s):
+//   RMSNorm                         /root/reference/amq/kernel/ft/layernorm/layernorm.cu:25-51
+//   single_query_attention + RoPE   /root/reference/amq/kernel/ft/attention/ft_attention.cpp:110-181
+//   static KV cache                 /root/reference/amq/kernel/monkeypatch/ftllama_modeling.py:61-68
+// Every kernel starts with griddepcontrol.launch_dependents / .wait so the whole step chains
+// with programmatic dependent launch inside one CUDA graph.
+#include "common.cuh"
+
+namespace amqb {
+
+static int g_pdl = 0;
+
+template <typename... KArgs, typename... Args>
+static int launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const char* what,
+                  Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args...);
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return AMQB_ERR_LAUNCH;
+  }
+  return AMQB_OK;
+}
+
+// ------------------------------------------------------------------ embedding
+__global__ void embed_kernel(const int64_t* __restrict__ ids, const __half* __restrict__ table,
+                             __half* __restrict__ out, int hidden) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int m = blockIdx.x;
+  const uint4* src = reinterpret_cast<const uint4*>(table + (size_t)ids[m] * hidden);
+  uint4* dst = reinterpret_cast<uint4*>(out + (size_t)m * hidden);
+  for (int i = threadIdx.x; i < hidden / 8; i += blockDim.x) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------ attention (decode)
+// grid (Hq, B), 128 threads.  Lane l of a warp owns head-dim elements [EPL*l, EPL*l+EPL).
+template <int D>
+__global__ void __launch_bounds__(128)
+attn_decode_kernel(const __half* __restrict__ qkv, __half* __restrict__ kc, __half* __restrict__ vc,
+                   __half* __restrict__ out, const int* __restrict__ pos_dev, int Hq, int Hkv, int max_seq,
+                   float theta) {
+  constexpr int EPL = D / 32;     // elements per lane
+  pdl_launch_dependents();
+  pdl_wait();
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int rep = Hq / Hkv, hk = h / rep;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pos = pos_dev[0];
+  const int ld = (Hq + 2 * Hkv) * D;
+  const __half* qp = qkv + (size_t)b * ld + h * D;
+  const __half* kp = qkv + (size_t)b * ld + (Hq + hk) * D;
+  const __half* vp = qkv + (size_t)b * ld + (Hq + Hkv + hk) * D;
+  // RoPE, HF rotate_half convention: pair (i, i + D/2), angle pos * theta^(-2i/D)
+  float q[EPL], kn[EPL], vn[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) {
+    const int i = EPL * lane + e;
+    const int ih = i % (D / 2);
+    const float inv = __powf(theta, -2.f * (float)ih / (float)D);
+    float sn, cs;
+    sincosf((float)pos * inv, &sn, &cs);
+    // fp16-rounded cos / sin as HF (LlamaRotaryEmbedding casts to the activation dtype)
+    cs = __half2float(__float2half_rn(cs));
+    sn = __half2float(__float2half_rn(sn));
+    const int ip = i < D / 2 ? i + D / 2 : i - D / 2;
+    const float sgn = i < D / 2 ? -1.f : 1.f;
+    q[e] = __half2float(qp[i]) * cs + sgn * __half2float(qp[ip]) * sn;
+    kn[e] = __half2float(kp[i]) * cs + sgn * __half2float(kp[ip]) * sn;
+    q[e] = __half2float(__float2half_rn(q[e]));
+    kn[e] = __half2float(__float2half_rn(kn[e]));
+    vn[e] = __half2float(vp[i]);
+  }
+  __half* kcb = kc + ((size_t)b * Hkv + hk) * max_seq * D;
+  __half* vcb = vc + ((size_t)b * Hkv + hk) * max_seq * D;
+  if (h % rep == 0 && warp == 0) {
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      kcb[(size_t)pos * D + EPL * lane + e] = __float2half_rn(kn[e]);
+      vcb[(size_t)pos * D + EPL * lane + e] = __float2half_rn(vn[e]);
+    }
+  }
+  const float scale = rsqrtf((float)D);
+  float mx = -INFINITY, den = 0.f, acc[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
+  for (int j = warp; j <= pos; j += 4) {
+    float kj[EPL], vj[EPL];
+    if (j == pos) {
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) { kj[e] = kn[e]; vj[e] = vn[e]; }
+    } else {
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        kj[e] = __half2float(kcb[(size_t)j * D + EPL * lane + e]);
+        vj[e] = __half2float(vcb[(size_t)j * D + EPL * lane + e]);
+      }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) s += q[e] * kj[e];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    s *= scale;
+    const float nm = fmaxf(mx, s);
+    const float corr = __expf(mx - nm), p = __expf(s - nm);
+    den = den * corr + p;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) acc[e] = acc[e] * corr + p * vj[e];
+    mx = nm;
+  }
+  __shared__ float s_m[4], s_d[4], s_acc[4][D];
+  if (lane == 0) { s_m[warp] = mx; s_d[warp] = den; }
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) s_acc[warp][EPL * lane + e] = acc[e];
+  __syncthreads();
+  if (warp == 0) {
+    float gm = fmaxf(fmaxf(s_m[0], s_m[1]), fmaxf(s_m[2], s_m[3]));
+    float gd = 0.f, w4[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) { w4[w] = (s_m[w] == -INFINITY) ? 0.f : __expf(s_m[w] - gm); gd += s_d[w] * w4[w]; }
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      const int i = EPL * lane + e;
+      const float o = (s_acc[0][i] * w4[0] + s_acc[1][i] * w4[1] + s_acc[2][i] * w4[2] + s_acc[3][i] * w4[3]) / gd;
+      out[(size_t)b * Hq * D + h * D + i] = __float2half_rn(o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ lm_head: fp16 GEMV + fused final RMSNorm
+// One warp per vocab row (grid-stride); x normalised once per CTA into shared memory (fp32).
+template <int MAXM>
+__global__ void __launch_bounds__(256)
+lm_head_kernel(const __half* __restrict__ W, const __half* __restrict__ x, const __half* __restrict__ gamma,
+               float eps, float* __restrict__ logits, int M, int V, int K) {
+  extern __shared__ float xs[];   // [M][K]
+  __shared__ float ssq[8];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int m = 0; m < M; ++m) {
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < K; i += 256) {
+      const float v = __half2float(x[(size_t)m * K + i]);
+      xs[m * K + i] = v;
+      ss += v * v;
+    }
+    if (gamma) {
+#pragma unroll
+      for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      if (lane == 0) ssq[warp] = ss;
+      __syncthreads();
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += ssq[w];
+      const float rs = rsqrtf(t / (float)K + eps);
+      for (int i = threadIdx.x; i < K; i += 256) {
+        const __half xn = __float2half_rn(xs[m * K + i] * rs);
+        xs[m * K + i] = __half2float(__hmul(gamma[i], xn));
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  const int gw = blockIdx.x * 8 + warp, nw = gridDim.x * 8;
+  for (int r = gw; r < V; r += nw) {
+    const uint4* wr = reinterpret_cast<const uint4*>(W + (size_t)r * K);
+    float acc[MAXM];
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m) acc[m] = 0.f;
+    for (int i = lane; i < K / 8; i += 32) {
+      uint4 wv;
+      asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(wv.x), "=r"(wv.y), "=r"(wv.z), "=r"(wv.w) : "l"(wr + i));
+      const __half2* h2 = reinterpret_cast<const __half2*>(&wv);
+      float wf[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h2[j]); wf[2 * j] = f.x; wf[2 * j + 1] = f.y; }
+#pragma unroll
+      for (int m = 0; m < MAXM; ++m) {
+        if (m < M) {
+          const float4 a = *reinterpret_cast<const float4*>(&xs[m * K + 8 * i]);
+          const float4 c = *reinterpret_cast<const float4*>(&xs[m * K + 8 * i + 4]);
+          acc[m] += wf[0] * a.x + wf[1] * a.y + wf[2] * a.z + wf[3] * a.w + wf[4] * c.x + wf[5] * c.y + wf[6] * c.z + wf[7] * c.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m) {
+      if (m < M) {
+        float v = acc[m];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) logits[(size_t)m * V + r] = v;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ argmax (lowest index among maxima)
+__global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ logits, int64_t* __restrict__ out, int V) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int m = blockIdx.x;
+  const float* row = logits + (size_t)m * V;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < V; i += 1024) {
+    const float v = row[i];
+    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+  }
+  __shared__ float sv[32];
+  __shared__ int si[32];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    best = sv[threadIdx.x]; bi = si[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (threadIdx.x == 0) out[m] = bi;
+  }
+}
+
+}  // namespace amqb
+
+using namespace amqb;
+
+extern "C" {
+
+int amqb_set_pdl(int enable) {
+  g_pdl = enable ? 1 : 0;
+  return AMQB_OK;
+}
+
+int amqb_embed(const int64_t* token_ids, const void* table_f16, void* out_f16, int M, int hidden, void* stream) {
+  if (!token_ids || !table_f16 || !out_f16 || M < 1 || hidden % 8) return fail(AMQB_ERR_BAD_ARG, "embed: bad argument");
+  return launch(embed_kernel, dim3(M), dim3(256), 0, (cudaStream_t)stream, "embed", token_ids,
+                (const __half*)table_f16, (__half*)out_f16, hidden);
+}
+
+int amqb_attn_decode(const void* qkv, void* k_cache, void* v_cache, void* out, const int* pos_dev, int B, int Hq,
+                     int Hkv, int D, int max_seq, float rope_theta, void* stream) {
+  if (!qkv || !k_cache || !v_cache || !out || !pos_dev || B < 1 || Hq < 1 || Hkv < 1 || Hq % Hkv)
+    return fail(AMQB_ERR_BAD_ARG, "attn_decode: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (D == 128)
+    return launch(attn_decode_kernel<128>, dim3(Hq, B), dim3(128), 0, st, "attn_decode", (const __half*)qkv,
+                  (__half*)k_cache, (__half*)v_cache, (__half*)out, pos_dev, Hq, Hkv, max_seq, rope_theta);
+  if (D == 64)
+    return launch(attn_decode_kernel<64>, dim3(Hq, B), dim3(128), 0, st, "attn_decode", (const __half*)qkv,
+                  (__half*)k_cache, (__half*)v_cache, (__half*)out, pos_dev, Hq, Hkv, max_seq, rope_theta);
+  return fail(AMQB_ERR_UNSUPPORTED_SHAPE, "attn_decode: head_dim must be 64 or 128");
+}
+
+int amqb_lm_head(const void* W_f16, const void* x, const void* gamma, float eps, float* logits, int M, int V, int K,
+                 void* stream) {
+  if (!W_f16 || !x || !logits || M < 1 || M > 16 || K % 8) return fail(AMQB_ERR_BAD_ARG, "lm_head: bad argument (M 1..16, K % 8)");
+  const size_t smem = (size_t)M * K * sizeof(float);
+  if (smem > 200 * 1024) return fail(AMQB_ERR_UNSUPPORTED_SHAPE, "lm_head: M*K too large for shared memory");
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int per_sm = smem > 100 * 1024 ? 1 : 2;
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(lm_head_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(lm_head_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(lm_head_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  const dim3 grid(sms * per_sm), block(256);
+  if (M == 1)
+    return launch(lm_head_kernel<1>, grid, block, smem, st, "lm_head", (const __half*)W_f16, (const __half*)x,
+                  (const __half*)gamma, eps, logits, M, V, K);
+  if (M <= 4)
+    return launch(lm_head_kernel<4>, grid, block, smem, st, "lm_head", (const __half*)W_f16, (const __half*)x,
+                  (const __half*)gamma, eps, logits, M, V, K);
+  return launch(lm_head_kernel<16>, grid, block, smem, st, "lm_head", (const __half*)W_f16, (const __half*)x,
+                (const __half*)gamma, eps, logits, M, V, K);
+}
+
+int amqb_argmax(const float* logits, int64_t* out_ids, int M, int V, void* stream) {
+  if (!logits || !out_ids || M < 1 || V < 1) return fail(AMQB_ERR_BAD_ARG, "argmax: bad argument");
+  return launch(argmax_kernel, dim3(M), dim3(1024), 0, (cudaStream_t)stream, "argmax", logits, out_ids, V);
+}
+
+}  // extern "C"

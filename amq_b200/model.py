@@ -1,0 +1,270 @@
+"""Mixed-precision decoder assembled from kernel-native quantized linears + the decode-step glue.
+
+This is what `amq_speed_benchmark.py` builds by swapping GPTQLinear / FT_QuantLinear modules into
+an HF model per the searched bit config (/root/reference/amq/amq_speed_benchmark.py:231-251) and
+then times (amq/utils/speed.py:23-46, 93-125).  Here the model is random-init (no checkpoints
+offline), built layer by layer directly in the kernel-native layout so fp16 weights are never
+materialised (mandatory for 70B), and a decode step is a fixed chain of C-ABI launches
+
+    [rmsnorm -> q|k|v GEMV] -> [rope + kv append + attention] -> [o_proj GEMV + residual]
+    -> [rmsnorm -> gate|up GEMV] -> [silu*up -> down_proj GEMV + residual]      (x n_block)
+    -> [final rmsnorm -> lm_head GEMV] -> [argmax]
+
+captured once in a CUDA graph with programmatic dependent launch between the kernels.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import PRO_NONE, PRO_RMSNORM, PRO_SILU_MUL, check, cur_stream, lib, ptr
+from .arch import LINEARS, ModelShape
+
+GROUP = 128
+_SCALE_RANGE = {2: (0.024, 0.054), 3: (0.010, 0.023), 4: (0.0047, 0.011)}   # SURVEY §8d realistic ranges
+
+
+def synthetic_native(bits: int, N: int, K: int, device, gen: torch.Generator) -> torch.Tensor:
+    """Random codes + realistic fp16 scale / zero*scale written straight into the native layout."""
+    nb = ops.native_bytes(bits, N, K)
+    rec = bits * 512 + 128
+    buf = torch.randint(0, 256, (nb // rec, rec), dtype=torch.uint8, device=device, generator=gen)
+    lo, hi = _SCALE_RANGE[bits]
+    n_meta = (nb // rec) * 32
+    scale = torch.empty(n_meta, device=device, dtype=torch.float32).uniform_(lo, hi, generator=gen)
+    zero = torch.empty(n_meta, device=device, dtype=torch.float32).uniform_(0.5, 2 ** bits - 1.5, generator=gen)
+    # keep the dequantised weights ~N(0, 0.02): centre the zero so (q - zero) is roughly symmetric
+    meta = torch.stack([scale.half(), (zero.half() * scale.half())], dim=1).contiguous()     # half2(scale, zero*scale)
+    buf[:, bits * 512:] = meta.view(torch.uint8).reshape(nb // rec, 128)
+    return buf.reshape(-1)
+
+
+class QuantDecoder:
+    """Random-init Llama / Mistral / Qwen2 decoder with per-linear bit widths (arch dict of
+    App. A4: {'self_attn.q_proj': [bits per block], ...})."""
+
+    def __init__(self, shape: ModelShape, arch: Dict[str, List[int]], batch: int = 1, max_seq: int = 256,
+                 device: str = "cuda:0", seed: int = 0, n_block: Optional[int] = None, pdl: bool = True,
+                 tp_rank: int = 0, tp_world: int = 1):
+        if not torch.cuda.is_available():
+            raise RuntimeError("amq_b200.QuantDecoder needs a CUDA device (no CPU path)")
+        self.shape = shape
+        self.arch = arch
+        self.B = batch
+        self.max_seq = max_seq
+        self.dev = torch.device(device)
+        self.n_block = n_block if n_block is not None else shape.n_block
+        self.pdl = pdl
+        self.tp_rank, self.tp_world = tp_rank, tp_world
+        self.H, self.I, self.D = shape.hidden, shape.inter, shape.head_dim
+        tp = tp_world
+        assert shape.n_heads % tp == 0 and shape.n_kv_heads % tp == 0 and shape.inter % (tp * GROUP) == 0
+        self.Hq, self.Hkv = shape.n_heads // tp, shape.n_kv_heads // tp
+        self.I_loc = shape.inter // tp
+        self.q_dim, self.kv_dim = self.Hq * self.D, self.Hkv * self.D
+        torch.cuda.set_device(self.dev)
+        gen = torch.Generator(device=self.dev).manual_seed(seed)
+        H, B = self.H, batch
+        self.embed = (torch.randn(shape.vocab, H, device=self.dev, generator=gen) * 0.02).half()
+        self.lm_head = (torch.randn(shape.vocab, H, device=self.dev, generator=gen) * 0.02).half()
+        self.final_norm = torch.ones(H, device=self.dev, dtype=torch.float16)
+        self.layers = []
+        self.weight_bytes = 0
+        for li in range(self.n_block):
+            L = {}
+            dims = {"self_attn.q_proj": (self.q_dim, H), "self_attn.k_proj": (self.kv_dim, H),
+                    "self_attn.v_proj": (self.kv_dim, H), "self_attn.o_proj": (H, self.q_dim),
+                    "mlp.gate_proj": (self.I_loc, H), "mlp.up_proj": (self.I_loc, H), "mlp.down_proj": (H, self.I_loc)}
+            for name in LINEARS:
+                bits = int(arch[name][li % len(arch[name])])
+                N, K = dims[name]
+                L[name] = (bits, synthetic_native(bits, N, K, self.dev, gen), N, K)
+                self.weight_bytes += L[name][1].numel()
+            L["norm1"] = torch.ones(H, device=self.dev, dtype=torch.float16)
+            L["norm2"] = torch.ones(H, device=self.dev, dtype=torch.float16)
+            if shape.qkv_bias:
+                L["qkv_bias"] = (torch.randn(self.q_dim + 2 * self.kv_dim, device=self.dev, generator=gen) * 0.02).half()
+            L["k_cache"] = torch.zeros(B, self.Hkv, max_seq, self.D, device=self.dev, dtype=torch.float16)
+            L["v_cache"] = torch.zeros(B, self.Hkv, max_seq, self.D, device=self.dev, dtype=torch.float16)
+            self.layers.append(L)
+        # step buffers
+        qkv_w = self.q_dim + 2 * self.kv_dim
+        self.tokens = torch.zeros(B, dtype=torch.int64, device=self.dev)
+        self.h = torch.zeros(B, H, device=self.dev, dtype=torch.float16)
+        self.qkv = torch.zeros(B, qkv_w, device=self.dev, dtype=torch.float16)
+        self.attn = torch.zeros(B, self.q_dim, device=self.dev, dtype=torch.float16)
+        self.gu = torch.zeros(B, 2 * self.I_loc, device=self.dev, dtype=torch.float16)
+        self.part = torch.zeros(B, H, device=self.dev, dtype=torch.float16)      # TP partial sums
+        self.logits = torch.zeros(B, shape.vocab, device=self.dev, dtype=torch.float32)
+        self.next_tokens = torch.zeros(B, dtype=torch.int64, device=self.dev)
+        self.pos = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.ws = ops.workspace(self.dev)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.allreduce = None          # set by amq_b200.tp for tensor-parallel runs
+        self.launches_per_step = 0
+        self._build_problems()
+
+    # ---------------------------------------------------------------- static launch descriptors
+    def _build_problems(self) -> None:
+        eps = self.shape.rms_eps
+        B = self.B
+        self._plan = []
+        for L in self.layers:
+            qb, qw, qn, qk = L["self_attn.q_proj"]
+            kb, kw, kn, kk = L["self_attn.k_proj"]
+            vb, vw, vn, vk = L["self_attn.v_proj"]
+            qkv_ld = self.qkv.stride(0)
+            bias = L.get("qkv_bias")
+
+            def sub(t, off):
+                return ctypes.c_void_p(t.data_ptr() + 2 * off)
+
+            def prob(bits, w, x, y_ptr, N, K, ldx, ldy, bias_ptr=None, residual=None, pro=PRO_NONE, gamma=None):
+                p = ops.GemvProblem()
+                p.bits, p.M, p.N, p.K = bits, B, N, K
+                p.w_native = w.data_ptr()
+                p.x = x.data_ptr()
+                p.ldx = ldx
+                p.y = y_ptr
+                p.ldy = ldy
+                p.bias = bias_ptr
+                p.residual = residual.data_ptr() if residual is not None else None
+                p.prologue = pro
+                p.gamma = gamma.data_ptr() if gamma is not None else None
+                p.eps = eps
+                return p
+
+            def bptr(off):
+                return (bias.data_ptr() + 2 * off) if bias is not None else None
+
+            qkv = [prob(qb, qw, self.h, self.qkv.data_ptr(), qn, qk, self.H, qkv_ld, bptr(0), None, PRO_RMSNORM, L["norm1"]),
+                   prob(kb, kw, self.h, self.qkv.data_ptr() + 2 * self.q_dim, kn, kk, self.H, qkv_ld, bptr(self.q_dim), None,
+                        PRO_RMSNORM, L["norm1"]),
+                   prob(vb, vw, self.h, self.qkv.data_ptr() + 2 * (self.q_dim + self.kv_dim), vn, vk, self.H, qkv_ld,
+                        bptr(self.q_dim + self.kv_dim), None, PRO_RMSNORM, L["norm1"])]
+            ob, ow, on, ok = L["self_attn.o_proj"]
+            tp = self.tp_world > 1
+            o = [prob(ob, ow, self.attn, (self.part if tp else self.h).data_ptr(), on, ok, self.q_dim, self.H, None,
+                      None if tp else self.h)]
+            gb, gw, gn, gk = L["mlp.gate_proj"]
+            ub, uw, un, uk = L["mlp.up_proj"]
+            gu_ld = self.gu.stride(0)
+            gu = [prob(gb, gw, self.h, self.gu.data_ptr(), gn, gk, self.H, gu_ld, None, None, PRO_RMSNORM, L["norm2"]),
+                  prob(ub, uw, self.h, self.gu.data_ptr() + 2 * self.I_loc, un, uk, self.H, gu_ld, None, None, PRO_RMSNORM,
+                       L["norm2"])]
+            db, dw, dn, dk = L["mlp.down_proj"]
+            down = [prob(db, dw, self.gu, (self.part if tp else self.h).data_ptr(), dn, dk, gu_ld, self.H, None,
+                         None if tp else self.h, PRO_SILU_MUL)]
+            self._plan.append({"qkv": (ops.GemvProblem * 3)(*qkv), "o": (ops.GemvProblem * 1)(*o),
+                               "gu": (ops.GemvProblem * 2)(*gu), "down": (ops.GemvProblem * 1)(*down), "L": L})
+
+    # ---------------------------------------------------------------- one decode step (all launches)
+    def _gemv(self, arr, n) -> None:
+        check(lib().amqb_gemv_grouped(arr, n, ptr(self.ws), ctypes.c_size_t(self.ws.numel()), int(self.pdl), cur_stream()),
+              "gemv_grouped")
+        self.launches_per_step += len({(arr[i].bits, arr[i].prologue) for i in range(n)})
+
+    def _step_launches(self) -> None:
+        Lb = lib()
+        st = cur_stream()
+        S = self.shape
+        self.launches_per_step = 0
+        check(Lb.amqb_embed(ptr(self.tokens), ptr(self.embed), ptr(self.h), self.B, self.H, st), "embed")
+        self.launches_per_step += 1
+        for P in self._plan:
+            L = P["L"]
+            self._gemv(P["qkv"], 3)
+            check(Lb.amqb_attn_decode(ptr(self.qkv), ptr(L["k_cache"]), ptr(L["v_cache"]), ptr(self.attn), ptr(self.pos),
+                                      self.B, self.Hq, self.Hkv, self.D, self.max_seq, ctypes.c_float(S.rope_theta), st),
+                  "attn_decode")
+            self.launches_per_step += 1
+            self._gemv(P["o"], 1)
+            if self.allreduce is not None:
+                self.allreduce(self.part, self.h)          # h += sum over ranks of part
+                self.launches_per_step += 1
+            self._gemv(P["gu"], 2)
+            self._gemv(P["down"], 1)
+            if self.allreduce is not None:
+                self.allreduce(self.part, self.h)
+                self.launches_per_step += 1
+        check(Lb.amqb_lm_head(ptr(self.lm_head), ptr(self.h), ptr(self.final_norm), ctypes.c_float(S.rms_eps),
+                              ptr(self.logits), self.B, S.vocab, self.H, st), "lm_head")
+        check(Lb.amqb_argmax(ptr(self.logits), ptr(self.next_tokens), self.B, S.vocab, st), "argmax")
+        self.launches_per_step += 2
+
+    def capture(self) -> None:
+        """Capture one decode step (+ feeding the argmax back as the next input, + position advance)
+        into a CUDA graph."""
+        lib().amqb_set_pdl(int(self.pdl))
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            saved_pos = self.pos.clone()
+            for _ in range(2):                      # warm-up outside capture (lazy module loads, attributes)
+                self._step_launches()
+            self.pos.copy_(saved_pos)
+            s.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
+                self._step_launches()
+                self.tokens.copy_(self.next_tokens)
+                self.pos.add_(1)
+            self.graph = g
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        self.pos.copy_(saved_pos)
+
+    def step(self) -> None:
+        """One token for every sequence of the batch: replay the captured graph."""
+        if self.graph is None:
+            self.capture()
+        self.graph.replay()
+
+    def step_eager(self) -> None:
+        lib().amqb_set_pdl(0)
+        saved = self.pdl
+        self.pdl = False
+        self._step_launches()
+        self.pdl = saved
+        self.tokens.copy_(self.next_tokens)
+        self.pos.add_(1)
+
+    def reset(self) -> None:
+        self.pos.zero_()
+
+    @torch.inference_mode()
+    def generate(self, input_ids: torch.Tensor, max_new_tokens: int, use_graph: bool = True) -> torch.Tensor:
+        """Greedy generation like model.generate(do_sample=False, min=max_new_tokens) in the reference's
+        benchmark_tps (speed.py:23-46).  input_ids: [B, prompt] (host or device).  The prompt is consumed
+        token by token through the decode path (prefill through the tensor-core GEMM: amq_b200.prefill)."""
+        assert input_ids.shape[0] == self.B
+        prompt = input_ids.shape[1]
+        assert prompt + max_new_tokens <= self.max_seq
+        ids = input_ids.to(self.dev, non_blocking=True)
+        self.reset()
+        fn = self.step if use_graph else self.step_eager
+        if use_graph and self.graph is None:
+            self.capture()
+        out = torch.empty(self.B, max_new_tokens, dtype=torch.int64, device=self.dev)
+        for t in range(prompt):
+            self.tokens.copy_(ids[:, t])
+            fn()
+        out[:, 0] = self.tokens
+        for t in range(1, max_new_tokens):
+            fn()
+            out[:, t] = self.tokens
+        return out
+
+    # ---------------------------------------------------------------- accounting
+    def algorithmic_bytes_per_token(self) -> Dict[str, int]:
+        lin = 0
+        for L in self.layers:
+            for name in LINEARS:
+                bits, _, N, K = L[name]
+                lin += N * K * bits // 8 + (K // GROUP) * N * 4
+        head = 2 * self.shape.vocab * self.H
+        return {"linears": lin, "lm_head": head, "total": lin + head}

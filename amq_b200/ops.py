@@ -22,13 +22,16 @@ def native_bytes(bits: int, N: int, K: int) -> int:
     return int(lib().amqb_native_bytes(bits, N, K))
 
 
-def workspace(device: torch.device, max_N: int = 1 << 17, max_K: int = 1 << 15, max_M: int = 16) -> torch.Tensor:
-    """Zero-filled split-K workspace, one per (device, stream).  The decode kernels leave the
-    arrival counters zeroed, so it is allocated and cleared exactly once."""
+def workspace(device: torch.device, sum_N: int = 32768, max_K: int = 16384, max_M: int = 1) -> torch.Tensor:
+    """Zero-filled split-K workspace, one per (device, stream), grown on demand (never while a CUDA
+    graph is being captured: size it first with the largest launch).  The decode kernels leave the
+    arrival counters zeroed, so it is cleared exactly once per allocation."""
     dev = device.index if device.index is not None else torch.cuda.current_device()
     key = (dev, torch.cuda.current_stream(dev).cuda_stream)
     ws = _workspaces.get(key)
-    need = int(lib().amqb_workspace_bytes(max_N, max_K, max_M))
+    need = int(lib().amqb_workspace_bytes(sum_N, max_K, max_M))
+    if need == 0:
+        raise RuntimeError("amq_b200: workspace request out of range")
     if ws is None or ws.numel() < need:
         ws = torch.zeros(need, dtype=torch.uint8, device=torch.device("cuda", dev))
         _workspaces[key] = ws
@@ -141,7 +144,7 @@ def gemv(bits: int, w_native: torch.Tensor, x: torch.Tensor, N: int, K: int,
     x = x.contiguous()
     M = x.shape[0]
     y = out if out is not None else torch.empty((M, N), dtype=torch.float16, device=x.device)
-    ws = workspace(x.device)
+    ws = workspace(x.device, N, K, M)
     fn = {2: lib().amqb_gemv_w2, 3: lib().amqb_gemv_w3, 4: lib().amqb_gemv_w4}[bits]
     check(fn(ptr(w_native), ptr(x), ptr(y), ptr(bias), M, N, K, ptr(ws), ctypes.c_size_t(ws.numel()), cur_stream()),
           f"gemv_w{bits}")
@@ -233,3 +236,13 @@ def hqq_quantize(W: torch.Tensor, bits: int, G: int = GROUP, round_zero: Optiona
     check(L.amqb_hqq_quantize(bits, ptr(W.half().contiguous()), ptr(codes), ptr(scale), ptr(zero), int(round_zero),
                               N, K, G, ptr(wsb), ctypes.c_size_t(wsb.numel()), ptr(iters), cur_stream()), "hqq_quantize")
     return codes, scale, zero, iters
+
+
+def native_to_dense(bits: int, w_native: torch.Tensor, N: int, K: int) -> torch.Tensor:
+    """fp32 [N, K] weights a native buffer encodes: scale * q - zero*scale (test / debugging aid)."""
+    codes = unpack_codes(w_native, bits, _lib.LAYOUT_NATIVE, N, K, GROUP).float()
+    rec = bits * 512 + 128
+    meta = w_native.reshape(-1, rec)[:, bits * 512:].contiguous().view(torch.float16).reshape(N // 32, K // GROUP, 32, 2)
+    scale = meta[..., 0].permute(0, 2, 1).reshape(N, K // GROUP).float()
+    zs = meta[..., 1].permute(0, 2, 1).reshape(N, K // GROUP).float()
+    return (codes.reshape(N, K // GROUP, GROUP) * scale[..., None] - zs[..., None]).reshape(N, K)

@@ -52,6 +52,8 @@ typedef enum {
 
 const char* amqb_last_error_string(void);
 int amqb_version(void);
+/* debug aid: when buf != NULL the next decode launches write 8 int64 globaltimer stamps per CTA */
+int amqb_debug_set_timeline(void* buf);
 
 /* ---- sizes ------------------------------------------------------------- */
 /* Bytes of the native weight buffer (codes + fp16 scale / zero*scale, interleaved
@@ -149,6 +151,9 @@ int amqb_hqq_quantize(int bits, const void* W_f16, uint8_t* codes, float* scale,
                       int* iters_run_out, void* stream);
 
 /* ---- decode-step glue ----------------------------- */
+/* enable != 0: the glue kernels below launch with programmatic stream serialization too, so a whole
+ * decode step chains kernel to kernel inside one CUDA graph. */
+int amqb_set_pdl(int enable);
 int amqb_embed(const int64_t* token_ids, const void* table_f16, void* out_f16,
                int M, int hidden, void* stream);
 /* RoPE (HF rotate_half convention) on q,k of this step, append k,v to the static cache,

@@ -30,7 +30,7 @@ def bench_case(N, K, bits, M, pool_mb=384, iters=20, pdl=False, simt=False):
     # sane meta: overwrite by packing a real synthetic layer into copy 0.. (values irrelevant for timing)
     x = torch.randn(M, K, device=dev).half()
     y = torch.empty(M, N, device=dev, dtype=torch.float16)
-    ws = ops.workspace(dev)
+    ws = ops.workspace(dev, N, K, M)
     probs = [ops.make_problem(bits, w, x, y, N, K) for w in pool]
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):
