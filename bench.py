@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native AMQ quantized-linear hot path.
+
+Metric (BASELINE.json): batch-1 decode tok/s, Llama-2-7B AMQ mixed 2/3/4-bit (avg 3.0 bits);
+dequant-GEMV achieved HBM GB/s vs peak.  A "step" is one decoded token = one pass of the hot
+path (224 quantized linears + glue + fp16 lm_head) over one batch of synthetic input.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
+
+* value      device-timed tok/s, inputs resident in HBM (CUDA-graph replay, token fed back on device)
+* e2e        the same through the host-facing API: token ids come from pinned host memory each step
+             and the next ids are read back to the host each step (copies inside the timed region)
+* roofline   the decode GEMV family: algorithmic bytes of one step's 224 launches / their CUDA-event
+             time, measured live on the launching stream, against MEASURED_PEAKS.json hbm_gbs
+* cpu_baseline / --impl reference: the oracle port of the reference's torch dequant+matmul
+             (GPTQLinear.forward, kernel_switch_threshold=0) on the host cores, on a bounded sample.
+N > 1: the 7B path does not shard ("replicas only"): every rank decodes its own
+batch-1 stream, no data-path collective, scaling "weak".  `--workload llama70b-tp` runs config 5
+(tensor-parallel 70B) instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        mhz = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(mhz)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+_CPU_CACHE = {}
+
+
+def cpu_reference_sample(arch, shape, threads: int):
+    """The reference's own CPU path on a bounded sample of this workload: ONE q_proj-shaped
+    4096x4096 3-bit group-128 linear, batch 1 (BASELINE.json configs[0]) through the oracle port of
+    GPTQLinear.forward's torch branch (autogptq.py:245-283: shift-unpack -> fp16 scales*q - zeros ->
+    matmul).  The torch path's cost is proportional to N*K whatever the bit width, so a token is
+    extrapolated as t_sample * sum(N*K over the model's quantized linears) / 4096^2 (attention, norms
+    and lm_head not counted, which favours the CPU arm).  Returns (seconds per token, description)."""
+    import numpy as np
+    import torch
+    from oracle import amq_oracle as O
+    torch.set_num_threads(threads)
+    G, N, K, bits = 128, 4096, 4096, 3
+    if "layer" not in _CPU_CACHE:
+        rs = np.random.RandomState(0)
+        qweight = rs.randint(-2 ** 31, 2 ** 31 - 1, size=(K * bits // 32, N), dtype=np.int64).astype(np.int32)
+        scales = torch.from_numpy(rs.uniform(0.01, 0.02, size=(K // G, N)).astype(np.float32)).half().float()
+        zeros = torch.from_numpy(rs.uniform(0.02, 0.1, size=(K // G, N)).astype(np.float32)).half().float()
+        _CPU_CACHE["layer"] = (torch.randn(1, K).half(), qweight, scales, zeros)
+    x, q, sc, z = _CPU_CACHE["layer"]
+    t0 = time.perf_counter()
+    O.gptq_forward_torch(x, q, sc, z, bits, G)
+    dt = time.perf_counter() - t0
+    total_nk = sum(n * k for (n, k) in shape.linear_shape.values()) * shape.n_block
+    return dt * total_nk / (N * K), ("one 4096x4096 3-bit g128 linear, batch 1 (configs[0]), torch dequant+matmul; token time "
+                                    "extrapolated by N*K over the 224 quantized linears")
+
+
+def run_reference(args, shape, arch):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    times = []
+    for i in range(args.warmup + args.steps):
+        t, desc = cpu_reference_sample(arch, shape, threads)
+        if i >= args.warmup:
+            times.append(t)
+    tok_time = sum(times) / len(times)
+    tok_s = 1.0 / tok_time
+    line = {
+        "impl": "reference", "metric": "batch-1 decode tok/s, Llama-2 7B AMQ 3-bit avg", "value": tok_s, "unit": "tok/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tok_time * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": f"{shape.name} random-init, AMQ mixed 2/3/4-bit avg 3.0 (synthetic arch, seed 0), batch-1 decode",
+                   "timing": "host wall clock; each step = one 4096x4096 3-bit linear on the CPU, token time extrapolated by N*K"},
+        "cpu_baseline": {"value": tok_s, "unit": "tok/s", "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": tok_s, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def gemv_roofline(model, iters: int = 5):
+    """Time one step's worth of decode-GEMV launches alone (same problems, same order, PDL on, CUDA
+    graph, events on the launching stream).  The 2.4 GB of packed weights exceed L2 (126 MB)."""
+    import torch
+    from amq_b200 import ops
+    s = torch.cuda.Stream(device=model.dev)
+    n_launch = 0
+    with torch.cuda.stream(s):
+        def launches():
+            n = 0
+            for P in model._plan:
+                for key, cnt in (("qkv", 3), ("o", 1), ("gu", 2), ("down", 1)):
+                    model._gemv(P[key], cnt)
+                    n += len({(P[key][i].bits, P[key][i].prologue) for i in range(cnt)})
+            return n
+        n_launch = launches()
+        s.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            launches()
+        g.replay()
+        s.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s)
+        for _ in range(iters):
+            g.replay()
+        e1.record(s)
+        s.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    alg = model.algorithmic_bytes_per_token()["linears"] + 7 * model.n_block * 2 * 2 * model.H   # + x / y traffic (approx.)
+    return ms, n_launch, alg
+
+
+def run_ours(args, shape, arch):
+    import torch
+    import torch.distributed as dist
+    from amq_b200.model import QuantDecoder
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    B = 1
+    model = QuantDecoder(shape, arch, batch=B, max_seq=max(512, args.warmup + 2 * args.steps + 8), device=f"cuda:{local}", seed=rank)
+    model.capture()
+    launches_per_step = model.launches_per_step
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: K graph replays, tokens fed back on the device
+    model.reset()
+    model.tokens.fill_(1)
+    for _ in range(args.warmup):
+        model.step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        model.step()
+    e1.record()
+    barrier()
+    ms_dev = e0.elapsed_time(e1)
+
+    # ---- end to end through the host-facing call: pinned host ids in, ids out, every step
+    host_in = torch.ones(B, dtype=torch.int64).pin_memory()
+    host_out = torch.zeros(B, dtype=torch.int64).pin_memory()
+    for _ in range(max(3, args.warmup // 2)):
+        model.tokens.copy_(host_in, non_blocking=True)
+        model.step()
+        host_out.copy_(model.tokens, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        model.tokens.copy_(host_in, non_blocking=True)      # H2D: this step's input ids
+        model.step()
+        host_out.copy_(model.tokens, non_blocking=True)     # D2H: this step's result
+        torch.cuda.current_stream().synchronize()
+        host_in.copy_(host_out)                             # the host owns the loop
+    e3.record()
+    barrier()
+    ms_e2e = max(e2.elapsed_time(e3), (time.perf_counter() - t0) * 1e3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if world > 1:
+        t = torch.tensor([ms_dev, ms_e2e], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        g_ms, g_launch, g_bytes = gemv_roofline(model)
+        achieved = g_bytes / (g_ms * 1e-3) / 1e9
+        bytes_tok = model.algorithmic_bytes_per_token()
+        cpu_runs = [cpu_reference_sample(arch, shape, os.cpu_count() or 1) for _ in range(12)]
+        cpu_desc = cpu_runs[0][1]
+        cpu_tok_s = 1.0 / (sum(r[0] for r in cpu_runs[2:]) / len(cpu_runs[2:]))
+        tok_s = world * B * args.steps / (ms_dev * 1e-3)
+        line = {
+            "metric": "batch-1 decode tok/s, Llama-2 7B AMQ 3-bit avg", "value": tok_s, "unit": "tok/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 (fp32 accumulate)",
+            "data": "synthetic",
+            "config": {"workload": f"{shape.name} random-init, AMQ mixed 2/3/4-bit avg "
+                                   f"{sum(sum(v) for v in arch.values()) / sum(len(v) for v in arch.values()):.2f} code bits "
+                                   "(synthetic arch, seed 0; 3.0 incl. 0.25 b scale/zero), batch-1 decode, group 128",
+                       "l2": "inputs larger than L2: every step streams %.2f GB of packed weights + fp16 lm_head" % (bytes_tok["total"] / 1e9),
+                       "parallelism": "replicas only (no data-path collective)" if world > 1 else "single GPU",
+                       "launches_per_step": launches_per_step, "cuda_graph": True, "pdl": model.pdl},
+            "clocks": clocks,
+            "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "tok/s",
+                    "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 8 * B},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "kernel": "gemv_mma_kernel<bits,..> (decode GEMV family, %d launches per step)" % g_launch,
+                         "algorithmic_bytes_per_step": g_bytes, "avg_launch_us": g_ms * 1e3 / g_launch,
+                         "step_frac_of_weight_roofline": (bytes_tok["total"] / (peak * 1e9)) / (ms_dev / args.steps * 1e-3)},
+            "cpu_baseline": {"value": cpu_tok_s, "unit": "tok/s", "cores": os.cpu_count(), "kind": "port", "sample": cpu_desc},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=128)
+    ap.add_argument("--warmup", type=int, default=16)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="llama7b", choices=["llama7b", "llama70b-tp"])
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    from amq_b200.arch import MODELS, sample_arch
+    if args.workload == "llama70b-tp":
+        from amq_b200 import tp
+        return tp.bench_main(args)
+    shape = MODELS["Llama-2-7b-hf"]
+    arch = sample_arch(shape, 3.0, seed=0)
+    if args.impl == "reference":
+        return run_reference(args, shape, arch)
+    return run_ours(args, shape, arch)
+
+
+if __name__ == "__main__":
+    main()
