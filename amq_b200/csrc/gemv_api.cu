@@ -19,15 +19,15 @@ static int sm_count() {
   return g_sm_count;
 }
 
-// One launch: problems sharing M, bit width and prologue kind.
+// One launch: problems sharing M and prologue kind (bit widths may differ).
 static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, cudaStream_t st) {
   GemvLaunch L{};
-  const int M = pr[0]->M, bits = pr[0]->bits, pro = pr[0]->prologue;
+  const int M = pr[0]->M, pro = pr[0]->prologue;
   const int NB = M <= 8 ? 1 : 2;
   L.count = count;
   L.M = M;
   L.dbg = g_dbg;
-  int max_rb = 0, min_g = 1 << 30;
+  int max_rb = 0, min_g = 1 << 30, max_rec = 0;
   const int B = sm_count();
   for (int i = 0; i < count; ++i) {
     const amqb_gemv_problem& q = *pr[i];
@@ -38,6 +38,7 @@ static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, 
     P.n_rb = q.N / 32; P.n_g = q.K / kGroup;
     if (P.n_rb > max_rb) max_rb = P.n_rb;
     if (P.n_g < min_g) min_g = P.n_g;
+    if (rec_bytes(q.bits) > max_rec) max_rec = rec_bytes(q.bits);
   }
   // K split across a cluster only when N is too small to occupy the chip (each cluster then owns at
   // most one row block per problem, which is what the DSMEM hand-off assumes)
@@ -48,17 +49,18 @@ static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, 
   if (ncl > max_rb) ncl = max_rb;
   if (ncl < 1) ncl = 1;
   // x' chunking along K when M * K is too large for shared memory
-  const int per_group = mmas_per_group(bits) * M * 32;
-  int max_kc = 0, acc_blocks = 0, max_slice = 0;
+  int max_xp = 0, max_kc = 0, acc_blocks = 0, max_slice = 0;
   for (int i = 0; i < count; ++i) {
     DevProblem& P = L.prob[i];
     const int slice = (P.n_g + S - 1) / S;
+    const int per_group = mmas_per_group(P.bits) * M * 32;
     int kc = kXprimeBudget / per_group;
     if (kc >= slice) kc = slice;
     else kc = (kc / kStageRecs) * kStageRecs;       // whole pipeline stages per chunk
     if (kc < 1) return fail(AMQB_ERR_UNSUPPORTED_SHAPE, "gemv: x' chunk does not fit shared memory");
     P.kc = kc;
     if (kc > max_kc) max_kc = kc;
+    if (kc * per_group > max_xp) max_xp = kc * per_group;
     if (slice > max_slice) max_slice = slice;
     if (kc < slice) {
       const int blocks = (P.n_rb + ncl - 1) / ncl;
@@ -70,12 +72,15 @@ static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, 
     const char* e = getenv("AMQB_COPY_RECS");
     L.copy_recs = e ? atoi(e) : 4;
     if (L.copy_recs < 1) L.copy_recs = 1;
+    const char* d = getenv("AMQB_DBG_DELAY_NS");
+    L.dbg_delay_ns = d ? atoi(d) : 0;
   }
   const int stage_recs = max_slice < kStageRecs ? max_slice : kStageRecs;
-  L.stage_bytes = stage_recs * rec_bytes(bits);
-  L.xprime_bytes = (max_kc * per_group + 127) & ~127;
+  L.stage_bytes = stage_recs * max_rec;
+  L.xprime_bytes = (max_xp + 127) & ~127;
+  L.xp_variants = (count > 1 && 3 * L.xprime_bytes <= 96 * 1024) ? 3 : 1;
   L.xs_floats = (max_kc * NB * 8 + 31) & ~31;
-  const size_t fixed = 256 + (size_t)L.xs_floats * 4 + 16 * kCW * 4 + L.xprime_bytes +
+  const size_t fixed = 256 + (size_t)L.xs_floats * 4 + 16 * kCW * 4 + (size_t)L.xp_variants * L.xprime_bytes +
                        (size_t)2 * kCW * 2 * NB * 128 * 4 + (size_t)acc_blocks * 2 * NB * 128 * 4 +
                        (S > 1 ? (size_t)count * S * 2 * NB * 128 * 4 : 0) + 128;
   if (fixed + 2 * (size_t)L.stage_bytes > (size_t)kSmemTarget)
@@ -85,9 +90,9 @@ static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, 
   L.n_stages = ns;
   const size_t smem = fixed + (size_t)ns * L.stage_bytes;
   const int grid = ncl * S;
-  if (bits == 2) return launch_w2(L, pro, grid, smem, pdl, st);
-  if (bits == 3) return launch_w3(L, pro, grid, smem, pdl, st);
-  return launch_w4(L, pro, grid, smem, pdl, st);
+  if (pro == AMQB_PRO_NONE) return launch_pro0(L, grid, smem, pdl, st);
+  if (pro == AMQB_PRO_RMSNORM) return launch_pro1(L, grid, smem, pdl, st);
+  return launch_pro2(L, grid, smem, pdl, st);
 }
 
 }  // namespace amqb
@@ -128,14 +133,14 @@ int amqb_gemv_grouped(const amqb_gemv_problem* pr, int count, void* workspace, s
     if (q.prologue < AMQB_PRO_NONE || q.prologue > AMQB_PRO_SILU_MUL) return fail(AMQB_ERR_BAD_ARG, "gemv: bad prologue");
     if (q.prologue == AMQB_PRO_RMSNORM && !q.gamma) return fail(AMQB_ERR_BAD_ARG, "gemv: rmsnorm prologue needs gamma");
   }
-  // one launch per (bit width, prologue) class present in the group, in first-appearance order
+  // one launch per prologue kind present in the group (normally one), in first-appearance order
   bool done[kMaxProblems] = {false, false, false, false};
   for (int i = 0; i < count; ++i) {
     if (done[i]) continue;
     const amqb_gemv_problem* sub[kMaxProblems];
     int n = 0;
     for (int j = i; j < count; ++j)
-      if (!done[j] && pr[j].bits == pr[i].bits && pr[j].prologue == pr[i].prologue) { sub[n++] = &pr[j]; done[j] = true; }
+      if (!done[j] && pr[j].prologue == pr[i].prologue) { sub[n++] = &pr[j]; done[j] = true; }
     const int rc = launch_group(sub, n, pdl, (cudaStream_t)stream);
     if (rc) return rc;
   }

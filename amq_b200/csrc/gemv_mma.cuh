@@ -65,6 +65,8 @@ struct GemvLaunch {
   int xs_floats;         // floats in the xsum region
   int accbuf_blocks;     // row blocks per CTA that need a smem accumulator (chunked K), else 0
   int copy_recs;         // records per cp.async.bulk (a stage is issued as several bulk copies)
+  int dbg_delay_ns;      // debug: consumers idle this long after building x' (0 in production)
+  int xp_variants;       // 3: x' kept per bit width so problems sharing x reuse it; 1: rebuilt per problem
   long long* dbg;        // optional per-CTA timeline (8 x int64 per CTA), NULL in production
 };
 
@@ -153,50 +155,73 @@ __device__ __forceinline__ void finish_item(uint2 a, uint2 b, float rs, __half2&
   }
 }
 
-// groups [g_lo, g_lo + len) of problem P -> xp / xs
-template <int BITS, bool M1, int PRO>
-__device__ __forceinline__ void build_xprime(const DevProblem& P, int M, int NB, int g_lo, int len, uint8_t* xp, float* xs,
-                                          float* sred, int cw, int lane) {
-  constexpr int pro = PRO;
-  constexpr int NM = mmas_per_group(BITS);
-  if (pro == AMQB_PRO_RMSNORM) {   // per-column sum of squares over the FULL row (all K, not only this slice)
-    for (int col = 0; col < M; ++col) {
+// x' of groups [g_lo, g_lo + len) of problem P.  Warp cw builds exactly the groups it will consume
+// (local index gl with gl % kCW == cw: record i of every pipeline stage goes to warp i), so no
+// CTA-wide barrier is needed; only the RMSNorm statistic crosses warps.
+template <bool M1, int PRO>
+__device__ __forceinline__ void build_xprime(const DevProblem& P, int M, int NB, int S, int g_lo, int len, uint8_t* xp,
+                                             float* xs, float* sred, int cw, int lane, bool have_stats, float& rs1) {
+  const int bits = P.bits;
+  const int NM = mmas_per_group(bits);
+  if (PRO == AMQB_PRO_RMSNORM && !have_stats) {
+    if (M1 && S == 1) {
+      // every warp sums the squares of the groups it owns; together the warps cover the whole row
       float ss = 0.f;
-      const uint2* xr = reinterpret_cast<const uint2*>(P.x + (size_t)col * P.ldx);
-      for (int i = cw * 32 + lane; i < P.K / 4; i += kCThreads) {
-        const uint2 v = xr[i];
+      for (int gl = cw; gl < len; gl += kCW) {
+        const uint2 v = *reinterpret_cast<const uint2*>(P.x + (g_lo + gl) * kGroup + 4 * lane);
         const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
         const float2 b2 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
         ss += a.x * a.x + a.y * a.y + b2.x * b2.x + b2.y * b2.y;
       }
 #pragma unroll
       for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-      if (lane == 0) sred[col * kCW + cw] = ss;
+      if (lane == 0) sred[cw] = ss;
+      named_bar_sync(1, kCThreads);
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kCW; ++w) t += sred[w];
+      rs1 = rsqrtf(t / (float)P.K + P.eps);
+    } else {   // general case: per-column sum of squares over the FULL row, all warps cooperate
+      for (int col = 0; col < M; ++col) {
+        float ss = 0.f;
+        const uint2* xr = reinterpret_cast<const uint2*>(P.x + (size_t)col * P.ldx);
+        for (int i = cw * 32 + lane; i < P.K / 4; i += kCThreads) {
+          const uint2 v = xr[i];
+          const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+          const float2 b2 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+          ss += a.x * a.x + a.y * a.y + b2.x * b2.x + b2.y * b2.y;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if (lane == 0) sred[col * kCW + cw] = ss;
+      }
+      named_bar_sync(1, kCThreads);
     }
-    named_bar_sync(1, kCThreads);
   }
-  const int items = len * M;
+  const int my_groups = (len - cw + kCW - 1) / kCW;     // gl = cw, cw + kCW, ...
+  const int items = my_groups > 0 ? my_groups * M : 0;
   constexpr int BATCH = 2;
-  for (int it0 = cw; it0 < items; it0 += kCW * BATCH) {
+  for (int it0 = 0; it0 < items; it0 += BATCH) {
     uint2 a[BATCH], b[BATCH];
 #pragma unroll
     for (int u = 0; u < BATCH; ++u) {
-      const int it = it0 + u * kCW;
+      const int it = it0 + u;
       if (it < items) {
-        const int gl = M1 ? it : it / M, col = M1 ? 0 : it - gl * M;
-        const int kbase = (g_lo + gl) * kGroup + 4 * lane;
+        const int gi = M1 ? it : it / M, col = M1 ? 0 : it - gi * M;
+        const int kbase = (g_lo + cw + gi * kCW) * kGroup + 4 * lane;
         a[u] = *reinterpret_cast<const uint2*>(P.x + (size_t)col * P.ldx + kbase);
-        if (pro == AMQB_PRO_SILU_MUL) b[u] = *reinterpret_cast<const uint2*>(P.x + (size_t)col * P.ldx + P.K + kbase);
-        else if (pro == AMQB_PRO_RMSNORM) b[u] = *reinterpret_cast<const uint2*>(P.gamma + kbase);
+        if (PRO == AMQB_PRO_SILU_MUL) b[u] = *reinterpret_cast<const uint2*>(P.x + (size_t)col * P.ldx + P.K + kbase);
+        else if (PRO == AMQB_PRO_RMSNORM) b[u] = *reinterpret_cast<const uint2*>(P.gamma + kbase);
       }
     }
 #pragma unroll
     for (int u = 0; u < BATCH; ++u) {
-      const int it = it0 + u * kCW;
+      const int it = it0 + u;
       if (it < items) {
-        const int gl = M1 ? it : it / M, col = M1 ? 0 : it - gl * M;
-        float rs = 1.f;
-        if (pro == AMQB_PRO_RMSNORM) {
+        const int gi = M1 ? it : it / M, col = M1 ? 0 : it - gi * M;
+        const int gl = cw + gi * kCW;
+        float rs = rs1;
+        if (PRO == AMQB_PRO_RMSNORM && !(M1 && S == 1)) {
           float ss = 0.f;
 #pragma unroll
           for (int w = 0; w < kCW; ++w) ss += sred[col * kCW + w];
@@ -204,7 +229,10 @@ __device__ __forceinline__ void build_xprime(const DevProblem& P, int M, int NB,
         }
         __half2 lo, hi;
         finish_item<PRO>(a[u], b[u], rs, lo, hi);
-        place_item<BITS>(xp + (size_t)gl * NM * M * 32, M, col, lane, lo, hi);
+        uint8_t* gb = xp + (size_t)gl * NM * M * 32;
+        if (bits == 3) place_item<3>(gb, M, col, lane, lo, hi);
+        else if (bits == 4) place_item<4>(gb, M, col, lane, lo, hi);
+        else place_item<2>(gb, M, col, lane, lo, hi);
         const float2 f0 = __half22float2(lo), f1 = __half22float2(hi);
         float sum = (f0.x + f0.y) + (f1.x + f1.y);
 #pragma unroll
@@ -214,8 +242,9 @@ __device__ __forceinline__ void build_xprime(const DevProblem& P, int M, int NB,
     }
   }
   if (!M1)
-    for (int i = cw * 32 + lane; i < len * NB * 8; i += kCThreads)
-      if ((i % (NB * 8)) >= M) xs[i] = 0.f;     // padded columns read by the epilogue
+    for (int gl = cw; gl < len; gl += kCW)
+      for (int i = M + lane; i < NB * 8; i += 32) xs[gl * NB * 8 + i] = 0.f;   // padded columns read by the epilogue
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -319,7 +348,7 @@ __device__ __forceinline__ void store_out(const DevProblem& P, int n, int col, f
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int BITS, int NB, bool M1, int PRO>
+template <int NB, bool M1, int PRO>
 __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_constant__ GemvLaunch L) {
   extern __shared__ __align__(1024) uint8_t smem[];
   // smem map: [0,256) barriers | xs | sred | x' | red[2] | accbuf | part[4][S] | ring
@@ -327,7 +356,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
   float* xs = reinterpret_cast<float*>(smem + 256);
   float* sred = xs + L.xs_floats;                           // 16 * kCW floats
   uint8_t* xp = reinterpret_cast<uint8_t*>(sred + 16 * kCW);
-  float* red = reinterpret_cast<float*>(xp + L.xprime_bytes);          // [2][kCW][2*NB*128]
+  float* red = reinterpret_cast<float*>(xp + (size_t)L.xp_variants * L.xprime_bytes);   // [2][kCW][2*NB*128]
   float* accbuf = red + 2 * kCW * 2 * NB * 128;                        // [accbuf_blocks][2*NB*128]
   float* part = accbuf + (size_t)L.accbuf_blocks * 2 * NB * 128;       // [count][S][2*NB*128] (S > 1)
   uint8_t* ring = reinterpret_cast<uint8_t*>(part + (L.S > 1 ? L.count * L.S * 2 * NB * 128 : 0));
@@ -347,6 +376,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
       mbar_init(smem_u32(&bars[NS + s]), kCW);     // empty: one arrive per consumer warp
     }
     for (int p = 0; p < kMaxProblems; ++p) mbar_init(smem_u32(&bars[24 + p]), S > 1 ? S - 1 : 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bars[28 + i]), kCW);   // red_full[buf]: every consumer warp deposited its partial sums
+      mbar_init(smem_u32(&bars[30 + i]), 1);     // red_free[buf]: the reducing warp is done with the buffer
+    }
     fence_mbar_init();
   }
   if (S > 1) cluster_sync_all();   // barriers initialised and peers' shared memory live before any DSMEM traffic
@@ -361,7 +394,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
       bool wrapped = false;
       for (int p = 0; p < L.count; ++p) {
         const DevProblem& P = L.prob[p];
-        constexpr uint32_t rbytes = rec_bytes(BITS);
+        const uint32_t rbytes = rec_bytes(P.bits);
         const int g_lo = (P.n_g * rank) / S, g_hi = (P.n_g * (rank + 1)) / S;
         for (int c_lo = g_lo; c_lo < g_hi; c_lo += P.kc) {
           const int c_hi = (c_lo + P.kc) < g_hi ? (c_lo + P.kc) : g_hi;
@@ -392,28 +425,26 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
   AMQB_STAMP(1);
   float acc[2][NB][4];
   int s = 0, ph = 0, nblk = 0;
-  const int e = tid;                                   // one output element per thread in the reductions
-  const bool live = e < 2 * NB * 128;
-  int row, col;
-  {
-    const int ci = e & 3, ln = (e >> 2) & 31, tn = e >> 7;   // tn = tile*NB + nb
-    const int tile = tn / NB, nb = tn - tile * NB;
-    row = tile * 16 + (ln >> 2) + 8 * (ci >> 1);
-    col = nb * 8 + 2 * (ln & 3) + (ci & 1);
-  }
+  const __half* cur_x = nullptr;     // x' cache: problems of a group that share x (q/k/v, gate/up)
+  int cur_K = 0, built_mask = 0;
+  float rs1 = 1.f;
   for (int p = 0; p < L.count; ++p) {
     const DevProblem& P = L.prob[p];
     if (cid >= P.n_rb) continue;
-    constexpr uint32_t rbytes = rec_bytes(BITS);
-    constexpr int NM = mmas_per_group(BITS);
+    const uint32_t rbytes = rec_bytes(P.bits);
+    const int NM = mmas_per_group(P.bits);
     const int g_lo = (P.n_g * rank) / S, g_hi = (P.n_g * (rank + 1)) / S;
     const bool chunked = (g_hi - g_lo) > P.kc;
+    const bool same_x = (P.x == cur_x) && (P.K == cur_K);
+    if (!same_x) { built_mask = 0; cur_x = P.x; cur_K = P.K; }
+    uint8_t* xpv = xp + (L.xp_variants == 3 ? (size_t)(P.bits - 2) * L.xprime_bytes : 0);
     for (int c_lo = g_lo; c_lo < g_hi; c_lo += P.kc) {
       const int c_hi = (c_lo + P.kc) < g_hi ? (c_lo + P.kc) : g_hi;
       const bool first_chunk = c_lo == g_lo, last_chunk = c_hi == g_hi;
-      named_bar_sync(1, kCThreads);          // previous chunk / problem done with x'
-      build_xprime<BITS, M1, PRO>(P, M, NB, c_lo, c_hi - c_lo, xp, xs, sred, warp, lane);
-      named_bar_sync(1, kCThreads);
+      if (chunked || L.xp_variants != 3 || !(built_mask & (1 << P.bits)))
+        build_xprime<M1, PRO>(P, M, NB, S, c_lo, c_hi - c_lo, xpv, xs, sred, warp, lane, same_x && built_mask != 0, rs1);
+      built_mask |= 1 << P.bits;
+      if (L.dbg_delay_ns) { const long long t_end = gtime() + L.dbg_delay_ns; while (gtime() < t_end) {} }
       AMQB_STAMP(2);
       int j = 0;
       for (int rb = cid; rb < P.n_rb; rb += ncl, ++nblk, ++j) {
@@ -429,54 +460,101 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
           if (warp < nrec) {
             const uint8_t* rec = ring + (size_t)s * L.stage_bytes + (size_t)warp * rbytes;
             const int gl = g - c_lo + warp;
-            const uint8_t* xpg = xp + (size_t)gl * NM * M * 32;
+            const uint8_t* xpg = xpv + (size_t)gl * NM * M * 32;
             const float* xsg = xs + gl * NB * 8;
-            process_record<BITS, NB, M1>(rec, xpg, xsg, M, lane, acc);
+            if (P.bits == 3) process_record<3, NB, M1>(rec, xpg, xsg, M, lane, acc);
+            else if (P.bits == 4) process_record<4, NB, M1>(rec, xpg, xsg, M, lane, acc);
+            else process_record<2, NB, M1>(rec, xpg, xsg, M, lane, acc);
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bars[NS + s]));
           if (++s == NS) { s = 0; ph ^= 1; }
         }
         AMQB_STAMP(3);
-        // ---- (chunk of a) row block done: cross-warp reduction through double-buffered shared memory
-        const int buf = nblk & 1;
-        float4* myred = reinterpret_cast<float4*>(red) + (size_t)(buf * kCW + warp) * 2 * NB * 32;
+        // ---- (chunk of a) row block done.  Every warp deposits its partial sums in a double-buffered
+        // shared-memory area and moves straight on; ONE warp (rotating) waits for all deposits, sums
+        // them in fixed order and stores / hands off.  mbarriers only: no CTA-wide barrier on this path.
+        const int buf = nblk & 1, use = nblk >> 1;
+        if (use > 0) mbar_wait(smem_u32(&bars[30 + buf]), (use - 1) & 1);       // red[buf] free again
+        float* myred = red + (size_t)(buf * kCW + warp) * 2 * NB * 128;
+        if (M1) {
+          if ((lane & 3) == 0) {
 #pragma unroll
-        for (int a = 0; a < 2; ++a)
-#pragma unroll
-          for (int nb = 0; nb < NB; ++nb)
-            myred[(a * NB + nb) * 32 + lane] = make_float4(acc[a][nb][0], acc[a][nb][1], acc[a][nb][2], acc[a][nb][3]);
-        named_bar_sync(1, kCThreads);
-        float v = 0.f;
-        if (live) {
-          const float* rsrc = red + (size_t)buf * kCW * 2 * NB * 128 + e;
-#pragma unroll
-          for (int w = 0; w < kCW; ++w) v += rsrc[w * 2 * NB * 128];
-          v *= 16777216.f;                                   // undo the 2^-24 of the subnormal code encoding
-          if (chunked) {
-            float* ab = accbuf + (size_t)j * 2 * NB * 128 + e;
-            if (!first_chunk) v += *ab;
-            if (!last_chunk) *ab = v;
+            for (int a = 0; a < 2; ++a) { myred[a * 16 + (lane >> 2)] = acc[a][0][0]; myred[a * 16 + (lane >> 2) + 8] = acc[a][0][2]; }
           }
-        }
-        if (!last_chunk) continue;
-        if (S == 1) {
-          if (live && col < M) store_out(P, rb * 32 + row, col, v);
         } else {
-          // K was split across the cluster: partial sums meet in rank 0's shared memory (DSMEM)
-          float* pslot = part + (size_t)(p * S + rank) * 2 * NB * 128 + e;
-          if (rank != 0) {
-            if (live) st_dsmem_f32(smem_u32(pslot), 0, v);
-            named_bar_sync(1, kCThreads);
-            if (tid == 0) mbar_arrive_remote(smem_u32(&bars[24 + p]), 0);
-          } else {
-            mbar_wait_cluster(smem_u32(&bars[24 + p]), 0);
-            if (live && col < M) {
-              float t = v;
-              for (int r = 1; r < S; ++r) t += part[(size_t)(p * S + r) * 2 * NB * 128 + e];
-              store_out(P, rb * 32 + row, col, t);
+#pragma unroll
+          for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb)
+              reinterpret_cast<float4*>(myred)[(a * NB + nb) * 32 + lane] =
+                  make_float4(acc[a][nb][0], acc[a][nb][1], acc[a][nb][2], acc[a][nb][3]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars[28 + buf]));
+        const int reducer = chunked ? 0 : (nblk % kCW);
+        if (warp == reducer) {
+          mbar_wait(smem_u32(&bars[28 + buf]), use & 1);
+          const float* rbase = red + (size_t)buf * kCW * 2 * NB * 128;
+          constexpr int EPT = M1 ? 1 : 8 * NB;                 // output elements per lane
+#pragma unroll
+          for (int q = 0; q < EPT; ++q) {
+            const int e = M1 ? lane : q * 32 + lane;
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < kCW; ++w) v += rbase[w * 2 * NB * 128 + e];
+            v *= 16777216.f;                                   // undo the 2^-24 of the subnormal code encoding
+            int row, col;
+            if (M1) { row = e; col = 0; }
+            else {
+              const int ci = e & 3, ln = (e >> 2) & 31, tn = e >> 7;   // tn = tile*NB + nb
+              const int tile = tn / NB, nb = tn - tile * NB;
+              row = tile * 16 + (ln >> 2) + 8 * (ci >> 1);
+              col = nb * 8 + 2 * (ln & 3) + (ci & 1);
+            }
+            if (chunked) {
+              float* ab = accbuf + (size_t)j * 2 * NB * 128 + e;
+              if (!first_chunk) v += *ab;
+              if (!last_chunk) *ab = v;
+            }
+            if (last_chunk) {
+              if (S == 1) {
+                if (col < M) store_out(P, rb * 32 + row, col, v);
+              } else {
+                // K was split across the cluster: partial sums meet in rank 0's shared memory (DSMEM)
+                float* pslot = part + (size_t)(p * S + rank) * 2 * NB * 128 + e;
+                if (rank != 0) st_dsmem_f32(smem_u32(pslot), 0, v);
+                else *pslot = v;
+              }
             }
           }
+          if (last_chunk && S > 1) {
+            __syncwarp();
+            if (rank != 0) {
+              if (lane == 0) mbar_arrive_remote(smem_u32(&bars[24 + p]), 0);
+            } else {
+              mbar_wait_cluster(smem_u32(&bars[24 + p]), 0);
+#pragma unroll
+              for (int q = 0; q < EPT; ++q) {
+                const int e = M1 ? lane : q * 32 + lane;
+                int row, col;
+                if (M1) { row = e; col = 0; }
+                else {
+                  const int ci = e & 3, ln = (e >> 2) & 31, tn = e >> 7;
+                  const int tile = tn / NB, nb = tn - tile * NB;
+                  row = tile * 16 + (ln >> 2) + 8 * (ci >> 1);
+                  col = nb * 8 + 2 * (ln & 3) + (ci & 1);
+                }
+                if (col < M) {
+                  float t = 0.f;
+                  for (int r = 0; r < S; ++r) t += part[(size_t)(p * S + r) * 2 * NB * 128 + e];
+                  store_out(P, rb * 32 + row, col, t);
+                }
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars[30 + buf]));
         }
         AMQB_STAMP(4);
       }
@@ -486,9 +564,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
 }
 
 
-template <int BITS, int NB, bool M1, int PRO>
+template <int NB, bool M1, int PRO>
 static int launch_variant(const GemvLaunch& L, int grid, size_t smem, int pdl, cudaStream_t st) {
-  auto kern = gemv_mma_kernel<BITS, NB, M1, PRO>;
+  auto kern = gemv_mma_kernel<NB, M1, PRO>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
@@ -523,24 +601,16 @@ static int launch_variant(const GemvLaunch& L, int grid, size_t smem, int pdl, c
   return AMQB_OK;
 }
 
-// one translation unit per bit width instantiates this (gemv_w2.cu / gemv_w3.cu / gemv_w4.cu)
-template <int BITS>
-static int launch_bits(const GemvLaunch& L, int pro, int grid, size_t smem, int pdl, cudaStream_t st) {
-  const int M = L.M;
-#define AMQB_PRO_SWITCH(NB_, M1_)                                                              \
-  switch (pro) {                                                                               \
-    case AMQB_PRO_NONE: return launch_variant<BITS, NB_, M1_, AMQB_PRO_NONE>(L, grid, smem, pdl, st);       \
-    case AMQB_PRO_RMSNORM: return launch_variant<BITS, NB_, M1_, AMQB_PRO_RMSNORM>(L, grid, smem, pdl, st); \
-    default: return launch_variant<BITS, NB_, M1_, AMQB_PRO_SILU_MUL>(L, grid, smem, pdl, st);              \
-  }
-  if (M == 1) { AMQB_PRO_SWITCH(1, true) }
-  if (M <= 8) { AMQB_PRO_SWITCH(1, false) }
-  AMQB_PRO_SWITCH(2, false)
-#undef AMQB_PRO_SWITCH
+// one translation unit per prologue kind instantiates this (gemv_pro0.cu / gemv_pro1.cu / gemv_pro2.cu)
+template <int PRO>
+static int launch_pro(const GemvLaunch& L, int grid, size_t smem, int pdl, cudaStream_t st) {
+  if (L.M == 1) return launch_variant<1, true, PRO>(L, grid, smem, pdl, st);
+  if (L.M <= 8) return launch_variant<1, false, PRO>(L, grid, smem, pdl, st);
+  return launch_variant<2, false, PRO>(L, grid, smem, pdl, st);
 }
 
-int launch_w2(const GemvLaunch& L, int pro, int grid, size_t smem, int pdl, cudaStream_t st);
-int launch_w3(const GemvLaunch& L, int pro, int grid, size_t smem, int pdl, cudaStream_t st);
-int launch_w4(const GemvLaunch& L, int pro, int grid, size_t smem, int pdl, cudaStream_t st);
+int launch_pro0(const GemvLaunch& L, int grid, size_t smem, int pdl, cudaStream_t st);
+int launch_pro1(const GemvLaunch& L, int grid, size_t smem, int pdl, cudaStream_t st);
+int launch_pro2(const GemvLaunch& L, int grid, size_t smem, int pdl, cudaStream_t st);
 
 }  // namespace amqb

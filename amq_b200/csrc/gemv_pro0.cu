@@ -1,0 +1,8 @@
+// Decode GEMV kernels with prologue kind AMQB_PRO_NONE (see gemv_mma.cuh).
+#include "gemv_mma.cuh"
+
+namespace amqb {
+int launch_pro0(const GemvLaunch& L, int grid, size_t smem, int pdl, cudaStream_t st) {
+  return launch_pro<AMQB_PRO_NONE>(L, grid, smem, pdl, st);
+}
+}  // namespace amqb

@@ -1,0 +1,8 @@
+// Decode GEMV kernels with prologue kind AMQB_PRO_SILU_MUL (see gemv_mma.cuh).
+#include "gemv_mma.cuh"
+
+namespace amqb {
+int launch_pro2(const GemvLaunch& L, int grid, size_t smem, int pdl, cudaStream_t st) {
+  return launch_pro<AMQB_PRO_SILU_MUL>(L, grid, smem, pdl, st);
+}
+}  // namespace amqb

@@ -99,30 +99,57 @@ attn_decode_kernel(const __half* __restrict__ qkv, __half* __restrict__ kc, __ha
   float mx = -INFINITY, den = 0.f, acc[EPL];
 #pragma unroll
   for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
-  for (int j = warp; j <= pos; j += 4) {
-    float kj[EPL], vj[EPL];
-    if (j == pos) {
+  // positions j = warp, warp+4, ... ; four at a time so the loads and the butterfly reductions of
+  // independent positions overlap (the loop is latency-bound, not bandwidth-bound)
+  constexpr int UNR = 4;
+  for (int j0 = warp; j0 <= pos; j0 += 4 * UNR) {
+    float kj[UNR][EPL], vj[UNR][EPL], sc[UNR];
 #pragma unroll
-      for (int e = 0; e < EPL; ++e) { kj[e] = kn[e]; vj[e] = vn[e]; }
-    } else {
+    for (int u = 0; u < UNR; ++u) {
+      const int j = j0 + 4 * u;
+      if (j < pos) {
+        if (EPL == 4) {
+          const uint2 kk = *reinterpret_cast<const uint2*>(kcb + (size_t)j * D + 4 * lane);
+          const uint2 vv = *reinterpret_cast<const uint2*>(vcb + (size_t)j * D + 4 * lane);
+          const float2 k0 = __half22float2(*reinterpret_cast<const __half2*>(&kk.x)), k1 = __half22float2(*reinterpret_cast<const __half2*>(&kk.y));
+          const float2 v0 = __half22float2(*reinterpret_cast<const __half2*>(&vv.x)), v1 = __half22float2(*reinterpret_cast<const __half2*>(&vv.y));
+          kj[u][0] = k0.x; kj[u][1] = k0.y; kj[u][EPL - 2] = k1.x; kj[u][EPL - 1] = k1.y;
+          vj[u][0] = v0.x; vj[u][1] = v0.y; vj[u][EPL - 2] = v1.x; vj[u][EPL - 1] = v1.y;
+        } else {
 #pragma unroll
-      for (int e = 0; e < EPL; ++e) {
-        kj[e] = __half2float(kcb[(size_t)j * D + EPL * lane + e]);
-        vj[e] = __half2float(vcb[(size_t)j * D + EPL * lane + e]);
+          for (int e = 0; e < EPL; ++e) {
+            kj[u][e] = __half2float(kcb[(size_t)j * D + EPL * lane + e]);
+            vj[u][e] = __half2float(vcb[(size_t)j * D + EPL * lane + e]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) { kj[u][e] = kn[e]; vj[u][e] = vn[e]; }   // j == pos: this step's k / v
       }
     }
-    float s = 0.f;
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) s += q[e] * kj[e];
+    for (int u = 0; u < UNR; ++u) {
+      float s = 0.f;
 #pragma unroll
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    s *= scale;
-    const float nm = fmaxf(mx, s);
-    const float corr = __expf(mx - nm), p = __expf(s - nm);
-    den = den * corr + p;
+      for (int e = 0; e < EPL; ++e) s += q[e] * kj[u][e];
+      sc[u] = s;
+    }
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) acc[e] = acc[e] * corr + p * vj[e];
-    mx = nm;
+    for (int o = 16; o; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], o);
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (j0 + 4 * u <= pos) {
+        const float s = sc[u] * scale;
+        const float nm = fmaxf(mx, s);
+        const float corr = __expf(mx - nm), p = __expf(s - nm);
+        den = den * corr + p;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) acc[e] = acc[e] * corr + p * vj[u][e];
+        mx = nm;
+      }
+    }
   }
   __shared__ float s_m[4], s_d[4], s_acc[4][D];
   if (lane == 0) { s_m[warp] = mx; s_d[warp] = den; }

@@ -166,7 +166,7 @@ class QuantDecoder:
     def _gemv(self, arr, n) -> None:
         check(lib().amqb_gemv_grouped(arr, n, ptr(self.ws), ctypes.c_size_t(self.ws.numel()), int(self.pdl), cur_stream()),
               "gemv_grouped")
-        self.launches_per_step += len({(arr[i].bits, arr[i].prologue) for i in range(n)})
+        self.launches_per_step += len({arr[i].prologue for i in range(n)})
 
     def _step_launches(self) -> None:
         Lb = lib()
