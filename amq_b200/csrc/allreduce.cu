@@ -1,0 +1,165 @@
+// One-shot all-reduce over NVLink peer memory for tensor-parallel decode (config 5): after each
+// row-parallel linear (o_proj, down_proj) the [M, hidden] fp16 partial sums of all ranks are summed
+// and added to the residual stream.  The reference has no collective on this path; the
+// message is 16 KB at batch 1, so latency decides: every rank PUSHES its partial vector straight into
+// every peer's exchange buffer with plain stores through the NVLink-mapped pointer, raises a flag
+// there, waits for the peers' flags in its own buffer and reduces locally in fixed rank order
+// (bit-identical on every rank, no atomics).  ncclAllReduce is the baseline it is measured against.
+//
+// Exchange buffer (per rank, cudaMalloc'ed by amqb_ar_alloc, zero-filled):
+//   [0,128)                       uint32 epoch counter (local; advances once per all-reduce, so a
+//                                 captured CUDA graph needs no per-launch argument)
+//   [128, 128 + 128*world)        flags[src] (one 128-byte line each), written by rank src
+//   then  data[parity][src][max_elems] fp16, parity = epoch & 1 (a rank can only be one all-reduce
+//   ahead of a peer, so two generations of slots suffice)
+#include <string.h>
+
+#include "common.cuh"
+
+namespace amqb {
+
+constexpr int kArHeader = 128;
+constexpr int kArMaxWorld = 16;
+
+struct ArArgs {
+  uint8_t* peer[kArMaxWorld];
+  int rank, world, n_elems, max_elems;
+  const __half* partial;
+  const __half* residual;
+  __half* out;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(1024) allreduce_push_kernel(const ArArgs A) {
+  __shared__ uint32_t s_epoch;
+  pdl_launch_dependents();
+  pdl_wait();
+  uint8_t* mine = A.peer[A.rank];
+  if (threadIdx.x == 0) {
+    uint32_t* ep = reinterpret_cast<uint32_t*>(mine);
+    s_epoch = *ep + 1;
+    *ep = s_epoch;
+  }
+  __syncthreads();
+  const uint32_t epoch = s_epoch;
+  const size_t slot_bytes = (size_t)A.max_elems * 2;
+  const size_t data_off = kArHeader + 128 * (size_t)A.world + (size_t)(epoch & 1) * A.world * slot_bytes;
+  const int nvec = A.n_elems / 8;                         // 16-byte vectors
+  const uint4* src = reinterpret_cast<const uint4*>(A.partial);
+  // 1. push my partial sums into slot [rank] of every peer (and my own buffer)
+  for (int i = threadIdx.x; i < nvec * A.world; i += blockDim.x) {
+    const int p = i / nvec, v = i - p * nvec;
+    reinterpret_cast<uint4*>(A.peer[p] + data_off + (size_t)A.rank * slot_bytes)[v] = src[v];
+  }
+  __threadfence_system();
+  __syncthreads();
+  // 2. raise my flag in every peer's buffer, 3. wait for every peer's flag in mine
+  if (threadIdx.x < A.world)
+    st_release_sys(reinterpret_cast<uint32_t*>(A.peer[threadIdx.x] + kArHeader + 128 * A.rank), epoch);
+  if (threadIdx.x < A.world) {
+    const uint32_t* f = reinterpret_cast<const uint32_t*>(mine + kArHeader + 128 * threadIdx.x);
+    while (ld_acquire_sys(f) != epoch) {}
+  }
+  __syncthreads();
+  // 4. reduce in rank order (+ residual)
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int r = 0; r < A.world; ++r) {
+      const uint4 q = reinterpret_cast<const uint4*>(mine + data_off + (size_t)r * slot_bytes)[v];
+      const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); acc[2 * i] += f.x; acc[2 * i + 1] += f.y; }
+    }
+    if (A.residual) {
+      const uint4 q = reinterpret_cast<const uint4*>(A.residual)[v];
+      const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); acc[2 * i] += f.x; acc[2 * i + 1] += f.y; }
+    }
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) oh[i] = __floats2half2_rn(acc[2 * i], acc[2 * i + 1]);
+    reinterpret_cast<uint4*>(A.out)[v] = o;
+  }
+}
+
+}  // namespace amqb
+
+using namespace amqb;
+
+extern "C" {
+
+size_t amqb_ar_buffer_bytes(int max_elems, int world) {
+  if (max_elems <= 0 || world < 1 || world > kArMaxWorld) return 0;
+  return kArHeader + 128 * (size_t)world + 2 * (size_t)world * max_elems * 2;
+}
+
+int amqb_ar_alloc(size_t bytes, void** dev_ptr, void* ipc_handle_out64) {
+  if (!dev_ptr || !ipc_handle_out64 || bytes == 0) return fail(AMQB_ERR_BAD_ARG, "ar_alloc: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e == cudaSuccess) e = cudaMemset(p, 0, bytes);
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(ipc_handle_out64), p);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { set_error("ar_alloc: %s", cudaGetErrorString(e)); return AMQB_ERR_LAUNCH; }
+  *dev_ptr = p;
+  return AMQB_OK;
+}
+
+int amqb_ar_open(const void* ipc_handle64, void** dev_ptr) {
+  if (!ipc_handle64 || !dev_ptr) return fail(AMQB_ERR_BAD_ARG, "ar_open: bad argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle64, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) { set_error("ar_open: %s", cudaGetErrorString(e)); return AMQB_ERR_LAUNCH; }
+  return AMQB_OK;
+}
+
+int amqb_ar_close(void* dev_ptr) {
+  cudaError_t e = cudaIpcCloseMemHandle(dev_ptr);
+  if (e != cudaSuccess) { set_error("ar_close: %s", cudaGetErrorString(e)); return AMQB_ERR_LAUNCH; }
+  return AMQB_OK;
+}
+
+int amqb_ar_free(void* dev_ptr) {
+  cudaError_t e = cudaFree(dev_ptr);
+  if (e != cudaSuccess) { set_error("ar_free: %s", cudaGetErrorString(e)); return AMQB_ERR_LAUNCH; }
+  return AMQB_OK;
+}
+
+int amqb_allreduce_f16(void* const* peer_bufs_host, int rank, int world, const void* partial_f16,
+                       const void* residual_f16, void* out_f16, int n_elems, int max_elems, int pdl, void* stream) {
+  if (!peer_bufs_host || !partial_f16 || !out_f16 || world < 1 || world > kArMaxWorld || rank < 0 || rank >= world)
+    return fail(AMQB_ERR_BAD_ARG, "allreduce: bad argument");
+  if (n_elems <= 0 || n_elems % 8 || n_elems > max_elems) return fail(AMQB_ERR_UNSUPPORTED_SHAPE, "allreduce: n_elems % 8 or > max_elems");
+  ArArgs A{};
+  for (int i = 0; i < world; ++i) A.peer[i] = (uint8_t*)peer_bufs_host[i];
+  A.rank = rank; A.world = world; A.n_elems = n_elems; A.max_elems = max_elems;
+  A.partial = (const __half*)partial_f16; A.residual = (const __half*)residual_f16; A.out = (__half*)out_f16;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(1);
+  cfg.blockDim = dim3(1024);
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, allreduce_push_kernel, A);
+  if (e != cudaSuccess) { set_error("allreduce: %s", cudaGetErrorString(e)); return AMQB_ERR_LAUNCH; }
+  return AMQB_OK;
+}
+
+}  // extern "C"

@@ -168,12 +168,21 @@ int amqb_lm_head(const void* W_f16, const void* x, const void* gamma, float eps,
                  float* logits, int M, int V, int K, void* stream);
 int amqb_argmax(const float* logits, int64_t* out_ids, int M, int V, void* stream);
 
-/* ---- tensor parallel (config 5): one-shot all-reduce over NVLink peer memory */
-/* peer_bufs_host[r] = device pointer of rank r's exchange buffer mapped into this process,
- * each amqb_ar_buffer_bytes(max_elems, world) bytes, zero-filled at creation. */
+/* ---- tensor parallel (config 5): one-shot all-reduce over NVLink peer memory ------------- */
+/* Exchange buffers are the one thing this library allocates itself, explicitly (cudaMalloc, so the
+ * block can be exported through CUDA IPC): create with amqb_ar_alloc, hand the 64-byte handle to
+ * the other ranks (any host channel), map theirs with amqb_ar_open. */
 size_t amqb_ar_buffer_bytes(int max_elems, int world);
-int amqb_allreduce_f16(void* const* peer_bufs_host, int rank, int world, void* data_f16,
-                       const void* residual_f16, int n_elems, uint32_t epoch, void* stream);
+int amqb_ar_alloc(size_t bytes, void** dev_ptr, void* ipc_handle_out64);
+int amqb_ar_open(const void* ipc_handle64, void** dev_ptr);
+int amqb_ar_close(void* dev_ptr);
+int amqb_ar_free(void* dev_ptr);
+/* out = residual + sum over ranks of partial (fp16 [n_elems], fp32 accumulation in rank order).
+ * peer_bufs_host[r]: rank r's exchange buffer as mapped into this process ([rank] = own).  Every
+ * rank must issue the same sequence of calls.  Graph-capturable (the epoch lives in the buffer). */
+int amqb_allreduce_f16(void* const* peer_bufs_host, int rank, int world, const void* partial_f16,
+                       const void* residual_f16, void* out_f16, int n_elems, int max_elems, int pdl,
+                       void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,150 @@
+"""GPU tests of the host-side mirror of the reference interface: Quantizer / HQQLinear (config 4),
+prepare_for_inference with the gptq / ft backends and the state-dict cache files, the drop-in modules'
+forward for decode and prefill row counts, against the oracle and the golden fixtures."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import amq_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+G = 128
+
+
+@pytest.fixture(scope="module")
+def amq():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import amq_b200
+    return amq_b200
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "linear_*_N256_K512.npz"))))
+def test_quantizer_against_reference_fixture(amq, path):
+    """Quantizer.quantize on the GPU vs the reference's CPU fp32 solver output (golden): same number
+    of solver iterations, codes equal up to rare rounding ties (powf / mean-order differences, see
+    hqq_quant.cu), meta within 1e-5, and the dequantised weights as close to W as the reference's."""
+    d = np.load(path)
+    bits = int(os.path.basename(path).split("_")[1][0])
+    W = torch.from_numpy(d["W"]).cuda()
+    N, K = W.shape
+    cfg = amq.BaseQuantizeConfig(nbits=bits, group_size=G)["weight_quant_params"]
+    W_q, meta = amq.Quantizer.quantize(W, device="cuda", compute_dtype=torch.float16, **cfg)
+    codes = amq.Quantizer.unpack[meta["packing"]](W_q)[: N * K // G].cpu().numpy()
+    mism = float((codes != d["codes"]).mean())
+    assert mism < 2e-3, mism
+    assert np.abs(meta["scale"].cpu().numpy() - d["hqq_scale"]).max() < 1e-6
+    dz = np.abs(meta["zero"].cpu().numpy() - d["hqq_zero"])
+    assert dz.max() < 3e-2 and float((dz > 1e-5).mean()) < 0.02      # a tie flips one code: zero moves by k/128 in that group
+    # packed tensor has the reference's shape / dtype (bitpack.py) and round-trips
+    assert tuple(W_q.shape) == d["hqq_Wq"].shape and str(W_q.dtype).endswith(str(d["hqq_Wq"].dtype))
+    meta16 = dict(meta, scale=meta["scale"].half(), zero=meta["zero"].half(), compute_dtype=torch.float16)
+    W_r = amq.Quantizer.dequantize(W_q, meta16).float().cpu()
+    err = float((W_r - torch.from_numpy(d["W"]).float()).abs().mean())
+    err_ref = float((torch.from_numpy(d["W_deq"]).float() - torch.from_numpy(d["W"]).float()).abs().mean())
+    assert err <= err_ref * 1.01
+
+
+@pytest.mark.parametrize("bits", [2, 3, 4])
+def test_hqq_to_kernel_modules_flow(amq, bits, tmp_path):
+    """nn.Linear -> HQQLinear -> prepare_for_inference(gptq / ft) -> forward, plus the cache file:
+    second run loads `*_GPTQLinear.pt` / `*_FTLinear.pt` through load_state_dict (patching.py:178-205)."""
+    import torch.nn as nn
+    torch.manual_seed(bits)
+    N, K = 256, 512
+
+    class Block(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.q_proj = nn.Linear(K, N, bias=(bits == 3))
+
+    def make():
+        torch.manual_seed(100 + bits)
+        blk = Block().half()
+        blk.q_proj = amq.HQQLinear(blk.q_proj, amq.BaseQuantizeConfig(nbits=bits, group_size=G), compute_dtype=torch.float16,
+                                   device="cuda")
+        return blk
+
+    blk = make()
+    hq = blk.q_proj
+    W_deq = hq.dequantize().float()
+    codes_hqq = hq.unpack_codes()
+    x = torch.randn(5, K, device="cuda").half()
+    y_hqq = hq(x)
+    bias = hq.bias.float() if hq.bias is not None else 0.0
+    ref = x.float() @ W_deq.t() + bias
+    assert O.max_rel(y_hqq.cpu(), ref.cpu()) < 2e-3
+    backend = "ft" if bits == 4 else "gptq"
+    cache = str(tmp_path / f"m_{bits}bit_128gs_1axis_{'FTLinear' if bits == 4 else 'GPTQLinear'}.pt")
+    amq.prepare_for_inference(blk, backend=backend, load_path=cache)
+    lin = blk.q_proj
+    assert type(lin).__name__ == ("FT_QuantLinear" if bits == 4 else "GPTQLinear") and os.path.exists(cache)
+    assert hasattr(lin, "weight")                       # dummy param HF code touches (patching.py:76-91)
+    from amq_b200 import ops, _lib
+    layout = _lib.LAYOUT_FT if bits == 4 else _lib.LAYOUT_GPTQ
+    assert torch.equal(ops.unpack_codes(lin.qweight, bits, layout, N, K, G), codes_hqq)      # codes survive, bit-exact
+    for M in (1, 5, 16, 40):                            # decode kernel and prefill entry point
+        xm = torch.randn(2, M // 2 if M > 1 else 1, K, device="cuda").half() if M > 1 else torch.randn(1, 1, K, device="cuda").half()
+        y = lin(xm)
+        assert y.shape == xm.shape[:-1] + (N,) and y.dtype == torch.float16
+        r = xm.reshape(-1, K).float() @ W_deq.t() + bias
+        assert O.max_rel(y.reshape(-1, N).cpu(), r.cpu()) <= 1e-3
+    # second run: empty shells + load_state_dict of the cache file
+    blk2 = make()
+    amq.prepare_for_inference(blk2, backend=backend, load_path=cache)
+    y2 = blk2.q_proj(x)
+    assert torch.equal(y2, lin(x))
+    # the dummy .weight is added after the cache is written, exactly as in the reference (patching.py:218-222)
+    assert set(blk2.state_dict()) - {"q_proj.weight"} == set(torch.load(cache, weights_only=True))
+
+
+def test_gptq_module_on_golden_reference_buffers(amq):
+    """A GPTQLinear filled with the buffers the REFERENCE produced (golden) reproduces the oracle."""
+    d = np.load(os.path.join(GOLD, "linear_3bit_N256_K512.npz"))
+    N, K = d["W"].shape
+    m = amq.GPTQLinear(3, G, K, N, bias=False)
+    m.load_state_dict({"qweight": torch.from_numpy(d["gptq_qweight"]), "scales": torch.from_numpy(d["gptq_scales"]),
+                       "zeros": torch.from_numpy(d["gptq_zeros"])})
+    m = m.cuda()
+    for M in (1, 5):
+        y = m(torch.from_numpy(d[f"x{M}"]).cuda())
+        assert O.max_rel(y.cpu(), torch.from_numpy(d[f"y{M}_fp32"])) <= 1e-3
+        assert O.max_rel(y.cpu(), torch.from_numpy(d[f"y{M}_ref_fp16"])) <= 2e-3
+    # pack() on the GPU reproduces the reference's packed buffers from the dequantised weights
+    m2 = amq.GPTQLinear(3, G, K, N, bias=False).cuda()
+    s = torch.from_numpy(d["hqq_scale"]).half().reshape(N, -1).cuda()
+    z = torch.from_numpy(d["hqq_zero"]).half().reshape(N, -1).cuda()
+    m2.pack(torch.from_numpy(d["W_deq"]).cuda(), s, z)
+    assert np.array_equal(m2.qweight.cpu().numpy(), d["gptq_qweight"])
+
+
+def test_pack_intweight_matches_reference_layout(amq):
+    d = np.load(os.path.join(GOLD, "linear_4bit_N256_K512.npz"))
+    codes = torch.from_numpy(d["codes"].reshape(256, 512).astype(np.int32)).cuda()
+    q = amq.pack_intweight(codes, interleave=4, kstride=64)
+    assert np.array_equal(q.cpu().numpy(), d["ft_qweight"])
+
+
+@pytest.mark.parametrize("bits", [2, 3, 4])
+def test_config4_proxy_sweep_shapes(amq, bits):
+    """Config 4 at Qwen2-7B shapes (k/v 512x3584 with the full K, one q-sized slab): quantize -> pack ->
+    dequantize round trip properties at full width: codes in range, pack/unpack bit-exact, error bound."""
+    torch.manual_seed(0)
+    N, K = 512, 3584
+    W = (torch.randn(N, K, device="cuda") * 0.02).half()
+    cfg = amq.BaseQuantizeConfig(nbits=bits, group_size=G)["weight_quant_params"]
+    W_q, meta = amq.Quantizer.quantize(W, device="cuda", compute_dtype=torch.float16, **cfg)
+    R = N * K // G
+    codes = amq.Quantizer.unpack[meta["packing"]](W_q)[:R]
+    assert int(codes.max()) <= 2 ** bits - 1
+    assert torch.equal(amq.Quantizer.pack[meta["packing"]](codes), W_q)
+    o_codes, o_scale, o_zero, _ = O.hqq_quantize(W.cpu(), bits, G)
+    assert float((codes.cpu().numpy() != o_codes).mean()) < 2e-3
+    meta16 = dict(meta, scale=meta["scale"].half(), zero=meta["zero"].half())
+    W_r = amq.Quantizer.dequantize(W_q, meta16)
+    step = meta["scale"].max().item()
+    assert float((W_r.float() - W.float()).abs().max()) <= 1.01 * step * (1.0 if bits > 2 else 1.5)
