@@ -40,6 +40,14 @@ static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, 
     if (P.n_g < min_g) min_g = P.n_g;
     if (rec_bytes(q.bits) > max_rec) max_rec = rec_bytes(q.bits);
   }
+  // x' build schedule: the first problem of a run sharing (x, K) builds every bit-width variant the run needs
+  for (int i = 0; i < count; ++i) {
+    DevProblem& P = L.prob[i];
+    const bool first = (i == 0) || L.prob[i - 1].x != P.x || L.prob[i - 1].K != P.K;
+    P.build_mask = 0;
+    if (first)
+      for (int j = i; j < count && L.prob[j].x == P.x && L.prob[j].K == P.K; ++j) P.build_mask |= 1 << L.prob[j].bits;
+  }
   // K split across a cluster only when N is too small to occupy the chip (each cluster then owns at
   // most one row block per problem, which is what the DSMEM hand-off assumes)
   int S = 1;

@@ -30,11 +30,11 @@ __device__ __forceinline__ long long gtime() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-#define AMQB_STAMP(i) do { if (L.dbg && tid == 0) L.dbg[blockIdx.x * 8 + (i)] = gtime(); } while (0)
+#define AMQB_STAMP(i) do { if (L.dbg && tid == 0) L.dbg[blockIdx.x * 16 + (i)] = gtime(); } while (0)
 
 constexpr int kCW = 16;                      // consumer warps
 constexpr int kCThreads = kCW * 32;
-constexpr int kThreads = kCThreads + 32;     // + producer warp = 544 threads, <= 120 registers
+constexpr int kThreads = kCThreads + 64;     // + producer warp + reducer warp = 576 threads (96 registers)
 constexpr int kStageRecs = kCW;              // records per pipeline stage: one per consumer warp
 constexpr int kMaxProblems = 4;
 constexpr int kXprimeBudget = 72 * 1024;
@@ -52,6 +52,7 @@ struct DevProblem {
   int bits, N, K, ldx, ldy, prologue;
   int n_rb, n_g;
   int kc;                // groups per x' chunk (K is walked chunk by chunk when x' would not fit)
+  int build_mask;        // bit b set: build the x' variant of bit width b when this problem starts (0: reuse)
 };
 
 struct GemvLaunch {
@@ -141,8 +142,8 @@ __device__ __forceinline__ void finish_item(uint2 a, uint2 b, float rs, __half2&
   const __half2* bh = reinterpret_cast<const __half2*>(&b);
   if (pro == AMQB_PRO_SILU_MUL) {          // silu(gate) * up, fp16 op by op like the HF MLP
     float2 g0 = __half22float2(ah[0]), g1 = __half22float2(ah[1]);
-    g0.x = g0.x / (1.f + __expf(-g0.x)); g0.y = g0.y / (1.f + __expf(-g0.y));
-    g1.x = g1.x / (1.f + __expf(-g1.x)); g1.y = g1.y / (1.f + __expf(-g1.y));
+    g0.x = __fdividef(g0.x, 1.f + __expf(-g0.x)); g0.y = __fdividef(g0.y, 1.f + __expf(-g0.y));
+    g1.x = __fdividef(g1.x, 1.f + __expf(-g1.x)); g1.y = __fdividef(g1.y, 1.f + __expf(-g1.y));
     lo = __hmul2(__float22half2_rn(g0), bh[0]);
     hi = __hmul2(__float22half2_rn(g1), bh[1]);
   } else if (pro == AMQB_PRO_RMSNORM) {    // gamma * fp16(x * rsqrt(mean x^2 + eps))
@@ -160,10 +161,13 @@ __device__ __forceinline__ void finish_item(uint2 a, uint2 b, float rs, __half2&
 // CTA-wide barrier is needed; only the RMSNorm statistic crosses warps.
 template <bool M1, int PRO>
 __device__ __forceinline__ void build_xprime(const DevProblem& P, int M, int NB, int S, int g_lo, int len, uint8_t* xp,
-                                             float* xs, float* sred, int cw, int lane, bool have_stats, float& rs1) {
-  const int bits = P.bits;
-  const int NM = mmas_per_group(bits);
-  if (PRO == AMQB_PRO_RMSNORM && !have_stats) {
+                                             float* xs, float* sred, int cw, int lane, bool have_stats, float& rs1,
+                                             int mask, int variants, int var_stride) {
+  constexpr int BATCH = 4;
+  // RMSNorm, batch 1, unsplit K, few groups per warp: x is loaded once and its squares summed from
+  // the registers that are then normalised (one pass, one barrier)
+  const bool one_pass = PRO == AMQB_PRO_RMSNORM && !have_stats && M1 && S == 1 && (len + kCW - 1) / kCW <= BATCH;
+  if (PRO == AMQB_PRO_RMSNORM && !have_stats && !one_pass) {
     if (M1 && S == 1) {
       // every warp sums the squares of the groups it owns; together the warps cover the whole row
       float ss = 0.f;
@@ -200,8 +204,7 @@ __device__ __forceinline__ void build_xprime(const DevProblem& P, int M, int NB,
   }
   const int my_groups = (len - cw + kCW - 1) / kCW;     // gl = cw, cw + kCW, ...
   const int items = my_groups > 0 ? my_groups * M : 0;
-  constexpr int BATCH = 2;
-  for (int it0 = 0; it0 < items; it0 += BATCH) {
+  for (int it0 = 0; it0 < items || (one_pass && it0 == 0); it0 += BATCH) {
     uint2 a[BATCH], b[BATCH];
 #pragma unroll
     for (int u = 0; u < BATCH; ++u) {
@@ -214,9 +217,29 @@ __device__ __forceinline__ void build_xprime(const DevProblem& P, int M, int NB,
         else if (PRO == AMQB_PRO_RMSNORM) b[u] = *reinterpret_cast<const uint2*>(P.gamma + kbase);
       }
     }
+    if (one_pass) {
+      float ss = 0.f;
+#pragma unroll
+      for (int u = 0; u < BATCH; ++u)
+        if (u < items) {
+          const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&a[u].x));
+          const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&a[u].y));
+          ss += x0.x * x0.x + x0.y * x0.y + x1.x * x1.x + x1.y * x1.y;
+        }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      if (lane == 0) sred[cw] = ss;
+      named_bar_sync(1, kCThreads);
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kCW; ++w) t += sred[w];
+      rs1 = rsqrtf(t / (float)P.K + P.eps);
+    }
+    float sums[BATCH];
 #pragma unroll
     for (int u = 0; u < BATCH; ++u) {
       const int it = it0 + u;
+      sums[u] = 0.f;
       if (it < items) {
         const int gi = M1 ? it : it / M, col = M1 ? 0 : it - gi * M;
         const int gl = cw + gi * kCW;
@@ -229,15 +252,26 @@ __device__ __forceinline__ void build_xprime(const DevProblem& P, int M, int NB,
         }
         __half2 lo, hi;
         finish_item<PRO>(a[u], b[u], rs, lo, hi);
-        uint8_t* gb = xp + (size_t)gl * NM * M * 32;
-        if (bits == 3) place_item<3>(gb, M, col, lane, lo, hi);
-        else if (bits == 4) place_item<4>(gb, M, col, lane, lo, hi);
-        else place_item<2>(gb, M, col, lane, lo, hi);
+        // one activation load / normalisation feeds every bit-width variant the group of problems needs
+        if (mask & 8) place_item<3>(xp + (size_t)(variants == 3 ? 1 : 0) * var_stride + (size_t)gl * 9 * M * 32, M, col, lane, lo, hi);
+        if (mask & 16) place_item<4>(xp + (size_t)(variants == 3 ? 2 : 0) * var_stride + (size_t)gl * 8 * M * 32, M, col, lane, lo, hi);
+        if (mask & 4) place_item<2>(xp + (size_t)gl * 8 * M * 32, M, col, lane, lo, hi);
         const float2 f0 = __half22float2(lo), f1 = __half22float2(hi);
-        float sum = (f0.x + f0.y) + (f1.x + f1.y);
+        sums[u] = (f0.x + f0.y) + (f1.x + f1.y);
+      }
+    }
 #pragma unroll
-        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if (lane == 0) xs[gl * NB * 8 + col] = sum * 5.9604644775390625e-08f;   // 2^-24
+    for (int o = 16; o; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < BATCH; ++u) sums[u] += __shfl_xor_sync(0xffffffffu, sums[u], o);
+    if (lane == 0) {
+#pragma unroll
+      for (int u = 0; u < BATCH; ++u) {
+        const int it = it0 + u;
+        if (it < items) {
+          const int gi = M1 ? it : it / M, col = M1 ? 0 : it - gi * M;
+          xs[(cw + gi * kCW) * NB * 8 + col] = sums[u] * 5.9604644775390625e-08f;   // 2^-24
+        }
       }
     }
   }
@@ -420,32 +454,121 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
     return;
   }
 
+  if (warp == kCW + 1) {
+    // ===== reducer warp: sums the consumer warps' partial tiles of every (chunk of a) row block in
+    // fixed order and stores / hands off, so no consumer warp is ever held up by the epilogue
+    pdl_wait();                      // bias / residual / y belong to the dependency chain
+    int nblk = 0;
+    for (int p = 0; p < L.count; ++p) {
+      const DevProblem& P = L.prob[p];
+      if (cid >= P.n_rb) continue;
+      const int g_lo = (P.n_g * rank) / S, g_hi = (P.n_g * (rank + 1)) / S;
+      const bool chunked = (g_hi - g_lo) > P.kc;
+      for (int c_lo = g_lo; c_lo < g_hi; c_lo += P.kc) {
+        const int c_hi = (c_lo + P.kc) < g_hi ? (c_lo + P.kc) : g_hi;
+        const bool first_chunk = c_lo == g_lo, last_chunk = c_hi == g_hi;
+        int j = 0;
+        for (int rb = cid; rb < P.n_rb; rb += ncl, ++nblk, ++j) {
+          const int buf = nblk & 1, use = nblk >> 1;
+            mbar_wait(smem_u32(&bars[28 + buf]), use & 1);
+            const float* rbase = red + (size_t)buf * kCW * 2 * NB * 128;
+            constexpr int EPT = M1 ? 1 : 8 * NB;                 // output elements per lane
+#pragma unroll
+            for (int q = 0; q < EPT; ++q) {
+              const int e = M1 ? lane : q * 32 + lane;
+              float v = 0.f;
+#pragma unroll
+              for (int w = 0; w < kCW; ++w) v += rbase[w * 2 * NB * 128 + e];
+              v *= 16777216.f;                                   // undo the 2^-24 of the subnormal code encoding
+              int row, col;
+              if (M1) { row = e; col = 0; }
+              else {
+                const int ci = e & 3, ln = (e >> 2) & 31, tn = e >> 7;   // tn = tile*NB + nb
+                const int tile = tn / NB, nb = tn - tile * NB;
+                row = tile * 16 + (ln >> 2) + 8 * (ci >> 1);
+                col = nb * 8 + 2 * (ln & 3) + (ci & 1);
+              }
+              if (chunked) {
+                float* ab = accbuf + (size_t)j * 2 * NB * 128 + e;
+                if (!first_chunk) v += *ab;
+                if (!last_chunk) *ab = v;
+              }
+              if (last_chunk) {
+                if (S == 1) {
+                  if (col < M) store_out(P, rb * 32 + row, col, v);
+                } else {
+                  // K was split across the cluster: partial sums meet in rank 0's shared memory (DSMEM)
+                  float* pslot = part + (size_t)(p * S + rank) * 2 * NB * 128 + e;
+                  if (rank != 0) st_dsmem_f32(smem_u32(pslot), 0, v);
+                  else *pslot = v;
+                }
+              }
+            }
+            if (last_chunk && S > 1) {
+              __syncwarp();
+              if (rank != 0) {
+                if (lane == 0) mbar_arrive_remote(smem_u32(&bars[24 + p]), 0);
+              } else {
+                mbar_wait_cluster(smem_u32(&bars[24 + p]), 0);
+#pragma unroll
+                for (int q = 0; q < EPT; ++q) {
+                  const int e = M1 ? lane : q * 32 + lane;
+                  int row, col;
+                  if (M1) { row = e; col = 0; }
+                  else {
+                    const int ci = e & 3, ln = (e >> 2) & 31, tn = e >> 7;
+                    const int tile = tn / NB, nb = tn - tile * NB;
+                    row = tile * 16 + (ln >> 2) + 8 * (ci >> 1);
+                    col = nb * 8 + 2 * (ln & 3) + (ci & 1);
+                  }
+                  if (col < M) {
+                    float t = 0.f;
+                    for (int r = 0; r < S; ++r) t += part[(size_t)(p * S + r) * 2 * NB * 128 + e];
+                    store_out(P, rb * 32 + row, col, t);
+                  }
+                }
+              }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars[30 + buf]));
+        }
+      }
+    }
+    return;
+  }
+
   // ===== consumers
   pdl_wait();                        // x / residual come from the previous kernel
   AMQB_STAMP(1);
   float acc[2][NB][4];
   int s = 0, ph = 0, nblk = 0;
   const __half* cur_x = nullptr;     // x' cache: problems of a group that share x (q/k/v, gate/up)
-  int cur_K = 0, built_mask = 0;
+  int cur_K = 0, built_mask = 0, stat_par = 0, run_mask = 0;
   float rs1 = 1.f;
   for (int p = 0; p < L.count; ++p) {
     const DevProblem& P = L.prob[p];
-    if (cid >= P.n_rb) continue;
     const uint32_t rbytes = rec_bytes(P.bits);
     const int NM = mmas_per_group(P.bits);
     const int g_lo = (P.n_g * rank) / S, g_hi = (P.n_g * (rank + 1)) / S;
     const bool chunked = (g_hi - g_lo) > P.kc;
+    AMQB_STAMP(4 + 4 * p);
     const bool same_x = (P.x == cur_x) && (P.K == cur_K);
-    if (!same_x) { built_mask = 0; cur_x = P.x; cur_K = P.K; }
+    if (!same_x) { built_mask = 0; cur_x = P.x; cur_K = P.K; stat_par ^= 1; }   // new x: new statistics buffer
+    if (P.build_mask) run_mask = P.build_mask;
+    if (cid >= P.n_rb) continue;          // (after the bookkeeping: a later problem may rely on this run's mask)
     uint8_t* xpv = xp + (L.xp_variants == 3 ? (size_t)(P.bits - 2) * L.xprime_bytes : 0);
     for (int c_lo = g_lo; c_lo < g_hi; c_lo += P.kc) {
       const int c_hi = (c_lo + P.kc) < g_hi ? (c_lo + P.kc) : g_hi;
       const bool first_chunk = c_lo == g_lo, last_chunk = c_hi == g_hi;
-      if (chunked || L.xp_variants != 3 || !(built_mask & (1 << P.bits)))
-        build_xprime<M1, PRO>(P, M, NB, S, c_lo, c_hi - c_lo, xpv, xs, sred, warp, lane, same_x && built_mask != 0, rs1);
-      built_mask |= 1 << P.bits;
+      // x' variants to (re)build now: chunked K or a single variant buffer -> this problem's own; else
+      // whatever the host scheduled at this problem (all bit widths of the problems sharing this x)
+      const int want = (chunked || L.xp_variants != 3) ? (1 << P.bits) : ((run_mask | (1 << P.bits)) & ~built_mask);
+      if (want)
+        build_xprime<M1, PRO>(P, M, NB, S, c_lo, c_hi - c_lo, xp, xs, sred + ((M1 && stat_par) ? kCW : 0), warp, lane,
+                              same_x && built_mask != 0, rs1, want, L.xp_variants, L.xprime_bytes);
+      built_mask |= want | (1 << P.bits);
       if (L.dbg_delay_ns) { const long long t_end = gtime() + L.dbg_delay_ns; while (gtime() < t_end) {} }
-      AMQB_STAMP(2);
+      AMQB_STAMP(5 + 4 * p);
       int j = 0;
       for (int rb = cid; rb < P.n_rb; rb += ncl, ++nblk, ++j) {
 #pragma unroll
@@ -470,7 +593,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
           if (lane == 0) mbar_arrive(smem_u32(&bars[NS + s]));
           if (++s == NS) { s = 0; ph ^= 1; }
         }
-        AMQB_STAMP(3);
+        AMQB_STAMP(6 + 4 * p);
         // ---- (chunk of a) row block done.  Every warp deposits its partial sums in a double-buffered
         // shared-memory area and moves straight on; ONE warp (rotating) waits for all deposits, sums
         // them in fixed order and stores / hands off.  mbarriers only: no CTA-wide barrier on this path.
@@ -492,75 +615,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars[28 + buf]));
-        const int reducer = chunked ? 0 : (nblk % kCW);
-        if (warp == reducer) {
-          mbar_wait(smem_u32(&bars[28 + buf]), use & 1);
-          const float* rbase = red + (size_t)buf * kCW * 2 * NB * 128;
-          constexpr int EPT = M1 ? 1 : 8 * NB;                 // output elements per lane
-#pragma unroll
-          for (int q = 0; q < EPT; ++q) {
-            const int e = M1 ? lane : q * 32 + lane;
-            float v = 0.f;
-#pragma unroll
-            for (int w = 0; w < kCW; ++w) v += rbase[w * 2 * NB * 128 + e];
-            v *= 16777216.f;                                   // undo the 2^-24 of the subnormal code encoding
-            int row, col;
-            if (M1) { row = e; col = 0; }
-            else {
-              const int ci = e & 3, ln = (e >> 2) & 31, tn = e >> 7;   // tn = tile*NB + nb
-              const int tile = tn / NB, nb = tn - tile * NB;
-              row = tile * 16 + (ln >> 2) + 8 * (ci >> 1);
-              col = nb * 8 + 2 * (ln & 3) + (ci & 1);
-            }
-            if (chunked) {
-              float* ab = accbuf + (size_t)j * 2 * NB * 128 + e;
-              if (!first_chunk) v += *ab;
-              if (!last_chunk) *ab = v;
-            }
-            if (last_chunk) {
-              if (S == 1) {
-                if (col < M) store_out(P, rb * 32 + row, col, v);
-              } else {
-                // K was split across the cluster: partial sums meet in rank 0's shared memory (DSMEM)
-                float* pslot = part + (size_t)(p * S + rank) * 2 * NB * 128 + e;
-                if (rank != 0) st_dsmem_f32(smem_u32(pslot), 0, v);
-                else *pslot = v;
-              }
-            }
-          }
-          if (last_chunk && S > 1) {
-            __syncwarp();
-            if (rank != 0) {
-              if (lane == 0) mbar_arrive_remote(smem_u32(&bars[24 + p]), 0);
-            } else {
-              mbar_wait_cluster(smem_u32(&bars[24 + p]), 0);
-#pragma unroll
-              for (int q = 0; q < EPT; ++q) {
-                const int e = M1 ? lane : q * 32 + lane;
-                int row, col;
-                if (M1) { row = e; col = 0; }
-                else {
-                  const int ci = e & 3, ln = (e >> 2) & 31, tn = e >> 7;
-                  const int tile = tn / NB, nb = tn - tile * NB;
-                  row = tile * 16 + (ln >> 2) + 8 * (ci >> 1);
-                  col = nb * 8 + 2 * (ln & 3) + (ci & 1);
-                }
-                if (col < M) {
-                  float t = 0.f;
-                  for (int r = 0; r < S; ++r) t += part[(size_t)(p * S + r) * 2 * NB * 128 + e];
-                  store_out(P, rb * 32 + row, col, t);
-                }
-              }
-            }
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&bars[30 + buf]));
-        }
-        AMQB_STAMP(4);
+        AMQB_STAMP(7 + 4 * p);
       }
     }
   }
-  AMQB_STAMP(6);
+  AMQB_STAMP(2);
 }
 
 

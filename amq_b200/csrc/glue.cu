@@ -49,12 +49,14 @@ __global__ void embed_kernel(const int64_t* __restrict__ ids, const __half* __re
 }
 
 // ------------------------------------------------------------------ attention (decode)
-// grid (Hq, B), 128 threads.  Lane l of a warp owns head-dim elements [EPL*l, EPL*l+EPL).
+// grid (Hq, B), 16 warps.  Lane l of a warp owns head-dim elements [EPL*l, EPL*l+EPL); warp w owns
+// positions w, w+16, ...  (8 in flight per warp: one pass covers 128 cached positions).
+constexpr int kAttnWarps = 16;
 template <int D>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kAttnWarps * 32)
 attn_decode_kernel(const __half* __restrict__ qkv, __half* __restrict__ kc, __half* __restrict__ vc,
                    __half* __restrict__ out, const int* __restrict__ pos_dev, int Hq, int Hkv, int max_seq,
-                   float theta) {
+                   float theta, const float* __restrict__ rope_tab) {
   constexpr int EPL = D / 32;     // elements per lane
   pdl_launch_dependents();
   pdl_wait();
@@ -72,9 +74,14 @@ attn_decode_kernel(const __half* __restrict__ qkv, __half* __restrict__ kc, __ha
   for (int e = 0; e < EPL; ++e) {
     const int i = EPL * lane + e;
     const int ih = i % (D / 2);
-    const float inv = __powf(theta, -2.f * (float)ih / (float)D);
     float sn, cs;
-    sincosf((float)pos * inv, &sn, &cs);
+    if (rope_tab) {                       // [max_seq][D/2] float2(cos, sin), built once by amqb_rope_table
+      const float2 t2 = reinterpret_cast<const float2*>(rope_tab)[(size_t)pos * (D / 2) + ih];
+      cs = t2.x; sn = t2.y;
+    } else {
+      const float inv = __powf(theta, -2.f * (float)ih / (float)D);
+      sincosf((float)pos * inv, &sn, &cs);
+    }
     // fp16-rounded cos / sin as HF (LlamaRotaryEmbedding casts to the activation dtype)
     cs = __half2float(__float2half_rn(cs));
     sn = __half2float(__float2half_rn(sn));
@@ -99,14 +106,14 @@ attn_decode_kernel(const __half* __restrict__ qkv, __half* __restrict__ kc, __ha
   float mx = -INFINITY, den = 0.f, acc[EPL];
 #pragma unroll
   for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
-  // positions j = warp, warp+4, ... ; four at a time so the loads and the butterfly reductions of
+  // positions j = warp, warp+16, ... ; eight at a time so the loads and the butterfly reductions of
   // independent positions overlap (the loop is latency-bound, not bandwidth-bound)
-  constexpr int UNR = 4;
-  for (int j0 = warp; j0 <= pos; j0 += 4 * UNR) {
+  constexpr int UNR = 8;
+  for (int j0 = warp; j0 <= pos; j0 += kAttnWarps * UNR) {
     float kj[UNR][EPL], vj[UNR][EPL], sc[UNR];
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
-      const int j = j0 + 4 * u;
+      const int j = j0 + kAttnWarps * u;
       if (j < pos) {
         if (EPL == 4) {
           const uint2 kk = *reinterpret_cast<const uint2*>(kcb + (size_t)j * D + 4 * lane);
@@ -140,7 +147,7 @@ attn_decode_kernel(const __half* __restrict__ qkv, __half* __restrict__ kc, __ha
       for (int u = 0; u < UNR; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], o);
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
-      if (j0 + 4 * u <= pos) {
+      if (j0 + kAttnWarps * u <= pos) {
         const float s = sc[u] * scale;
         const float nm = fmaxf(mx, s);
         const float corr = __expf(mx - nm), p = __expf(s - nm);
@@ -151,23 +158,37 @@ attn_decode_kernel(const __half* __restrict__ qkv, __half* __restrict__ kc, __ha
       }
     }
   }
-  __shared__ float s_m[4], s_d[4], s_acc[4][D];
+  __shared__ float s_m[kAttnWarps], s_d[kAttnWarps], s_acc[kAttnWarps][D];
   if (lane == 0) { s_m[warp] = mx; s_d[warp] = den; }
 #pragma unroll
   for (int e = 0; e < EPL; ++e) s_acc[warp][EPL * lane + e] = acc[e];
   __syncthreads();
   if (warp == 0) {
-    float gm = fmaxf(fmaxf(s_m[0], s_m[1]), fmaxf(s_m[2], s_m[3]));
-    float gd = 0.f, w4[4];
+    float gm = -INFINITY;
 #pragma unroll
-    for (int w = 0; w < 4; ++w) { w4[w] = (s_m[w] == -INFINITY) ? 0.f : __expf(s_m[w] - gm); gd += s_d[w] * w4[w]; }
+    for (int w = 0; w < kAttnWarps; ++w) gm = fmaxf(gm, s_m[w]);
+    float gd = 0.f, wt[kAttnWarps];
+#pragma unroll
+    for (int w = 0; w < kAttnWarps; ++w) { wt[w] = (s_m[w] == -INFINITY) ? 0.f : __expf(s_m[w] - gm); gd += s_d[w] * wt[w]; }
 #pragma unroll
     for (int e = 0; e < EPL; ++e) {
       const int i = EPL * lane + e;
-      const float o = (s_acc[0][i] * w4[0] + s_acc[1][i] * w4[1] + s_acc[2][i] * w4[2] + s_acc[3][i] * w4[3]) / gd;
-      out[(size_t)b * Hq * D + h * D + i] = __float2half_rn(o);
+      float o = 0.f;
+#pragma unroll
+      for (int w = 0; w < kAttnWarps; ++w) o += s_acc[w][i] * wt[w];
+      out[(size_t)b * Hq * D + h * D + i] = __float2half_rn(o / gd);
     }
   }
+}
+
+__global__ void rope_table_kernel(float2* __restrict__ tab, int max_seq, int D, float theta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= max_seq * (D / 2)) return;
+  const int pos = i / (D / 2), ih = i - pos * (D / 2);
+  const float inv = powf(theta, -2.f * (float)ih / (float)D);
+  float sn, cs;
+  sincosf((float)pos * inv, &sn, &cs);
+  tab[i] = make_float2(cs, sn);
 }
 
 // ------------------------------------------------------------------ lm_head: fp16 GEMV + fused final RMSNorm
@@ -291,17 +312,24 @@ int amqb_embed(const int64_t* token_ids, const void* table_f16, void* out_f16, i
                 (const __half*)table_f16, (__half*)out_f16, hidden);
 }
 
+int amqb_rope_table(float* cos_sin, int max_seq, int D, float rope_theta, void* stream) {
+  if (!cos_sin || max_seq < 1 || D < 2 || D % 2) return fail(AMQB_ERR_BAD_ARG, "rope_table: bad argument");
+  const int n = max_seq * (D / 2);
+  rope_table_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((float2*)cos_sin, max_seq, D, rope_theta);
+  return check_launch("rope_table");
+}
+
 int amqb_attn_decode(const void* qkv, void* k_cache, void* v_cache, void* out, const int* pos_dev, int B, int Hq,
-                     int Hkv, int D, int max_seq, float rope_theta, void* stream) {
+                     int Hkv, int D, int max_seq, float rope_theta, const float* rope_cos_sin, void* stream) {
   if (!qkv || !k_cache || !v_cache || !out || !pos_dev || B < 1 || Hq < 1 || Hkv < 1 || Hq % Hkv)
     return fail(AMQB_ERR_BAD_ARG, "attn_decode: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   if (D == 128)
-    return launch(attn_decode_kernel<128>, dim3(Hq, B), dim3(128), 0, st, "attn_decode", (const __half*)qkv,
-                  (__half*)k_cache, (__half*)v_cache, (__half*)out, pos_dev, Hq, Hkv, max_seq, rope_theta);
+    return launch(attn_decode_kernel<128>, dim3(Hq, B), dim3(kAttnWarps * 32), 0, st, "attn_decode", (const __half*)qkv,
+                  (__half*)k_cache, (__half*)v_cache, (__half*)out, pos_dev, Hq, Hkv, max_seq, rope_theta, rope_cos_sin);
   if (D == 64)
-    return launch(attn_decode_kernel<64>, dim3(Hq, B), dim3(128), 0, st, "attn_decode", (const __half*)qkv,
-                  (__half*)k_cache, (__half*)v_cache, (__half*)out, pos_dev, Hq, Hkv, max_seq, rope_theta);
+    return launch(attn_decode_kernel<64>, dim3(Hq, B), dim3(kAttnWarps * 32), 0, st, "attn_decode", (const __half*)qkv,
+                  (__half*)k_cache, (__half*)v_cache, (__half*)out, pos_dev, Hq, Hkv, max_seq, rope_theta, rope_cos_sin);
   return fail(AMQB_ERR_UNSUPPORTED_SHAPE, "attn_decode: head_dim must be 64 or 128");
 }
 

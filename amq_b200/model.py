@@ -102,6 +102,8 @@ class QuantDecoder:
         self.logits = torch.zeros(B, shape.vocab, device=self.dev, dtype=torch.float32)
         self.next_tokens = torch.zeros(B, dtype=torch.int64, device=self.dev)
         self.pos = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.rope = torch.empty(max_seq, self.D // 2, 2, dtype=torch.float32, device=self.dev)
+        check(lib().amqb_rope_table(ptr(self.rope), max_seq, self.D, ctypes.c_float(shape.rope_theta), cur_stream()), "rope_table")
         self.ws = ops.workspace(self.dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.allreduce = None          # set by amq_b200.tp for tensor-parallel runs
@@ -179,7 +181,7 @@ class QuantDecoder:
             L = P["L"]
             self._gemv(P["qkv"], 3)
             check(Lb.amqb_attn_decode(ptr(self.qkv), ptr(L["k_cache"]), ptr(L["v_cache"]), ptr(self.attn), ptr(self.pos),
-                                      self.B, self.Hq, self.Hkv, self.D, self.max_seq, ctypes.c_float(S.rope_theta), st),
+                                      self.B, self.Hq, self.Hkv, self.D, self.max_seq, ctypes.c_float(S.rope_theta), ptr(self.rope), st),
                   "attn_decode")
             self.launches_per_step += 1
             self._gemv(P["o"], 1)

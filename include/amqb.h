@@ -159,9 +159,11 @@ int amqb_embed(const int64_t* token_ids, const void* table_f16, void* out_f16,
 /* RoPE (HF rotate_half convention) on q,k of this step, append k,v to the static cache,
  * single-query attention over positions [0, pos].  qkv: fp16 [B, (Hq+2*Hkv)*D].
  * k_cache/v_cache: fp16 [B, Hkv, max_seq, D].  out: fp16 [B, Hq*D]. */
+/* rope_cos_sin: optional fp32 [max_seq, D/2, 2] table from amqb_rope_table (else computed in-kernel). */
+int amqb_rope_table(float* cos_sin, int max_seq, int D, float rope_theta, void* stream);
 int amqb_attn_decode(const void* qkv, void* k_cache, void* v_cache, void* out,
                      const int* pos_dev, int B, int Hq, int Hkv, int D, int max_seq,
-                     float rope_theta, void* stream);
+                     float rope_theta, const float* rope_cos_sin, void* stream);
 /* fp16 GEMV for the unquantised lm_head with fused final RMSNorm prologue:
  * logits fp32 [M, V] = rmsnorm(x) @ W^T. */
 int amqb_lm_head(const void* W_f16, const void* x, const void* gamma, float eps,
