@@ -53,6 +53,8 @@ static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, 
   int S = 1;
   while (S < kMaxCluster && max_rb * S * 2 <= B && S * 2 <= min_g) S *= 2;
   L.S = S;
+  L.log2S = 0;
+  while ((1 << L.log2S) < S) ++L.log2S;
   int ncl = B / S;
   if (ncl > max_rb) ncl = max_rb;
   if (ncl < 1) ncl = 1;

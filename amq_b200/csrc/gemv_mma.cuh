@@ -59,7 +59,8 @@ struct GemvLaunch {
   DevProblem prob[kMaxProblems];
   int count;
   int M;
-  int S;                 // cluster size = K split
+  int S;                 // cluster size = K split (power of two)
+  int log2S;
   int n_stages;          // ring depth
   int stage_bytes;
   int xprime_bytes;      // x' region
@@ -286,6 +287,7 @@ template <int BITS, int NB, bool M1>
 __device__ __forceinline__ void process_record(const uint8_t* rec, const uint8_t* xpg, const float* xsg, int M,
                                                int lane, float (&acc)[2][NB][4]) {
   constexpr int NW = words_per_tile(BITS), NV = vecs_per_rec(BITS), NM = mmas_per_group(BITS);
+  if (M1) M = 1;                              // compile-time addressing of the B fragments at batch 1
   const int g = lane >> 2, t = lane & 3;
   uint32_t w[2 * NW];
   const uint4* cv = reinterpret_cast<const uint4*>(rec);
@@ -399,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = L.S;
   const int rank = S > 1 ? (int)cluster_ctarank() : 0;
-  const int cid = blockIdx.x / S, ncl = gridDim.x / S;
+  const int cid = blockIdx.x >> L.log2S, ncl = gridDim.x >> L.log2S;
   const int NS = L.n_stages;
   const int M = L.M;
 
@@ -429,7 +431,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
       for (int p = 0; p < L.count; ++p) {
         const DevProblem& P = L.prob[p];
         const uint32_t rbytes = rec_bytes(P.bits);
-        const int g_lo = (P.n_g * rank) / S, g_hi = (P.n_g * (rank + 1)) / S;
+        const int g_lo = (P.n_g * rank) >> L.log2S, g_hi = (P.n_g * (rank + 1)) >> L.log2S;
         for (int c_lo = g_lo; c_lo < g_hi; c_lo += P.kc) {
           const int c_hi = (c_lo + P.kc) < g_hi ? (c_lo + P.kc) : g_hi;
           for (int rb = cid; rb < P.n_rb; rb += ncl) {
@@ -462,7 +464,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
     for (int p = 0; p < L.count; ++p) {
       const DevProblem& P = L.prob[p];
       if (cid >= P.n_rb) continue;
-      const int g_lo = (P.n_g * rank) / S, g_hi = (P.n_g * (rank + 1)) / S;
+      const int g_lo = (P.n_g * rank) >> L.log2S, g_hi = (P.n_g * (rank + 1)) >> L.log2S;
       const bool chunked = (g_hi - g_lo) > P.kc;
       for (int c_lo = g_lo; c_lo < g_hi; c_lo += P.kc) {
         const int c_hi = (c_lo + P.kc) < g_hi ? (c_lo + P.kc) : g_hi;
@@ -549,7 +551,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
     const DevProblem& P = L.prob[p];
     const uint32_t rbytes = rec_bytes(P.bits);
     const int NM = mmas_per_group(P.bits);
-    const int g_lo = (P.n_g * rank) / S, g_hi = (P.n_g * (rank + 1)) / S;
+    const int g_lo = (P.n_g * rank) >> L.log2S, g_hi = (P.n_g * (rank + 1)) >> L.log2S;
     const bool chunked = (g_hi - g_lo) > P.kc;
     AMQB_STAMP(4 + 4 * p);
     const bool same_x = (P.x == cur_x) && (P.K == cur_K);
