@@ -197,7 +197,7 @@ template <int MAXM>
 __global__ void __launch_bounds__(256)
 lm_head_kernel(const __half* __restrict__ W, const __half* __restrict__ x, const __half* __restrict__ gamma,
                float eps, float* __restrict__ logits, int M, int V, int K) {
-  extern __shared__ float xs[];   // [M][K]
+  extern __shared__ __half xs[];   // [M][K] normalised activations (fp16, as the HF model feeds lm_head)
   __shared__ float ssq[8];
   pdl_launch_dependents();
   pdl_wait();
@@ -205,8 +205,9 @@ lm_head_kernel(const __half* __restrict__ W, const __half* __restrict__ x, const
   for (int m = 0; m < M; ++m) {
     float ss = 0.f;
     for (int i = threadIdx.x; i < K; i += 256) {
-      const float v = __half2float(x[(size_t)m * K + i]);
-      xs[m * K + i] = v;
+      const __half hv = x[(size_t)m * K + i];
+      const float v = __half2float(hv);
+      xs[m * K + i] = hv;
       ss += v * v;
     }
     if (gamma) {
@@ -219,8 +220,8 @@ lm_head_kernel(const __half* __restrict__ W, const __half* __restrict__ x, const
       for (int w = 0; w < 8; ++w) t += ssq[w];
       const float rs = rsqrtf(t / (float)K + eps);
       for (int i = threadIdx.x; i < K; i += 256) {
-        const __half xn = __float2half_rn(xs[m * K + i] * rs);
-        xs[m * K + i] = __half2float(__hmul(gamma[i], xn));
+        const __half xn = __float2half_rn(__half2float(xs[m * K + i]) * rs);
+        xs[m * K + i] = __hmul(gamma[i], xn);
       }
       __syncthreads();
     }
@@ -243,9 +244,10 @@ lm_head_kernel(const __half* __restrict__ W, const __half* __restrict__ x, const
 #pragma unroll
       for (int m = 0; m < MAXM; ++m) {
         if (m < M) {
-          const float4 a = *reinterpret_cast<const float4*>(&xs[m * K + 8 * i]);
-          const float4 c = *reinterpret_cast<const float4*>(&xs[m * K + 8 * i + 4]);
-          acc[m] += wf[0] * a.x + wf[1] * a.y + wf[2] * a.z + wf[3] * a.w + wf[4] * c.x + wf[5] * c.y + wf[6] * c.z + wf[7] * c.w;
+          const uint4 xv = *reinterpret_cast<const uint4*>(&xs[m * K + 8 * i]);
+          const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+          const float2 a0 = __half22float2(xh[0]), a1 = __half22float2(xh[1]), a2 = __half22float2(xh[2]), a3 = __half22float2(xh[3]);
+          acc[m] += wf[0] * a0.x + wf[1] * a0.y + wf[2] * a1.x + wf[3] * a1.y + wf[4] * a2.x + wf[5] * a2.y + wf[6] * a3.x + wf[7] * a3.y;
         }
       }
     }
@@ -336,8 +338,14 @@ int amqb_attn_decode(const void* qkv, void* k_cache, void* v_cache, void* out, c
 int amqb_lm_head(const void* W_f16, const void* x, const void* gamma, float eps, float* logits, int M, int V, int K,
                  void* stream) {
   if (!W_f16 || !x || !logits || M < 1 || M > 16 || K % 8) return fail(AMQB_ERR_BAD_ARG, "lm_head: bad argument (M 1..16, K % 8)");
-  const size_t smem = (size_t)M * K * sizeof(float);
-  if (smem > 200 * 1024) return fail(AMQB_ERR_UNSUPPORTED_SHAPE, "lm_head: M*K too large for shared memory");
+  if ((size_t)M * K * sizeof(__half) > 200 * 1024) {      // serve the rows in halves (the head is re-read per half)
+    const int h1 = M / 2;
+    if (h1 < 1) return fail(AMQB_ERR_UNSUPPORTED_SHAPE, "lm_head: K too large for shared memory");
+    int rc = amqb_lm_head(W_f16, x, gamma, eps, logits, h1, V, K, stream);
+    if (rc) return rc;
+    return amqb_lm_head(W_f16, (const __half*)x + (size_t)h1 * K, gamma, eps, logits + (size_t)h1 * V, M - h1, V, K, stream);
+  }
+  const size_t smem = (size_t)M * K * sizeof(__half);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
