@@ -171,6 +171,7 @@ def gemv_roofline(model, iters: int = 5):
 def run_ours(args, shape, arch):
     import torch
     import torch.distributed as dist
+    from amq_b200.arch import get_bits_usage
     from amq_b200.model import QuantDecoder
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -248,14 +249,19 @@ def run_ours(args, shape, arch):
         cpu_desc = cpu_runs[0][1]
         cpu_tok_s = 1.0 / (sum(r[0] for r in cpu_runs[2:]) / len(cpu_runs[2:]))
         tok_s = world * B * args.steps / (ms_dev * 1e-3)
+        traffic = None            # dram bytes per launch (average over one layer's four launches), from the committed ncu capture
+        tp_ = os.path.join(ROOT, "profiles", "r01_ncu_gemv_traffic.json")
+        if os.path.exists(tp_):
+            with open(tp_) as f:
+                traffic = json.load(f).get("traffic_bytes_per_launch_avg")
         line = {
             "metric": "batch-1 decode tok/s, Llama-2 7B AMQ 3-bit avg", "value": tok_s, "unit": "tok/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 (fp32 accumulate)",
             "data": "synthetic",
-            "config": {"workload": f"{shape.name} random-init, AMQ mixed 2/3/4-bit avg "
-                                   f"{sum(sum(v) for v in arch.values()) / sum(len(v) for v in arch.values()):.2f} code bits "
-                                   "(synthetic arch, seed 0; 3.0 incl. 0.25 b scale/zero), batch-1 decode, group 128",
+            "config": {"workload": f"{shape.name} random-init, AMQ mixed 2/3/4-bit, bits_usage "
+                                   f"{get_bits_usage({'linear': arch}, shape.config()):.2f} (synthetic arch drawn like the search space, "
+                                   "seed 0; func.py accounting incl. 0.25 b scale/zero), batch-1 decode, group 128",
                        "l2": "inputs larger than L2: every step streams %.2f GB of packed weights + fp16 lm_head" % (bytes_tok["total"] / 1e9),
                        "parallelism": "replicas only (no data-path collective)" if world > 1 else "single GPU",
                        "launches_per_step": launches_per_step, "cuda_graph": True, "pdl": model.pdl},
@@ -264,7 +270,7 @@ def run_ours(args, shape, arch):
                     "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 8 * B},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "algorithmic_bytes_per_launch": g_bytes / g_launch, "peak_source": peak_src,
                          "kernel": "gemv_mma_kernel<bits,..> (decode GEMV family, %d launches per step)" % g_launch,
                          "algorithmic_bytes_per_step": g_bytes, "avg_launch_us": g_ms * 1e3 / g_launch,
                          "step_frac_of_weight_roofline": (bytes_tok["total"] / (peak * 1e9)) / (ms_dev / args.steps * 1e-3)},
