@@ -79,6 +79,13 @@ static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, 
   }
   L.accbuf_blocks = acc_blocks;
   {
+    int rot = 0;                               // rotate where each problem's remainder blocks land
+    for (int i = 0; i < count; ++i) {
+      L.prob[i].rot = rot;
+      rot = (rot + L.prob[i].n_rb) % ncl;
+    }
+  }
+  {
     const char* e = getenv("AMQB_COPY_RECS");
     L.copy_recs = e ? atoi(e) : 4;
     if (L.copy_recs < 1) L.copy_recs = 1;

@@ -52,6 +52,8 @@ struct DevProblem {
   int bits, N, K, ldx, ldy, prologue;
   int n_rb, n_g;
   int kc;                // groups per x' chunk (K is walked chunk by chunk when x' would not fit)
+  int rot;               // row block rb goes to cluster (rb + rot) % ncl: spreads the remainder blocks of
+                         // consecutive problems over different CTAs
   int build_mask;        // bit b set: build the x' variant of bit width b when this problem starts (0: reuse)
 };
 
@@ -377,6 +379,11 @@ __device__ __forceinline__ void process_record(const uint8_t* rec, const uint8_t
   }
 }
 
+__device__ __forceinline__ int first_rb(int cid, int rot, int ncl) {
+  const int r = cid - rot;
+  return r < 0 ? r + ncl : r;
+}
+
 __device__ __forceinline__ void store_out(const DevProblem& P, int n, int col, float v) {
   if (P.bias) v += __half2float(P.bias[n]);
   if (P.residual) v += __half2float(P.residual[(size_t)col * P.ldy + n]);
@@ -434,7 +441,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
         const int g_lo = (P.n_g * rank) >> L.log2S, g_hi = (P.n_g * (rank + 1)) >> L.log2S;
         for (int c_lo = g_lo; c_lo < g_hi; c_lo += P.kc) {
           const int c_hi = (c_lo + P.kc) < g_hi ? (c_lo + P.kc) : g_hi;
-          for (int rb = cid; rb < P.n_rb; rb += ncl) {
+          for (int rb = first_rb(cid, P.rot, ncl); rb < P.n_rb; rb += ncl) {
             const uint8_t* src = P.w + ((size_t)rb * P.n_g + c_lo) * rbytes;
             for (int g = c_lo; g < c_hi; g += kStageRecs) {
               const int nrec = (c_hi - g) < kStageRecs ? (c_hi - g) : kStageRecs;
@@ -463,14 +470,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
     int nblk = 0;
     for (int p = 0; p < L.count; ++p) {
       const DevProblem& P = L.prob[p];
-      if (cid >= P.n_rb) continue;
+      if (first_rb(cid, P.rot, ncl) >= P.n_rb) continue;
       const int g_lo = (P.n_g * rank) >> L.log2S, g_hi = (P.n_g * (rank + 1)) >> L.log2S;
       const bool chunked = (g_hi - g_lo) > P.kc;
       for (int c_lo = g_lo; c_lo < g_hi; c_lo += P.kc) {
         const int c_hi = (c_lo + P.kc) < g_hi ? (c_lo + P.kc) : g_hi;
         const bool first_chunk = c_lo == g_lo, last_chunk = c_hi == g_hi;
         int j = 0;
-        for (int rb = cid; rb < P.n_rb; rb += ncl, ++nblk, ++j) {
+        for (int rb = first_rb(cid, P.rot, ncl); rb < P.n_rb; rb += ncl, ++nblk, ++j) {
           const int buf = nblk & 1, use = nblk >> 1;
             mbar_wait(smem_u32(&bars[28 + buf]), use & 1);
             const float* rbase = red + (size_t)buf * kCW * 2 * NB * 128;
@@ -557,7 +564,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
     const bool same_x = (P.x == cur_x) && (P.K == cur_K);
     if (!same_x) { built_mask = 0; cur_x = P.x; cur_K = P.K; stat_par ^= 1; }   // new x: new statistics buffer
     if (P.build_mask) run_mask = P.build_mask;
-    if (cid >= P.n_rb) continue;          // (after the bookkeeping: a later problem may rely on this run's mask)
+    if (first_rb(cid, P.rot, ncl) >= P.n_rb) continue;          // (after the bookkeeping: a later problem may rely on this run's mask)
     uint8_t* xpv = xp + (L.xp_variants == 3 ? (size_t)(P.bits - 2) * L.xprime_bytes : 0);
     for (int c_lo = g_lo; c_lo < g_hi; c_lo += P.kc) {
       const int c_hi = (c_lo + P.kc) < g_hi ? (c_lo + P.kc) : g_hi;
@@ -572,7 +579,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
       if (L.dbg_delay_ns) { const long long t_end = gtime() + L.dbg_delay_ns; while (gtime() < t_end) {} }
       AMQB_STAMP(5 + 4 * p);
       int j = 0;
-      for (int rb = cid; rb < P.n_rb; rb += ncl, ++nblk, ++j) {
+      for (int rb = first_rb(cid, P.rot, ncl); rb < P.n_rb; rb += ncl, ++nblk, ++j) {
 #pragma unroll
         for (int a = 0; a < 2; ++a)
 #pragma unroll

@@ -233,6 +233,7 @@ lm_head_kernel(const __half* __restrict__ W, const __half* __restrict__ x, const
     float acc[MAXM];
 #pragma unroll
     for (int m = 0; m < MAXM; ++m) acc[m] = 0.f;
+#pragma unroll 4
     for (int i = lane; i < K / 8; i += 32) {
       uint4 wv;
       asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
