@@ -278,7 +278,10 @@ extern "C" {
 size_t amqb_gemm_workspace_bytes(int M, int K, int bits) {
   (void)bits;
   if (M <= 0 || K <= 0) return 0;
-  return (size_t)((M + 127) / 128) * 128 * (size_t)K * 2 + 256;
+  // pre-swizzled activations for the tcgen05 kernel, or (fallback path) the decode kernel's M > 1 workspace
+  const size_t swz = (size_t)((M + 127) / 128) * 128 * (size_t)K * 2 + 256;
+  const size_t dec = amqb_workspace_bytes(1, K, 16);
+  return swz > dec ? swz : dec;
 }
 
 int amqb_gemm_tc(int bits, const void* w_native, const void* x, void* y, const void* bias, int M, int N, int K,

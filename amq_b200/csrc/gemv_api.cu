@@ -20,7 +20,13 @@ static int sm_count() {
 }
 
 // One launch: problems sharing M and prologue kind (bit widths may differ).
-static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, cudaStream_t st) {
+static size_t xg_run_bytes(int K, int M) {
+  const int n_g = K / kGroup, NB = M <= 8 ? 1 : 2;
+  return (((size_t)n_g * NB * 8 * 4 + 255) & ~size_t(255)) + (size_t)n_g * (8 + 9 + 8) * M * 32;
+}
+
+static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, cudaStream_t st, void* workspace,
+                        size_t workspace_bytes) {
   GemvLaunch L{};
   const int M = pr[0]->M, pro = pr[0]->prologue;
   const int NB = M <= 8 ? 1 : 2;
@@ -47,6 +53,42 @@ static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, 
     P.build_mask = 0;
     if (first)
       for (int j = i; j < count && L.prob[j].x == P.x && L.prob[j].K == P.K; ++j) P.build_mask |= 1 << L.prob[j].bits;
+  }
+  // M > 1: x' is built once per launch into the workspace by a pre-pass kernel (one per run of problems
+  // sharing x) and fetched by the CTAs with bulk copies; M == 1 builds it inside the CTA
+  if (M > 1) {
+    size_t off = 0;
+    for (int i = 0; i < count; ++i) {
+      DevProblem& P = L.prob[i];
+      if (P.build_mask == 0) {                      // later member of a run: share the first member's buffers
+        int f = i - 1;
+        while (L.prob[f].build_mask == 0) --f;
+        const int n_g = P.n_g;
+        const uint8_t* base = (const uint8_t*)L.prob[f].xsg;
+        const size_t xs_b = ((size_t)n_g * NB * 8 * 4 + 255) & ~size_t(255);
+        const size_t voff[3] = {0, (size_t)n_g * 8 * M * 32, (size_t)n_g * 17 * M * 32};
+        P.xsg = L.prob[f].xsg;
+        P.xg = base + xs_b + voff[P.bits - 2];
+        continue;
+      }
+      const size_t need = xg_run_bytes(P.K, M);
+      if (!workspace || off + need > workspace_bytes || ((uintptr_t)workspace & 255))
+        return fail(AMQB_ERR_WORKSPACE, "gemv: M > 1 needs a 256-byte aligned workspace of amqb_workspace_bytes()");
+      uint8_t* base = (uint8_t*)workspace + off;
+      off += (need + 255) & ~size_t(255);
+      const int n_g = P.n_g;
+      const size_t xs_b = ((size_t)n_g * NB * 8 * 4 + 255) & ~size_t(255);
+      XgArgs X{};
+      X.x = P.x; X.gamma = P.gamma; X.eps = P.eps; X.ldx = P.ldx; X.K = P.K; X.M = M; X.NB = NB; X.mask = P.build_mask;
+      X.xsg = (float*)base;
+      X.xg[0] = base + xs_b;
+      X.xg[1] = base + xs_b + (size_t)n_g * 8 * M * 32;
+      X.xg[2] = base + xs_b + (size_t)n_g * 17 * M * 32;
+      int rc = pro == AMQB_PRO_NONE ? launch_xg0(X, pdl, st) : (pro == AMQB_PRO_RMSNORM ? launch_xg1(X, pdl, st) : launch_xg2(X, pdl, st));
+      if (rc) return rc;
+      P.xsg = X.xsg;
+      P.xg = X.xg[P.bits - 2];
+    }
   }
   // K split across a cluster only when N is too small to occupy the chip (each cluster then owns at
   // most one row block per problem, which is what the DSMEM hand-off assumes)
@@ -95,9 +137,9 @@ static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, 
   const int stage_recs = max_slice < kStageRecs ? max_slice : kStageRecs;
   L.stage_bytes = stage_recs * max_rec;
   L.xprime_bytes = (max_xp + 127) & ~127;
-  L.xp_variants = (count > 1 && 3 * L.xprime_bytes <= 96 * 1024) ? 3 : 1;
+  L.xp_variants = (M == 1 && count > 1 && 3 * L.xprime_bytes <= 96 * 1024) ? 3 : 1;
   L.xs_floats = (max_kc * NB * 8 + 31) & ~31;
-  const size_t fixed = 256 + (size_t)L.xs_floats * 4 + 16 * kCW * 4 + (size_t)L.xp_variants * L.xprime_bytes +
+  const size_t fixed = 384 + (size_t)L.xs_floats * 4 + 16 * kCW * 4 + (size_t)L.xp_variants * L.xprime_bytes +
                        (size_t)2 * kCW * 2 * NB * 128 * 4 + (size_t)acc_blocks * 2 * NB * 128 * 4 +
                        (S > 1 ? (size_t)count * S * 2 * NB * 128 * 4 : 0) + 128;
   if (fixed + 2 * (size_t)L.stage_bytes > (size_t)kSmemTarget)
@@ -124,17 +166,19 @@ int amqb_debug_set_timeline(void* buf) {
   return AMQB_OK;
 }
 
-/* The decode kernels need no global workspace (all reductions stay on chip: shared memory within
- * a CTA, distributed shared memory within a cluster); the entry points keep the parameter so the
- * ABI stays stable.  A small non-zero size is returned so callers can keep one buffer per stream. */
+/* Reductions never leave the chip (shared memory within a CTA, distributed shared memory within a
+ * cluster), so batch-1 launches need no workspace.  For M > 1 the workspace holds the permuted
+ * activations built once per launch by the pre-pass kernel. */
 size_t amqb_workspace_bytes(int max_N, int max_K, int max_M) {
   if (max_N <= 0 || max_K <= 0 || max_M <= 0) return 0;
-  return 256;
+  if (max_M > 16) max_M = 16;
+  if (max_M == 1) return 256;
+  const int K = ((max_K + kGroup - 1) / kGroup) * kGroup;
+  return kMaxProblems * ((xg_run_bytes(K, max_M) + 255) & ~size_t(255));
 }
 
 int amqb_gemv_grouped(const amqb_gemv_problem* pr, int count, void* workspace, size_t workspace_bytes, int pdl,
                       void* stream) {
-  (void)workspace; (void)workspace_bytes;
   if (!pr || count < 1 || count > kMaxProblems) return fail(AMQB_ERR_BAD_ARG, "gemv: bad argument");
   const int M = pr[0].M;
   if (M < 1 || M > 16) return fail(AMQB_ERR_BAD_ARG, "gemv: M must be 1..16 (use amqb_gemm_tc for prefill)");
@@ -158,7 +202,7 @@ int amqb_gemv_grouped(const amqb_gemv_problem* pr, int count, void* workspace, s
     int n = 0;
     for (int j = i; j < count; ++j)
       if (!done[j] && pr[j].prologue == pr[i].prologue) { sub[n++] = &pr[j]; done[j] = true; }
-    const int rc = launch_group(sub, n, pdl, (cudaStream_t)stream);
+    const int rc = launch_group(sub, n, pdl, (cudaStream_t)stream, workspace, workspace_bytes);
     if (rc) return rc;
   }
   return AMQB_OK;

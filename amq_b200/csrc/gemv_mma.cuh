@@ -52,6 +52,8 @@ struct DevProblem {
   int bits, N, K, ldx, ldy, prologue;
   int n_rb, n_g;
   int kc;                // groups per x' chunk (K is walked chunk by chunk when x' would not fit)
+  const uint8_t* xg;     // M > 1: this problem's x' variant, built once per launch by xprime_global_kernel
+  const float* xsg;      //        and the matching group sums (NULL at M = 1: built inside the CTA)
   int rot;               // row block rb goes to cluster (rb + rot) % ncl: spreads the remainder blocks of
                          // consecutive problems over different CTAs
   int build_mask;        // bit b set: build the x' variant of bit width b when this problem starts (0: reuse)
@@ -285,6 +287,82 @@ __device__ __forceinline__ void build_xprime(const DevProblem& P, int M, int NB,
 }
 
 // ---------------------------------------------------------------------------------------------
+// M > 1: the permuted / pre-scaled activations are built ONCE per launch into global memory (one CTA
+// per activation row) instead of once per CTA; the GEMV CTAs then fetch their chunks with bulk copies.
+struct XgArgs {
+  const __half* x;
+  const __half* gamma;
+  float eps;
+  int ldx, K, M, NB, mask;
+  uint8_t* xg[3];        // x' of the 2 / 3 / 4-bit variants: [group][mmas][M][32 B]
+  float* xsg;            // [group][NB*8] group sums * 2^-24 (padded columns zero)
+};
+
+template <int PRO>
+__global__ void __launch_bounds__(kCThreads) xprime_global_kernel(const XgArgs A) {
+  __shared__ float sred[kCW];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int col = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_g = A.K / kGroup;
+  float rs = 1.f;
+  if (PRO == AMQB_PRO_RMSNORM) {
+    float ss = 0.f;
+    const uint2* xr = reinterpret_cast<const uint2*>(A.x + (size_t)col * A.ldx);
+    for (int i = threadIdx.x; i < A.K / 4; i += kCThreads) {
+      const uint2 v = xr[i];
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+      const float2 b2 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+      ss += a.x * a.x + a.y * a.y + b2.x * b2.x + b2.y * b2.y;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) sred[warp] = ss;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kCW; ++w) t += sred[w];
+    rs = rsqrtf(t / (float)A.K + A.eps);
+  }
+  for (int gl = warp; gl < n_g; gl += kCW) {
+    const int kbase = gl * kGroup + 4 * lane;
+    uint2 a = *reinterpret_cast<const uint2*>(A.x + (size_t)col * A.ldx + kbase), b = make_uint2(0u, 0u);
+    if (PRO == AMQB_PRO_SILU_MUL) b = *reinterpret_cast<const uint2*>(A.x + (size_t)col * A.ldx + A.K + kbase);
+    else if (PRO == AMQB_PRO_RMSNORM) b = *reinterpret_cast<const uint2*>(A.gamma + kbase);
+    __half2 lo, hi;
+    finish_item<PRO>(a, b, rs, lo, hi);
+    if (A.mask & 4) place_item<2>(A.xg[0] + (size_t)gl * 8 * A.M * 32, A.M, col, lane, lo, hi);
+    if (A.mask & 8) place_item<3>(A.xg[1] + (size_t)gl * 9 * A.M * 32, A.M, col, lane, lo, hi);
+    if (A.mask & 16) place_item<4>(A.xg[2] + (size_t)gl * 8 * A.M * 32, A.M, col, lane, lo, hi);
+    const float2 f0 = __half22float2(lo), f1 = __half22float2(hi);
+    float sum = (f0.x + f0.y) + (f1.x + f1.y);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) A.xsg[gl * A.NB * 8 + col] = sum * 5.9604644775390625e-08f;
+    if (col == 0 && lane >= A.M && lane < A.NB * 8) A.xsg[gl * A.NB * 8 + lane] = 0.f;     // padded columns
+  }
+}
+
+template <int PRO>
+static int launch_xprime_global(const XgArgs& A, int pdl, cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(A.M);
+  cfg.blockDim = dim3(kCThreads);
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, xprime_global_kernel<PRO>, A);
+  if (e != cudaSuccess) {
+    set_error("xprime pre-pass launch: %s", cudaGetErrorString(e));
+    return AMQB_ERR_LAUNCH;
+  }
+  return AMQB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 template <int BITS, int NB, bool M1>
 __device__ __forceinline__ void process_record(const uint8_t* rec, const uint8_t* xpg, const float* xsg, int M,
                                                int lane, float (&acc)[2][NB][4]) {
@@ -395,8 +473,8 @@ template <int NB, bool M1, int PRO>
 __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_constant__ GemvLaunch L) {
   extern __shared__ __align__(1024) uint8_t smem[];
   // smem map: [0,256) barriers | xs | sred | x' | red[2] | accbuf | part[4][S] | ring
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);      // [0,NS) full, [NS,2NS) empty, [24,28) cluster-reduce
-  float* xs = reinterpret_cast<float*>(smem + 256);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);      // [0,NS) full, [NS,2NS) empty, [24,28) cluster-reduce, 28..32 misc
+  float* xs = reinterpret_cast<float*>(smem + 384);
   float* sred = xs + L.xs_floats;                           // 16 * kCW floats
   uint8_t* xp = reinterpret_cast<uint8_t*>(sred + 16 * kCW);
   float* red = reinterpret_cast<float*>(xp + (size_t)L.xp_variants * L.xprime_bytes);   // [2][kCW][2*NB*128]
@@ -423,6 +501,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
       mbar_init(smem_u32(&bars[28 + i]), kCW);   // red_full[buf]: every consumer warp deposited its partial sums
       mbar_init(smem_u32(&bars[30 + i]), 1);     // red_free[buf]: the reducing warp is done with the buffer
     }
+    mbar_init(smem_u32(&bars[32]), 1);           // x' chunk landed (M > 1 path)
     fence_mbar_init();
   }
   if (S > 1) cluster_sync_all();   // barriers initialised and peers' shared memory live before any DSMEM traffic
@@ -553,6 +632,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
   int s = 0, ph = 0, nblk = 0;
   const __half* cur_x = nullptr;     // x' cache: problems of a group that share x (q/k/v, gate/up)
   int cur_K = 0, built_mask = 0, stat_par = 0, run_mask = 0;
+  uint32_t xphase = 0;
   float rs1 = 1.f;
   for (int p = 0; p < L.count; ++p) {
     const DevProblem& P = L.prob[p];
@@ -571,11 +651,25 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
       const bool first_chunk = c_lo == g_lo, last_chunk = c_hi == g_hi;
       // x' variants to (re)build now: chunked K or a single variant buffer -> this problem's own; else
       // whatever the host scheduled at this problem (all bit widths of the problems sharing this x)
+      if (P.xg) {
+        // M > 1: x' of this chunk was built once for the whole grid; fetch it like the weights (TMA bulk copy)
+        named_bar_sync(1, kCThreads);              // every warp is done with the previous chunk's x'
+        const uint32_t xb = smem_u32(&bars[32]);
+        if (tid == 0) {
+          const uint32_t bx = (uint32_t)(c_hi - c_lo) * NM * M * 32, bs = (uint32_t)(c_hi - c_lo) * NB * 8 * 4;
+          mbar_expect_tx(xb, bx + bs);
+          bulk_g2s(smem_u32(xpv), P.xg + (size_t)c_lo * NM * M * 32, bx, xb);
+          bulk_g2s(smem_u32(xs), P.xsg + (size_t)c_lo * NB * 8, bs, xb);
+        }
+        mbar_wait(xb, xphase);
+        xphase ^= 1;
+      } else {
       const int want = (chunked || L.xp_variants != 3) ? (1 << P.bits) : ((run_mask | (1 << P.bits)) & ~built_mask);
       if (want)
         build_xprime<M1, PRO>(P, M, NB, S, c_lo, c_hi - c_lo, xp, xs, sred + ((M1 && stat_par) ? kCW : 0), warp, lane,
                               same_x && built_mask != 0, rs1, want, L.xp_variants, L.xprime_bytes);
       built_mask |= want | (1 << P.bits);
+      }
       if (L.dbg_delay_ns) { const long long t_end = gtime() + L.dbg_delay_ns; while (gtime() < t_end) {} }
       AMQB_STAMP(5 + 4 * p);
       int j = 0;
@@ -678,6 +772,9 @@ static int launch_pro(const GemvLaunch& L, int grid, size_t smem, int pdl, cudaS
 }
 
 int launch_pro0(const GemvLaunch& L, int grid, size_t smem, int pdl, cudaStream_t st);
+int launch_xg0(const XgArgs& A, int pdl, cudaStream_t st);
+int launch_xg1(const XgArgs& A, int pdl, cudaStream_t st);
+int launch_xg2(const XgArgs& A, int pdl, cudaStream_t st);
 int launch_pro1(const GemvLaunch& L, int grid, size_t smem, int pdl, cudaStream_t st);
 int launch_pro2(const GemvLaunch& L, int grid, size_t smem, int pdl, cudaStream_t st);
 

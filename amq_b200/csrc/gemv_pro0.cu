@@ -5,4 +5,5 @@ namespace amqb {
 int launch_pro0(const GemvLaunch& L, int grid, size_t smem, int pdl, cudaStream_t st) {
   return launch_pro<AMQB_PRO_NONE>(L, grid, smem, pdl, st);
 }
+int launch_xg0(const XgArgs& A, int pdl, cudaStream_t st) { return launch_xprime_global<AMQB_PRO_NONE>(A, pdl, st); }
 }  // namespace amqb

@@ -104,7 +104,7 @@ class QuantDecoder:
         self.pos = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.rope = torch.empty(max_seq, self.D // 2, 2, dtype=torch.float32, device=self.dev)
         check(lib().amqb_rope_table(ptr(self.rope), max_seq, self.D, ctypes.c_float(shape.rope_theta), cur_stream()), "rope_table")
-        self.ws = ops.workspace(self.dev)
+        self.ws = ops.workspace(self.dev, 4 * shape.inter, max(shape.inter, shape.hidden), batch)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.allreduce = None          # set by amq_b200.tp for tensor-parallel runs
         self.launches_per_step = 0

@@ -29,7 +29,7 @@ def workspace(device: torch.device, sum_N: int = 32768, max_K: int = 16384, max_
     dev = device.index if device.index is not None else torch.cuda.current_device()
     key = (dev, torch.cuda.current_stream(dev).cuda_stream)
     ws = _workspaces.get(key)
-    need = int(lib().amqb_workspace_bytes(sum_N, max_K, max_M))
+    need = max(int(lib().amqb_workspace_bytes(sum_N, max_K, max_M)), 256)
     if need == 0:
         raise RuntimeError("amq_b200: workspace request out of range")
     if ws is None or ws.numel() < need:

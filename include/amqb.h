@@ -60,9 +60,9 @@ int amqb_debug_set_timeline(void* buf);
  * per 32-row x 128-k record).  Requires N % 32 == 0, K % 128 == 0, G == 128.
  * Returns 0 for an unsupported shape. */
 size_t amqb_native_bytes(int bits, int N, int K);
-/* Bytes of the split-K workspace a decode launch may touch (fp32 partials +
- * int32 arrival counters).  The caller allocates it once, ZERO-FILLED, per
- * stream; the kernels leave the counters zeroed again. */
+/* Bytes of the per-stream workspace a decode launch may touch.  Batch-1 launches need none (256 is
+ * returned); for M > 1 it holds the permuted activations a pre-pass kernel builds once per launch.
+ * 256-byte aligned, no initialisation required. */
 size_t amqb_workspace_bytes(int max_N, int max_K, int max_M);
 
 /* ---- bit-exactness probe ---------------------------------------------- */
@@ -108,7 +108,7 @@ typedef struct {
 } amqb_gemv_problem;
 
 /* One launch over `count` independent problems sharing M (q/k/v or gate/up, mixed bit-widths
- * allowed).  workspace: amqb_workspace_bytes() bytes, zero-filled once.  pdl != 0 launches with
+ * allowed).  workspace: amqb_workspace_bytes() bytes.  pdl != 0 launches with
  * programmatic stream serialization (weights prefetch overlaps the previous kernel's tail). */
 int amqb_gemv_grouped(const amqb_gemv_problem* problems_host, int count,
                       void* workspace, size_t workspace_bytes, int pdl, void* stream);
