@@ -55,6 +55,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}" ::"r"(bar), "r"(parity), "r"(0x989680) : "memory");   // suspend-time hint: sleep, do not spin
 }
+// same, default (short) suspend window: lower wake-up latency for single-thread pipeline roles
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
 // global -> shared bulk copy, completion signalled on an mbarrier (bytes % 16 == 0)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile(

@@ -4,17 +4,26 @@
 // GPTQLinear.forward (amq/kernel/hqq/hqq/backends/autogptq.py:245-283) for 2/3/4 bits.
 //
 //   Y[M,N] = X[M,K] . W^T,  computed as  D[128 n, 128 m] += A[128 n, 16 k] . B[128 m, 16 k]^T
-//   A = dequantised weights (fp16, K-major, SWIZZLE_128B) written to shared memory by CUDA cores,
+//   A = dequantised weights, fp16, written by CUDA cores straight into TMEM (tcgen05.st.16x128b: its register
+//       layout is the mma fragment layout the native records are already stored in) — the A operand never
+//       touches shared memory, which is the bandwidth that bounded the first (A-in-smem) version,
 //   B = activations (fp16, K-major, SWIZZLE_128B) bulk-copied from a pre-swizzled copy of X,
 //   D = fp32 accumulator in TMEM (128 lanes x 128 columns), read back with tcgen05.ld.
 //
-// One CTA = one 128(n) x 128(m) output tile, 12 warps:
-//   warp 0  producer   cp.async.bulk: 4 packed weight records + 2 activation atoms per 128-k block
-//   warp 1  MMA issuer one thread: 8 x tcgen05.mma.cta_group::1.kind::f16 per k block, tcgen05.commit
-//   warp 2  TMEM allocator
-//   warps 4..11        dequant (one 16-row tile each per k block: AND|magic -> HSUB2 -> HFMA2 with the
-//                      group's scale / zero*scale -> conflict-free STS into the swizzled A tile), then
-//                      the epilogue (tcgen05.ld 32x32b, + bias, fp16 stores coalesced along n).
+// One CTA = one 128(n) x 128(m) output tile, 20 warps:
+//   warp 0  W producer cp.async.bulk: the n tile's 4 packed weight records per 128-k block (deep ring, ~10 stages)
+//   warp 3  X producer cp.async.bulk: 2 pre-swizzled activation atoms per k block (5 stages x 32 KB)
+//   warp 1  MMA issuer the whole warp runs the loop so descriptors stay in uniform registers; one elected lane issues
+//                      8 x tcgen05.mma.cta_group::1.kind::f16 (A from TMEM) per k block + one tcgen05.commit
+//   warp 2  TMEM allocator (512 columns: 128 accumulator + 5 A stages x 64)
+//   warps 4..19        dequant: a warp may only touch the TMEM lanes of its quarter (warp & 3) = one 32-row record;
+//                      per quarter two warps take the record's two 16-row tiles on even k blocks, two on odd ones:
+//                      AND|magic -> HSUB2 -> HFMA2 with the group's scale / zero*scale -> tcgen05.st.16x128b.
+//                      Then the epilogue (tcgen05.ld 32x32b, + bias, fp16 stores coalesced along n).
+// What bounds it (B200, traced with AMQB_TC_DBG=16): tcgen05.mma issue back-pressures at the tensor rate (8 MMAs =
+// ~500 clk), the issuing warp's wait + commit add ~150-280 clk per k block, and the X ring (160 KB) is just one
+// bulk-copy round trip (~2000 clk) deep at that pace.  Next steps: cta_group::2 (half the X footprint per SM) and a
+// second issuer with its own accumulator.
 // fp16 operands (the reference is fp16 end to end; bf16 weights would break the 1e-3 bound),
 // fp32 accumulation; each weight is rounded once (single HFMA2 from the exact integer code).
 // Shapes the kernel does not take (N % 128 != 0) go through the 16-row slabs of the decode kernel.
@@ -22,12 +31,25 @@
 
 namespace amqb {
 
-constexpr int kTcThreads = 384;
+constexpr int kTcThreads = 640;                    // 4 service warps + 16 dequant warps
 constexpr int kTileN = 128, kTileM = 128, kBlockK = 128;
-constexpr int kWStages = 4, kXStages = 3, kAStages = 2;
+// Every ring is latency-bound, not bandwidth-bound: a stage is reusable one bulk-copy round trip (~1.3 us) after its
+// MMAs retire, so depth = round trip / 0.27 us per k block.  W stages are small: as many as shared memory still holds.
+// A (TMEM) and X (shared memory) share one stage ring: one "full" barrier (8 dequant warps + the X bytes) and one
+// "done" barrier (tcgen05.commit) per k block keep the single MMA-issuing thread's serial overhead small.
+constexpr int kWStagesMax = 12, kStages = 5;
+constexpr int kWStages = kWStagesMax;              // barrier slots reserved
+constexpr int kXStages = kStages, kAStages = kStages;
 constexpr int kAtomBytes = 128 * 128;              // 128 rows x 128 B (64 fp16 of K)
-constexpr int kABytes = 2 * kAtomBytes;            // 128 k = two swizzle atoms
-constexpr int kXBytes = 2 * kAtomBytes;
+constexpr int kXBytes = 2 * kAtomBytes;            // 128 k = two swizzle atoms
+// TMEM columns: [0, 128) fp32 accumulator, then kAStages x 64 columns of A (128 k of fp16, two per column)
+constexpr int kTmemCols = 512, kTmemA0 = 128, kTmemAStage = 64;
+static_assert(kTmemA0 + kAStages * kTmemAStage <= kTmemCols, "TMEM columns");
+constexpr int kTcHeader = 4096;                    // barriers, tmem slot, debug trace
+constexpr int kTcSmemMax = 232448;                 // 227 KB opt-in limit per CTA
+// mbarrier slots
+constexpr int kBarWFull = 0, kBarWEmpty = kBarWFull + kWStages, kBarFull = kBarWEmpty + kWStages,
+              kBarDone = kBarFull + kStages, kBarAcc = kBarDone + kStages;
 
 // ---- tcgen05 / TMEM PTX ------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
@@ -46,6 +68,47 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand read from TMEM (lane = row, one 32-bit column = two consecutive k), B from shared memory
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 16 TMEM lanes x 32 columns: register 2n -> (lane g, column 4n + t), 2n+1 -> (lane g + 8, column 4n + t), g = lane >> 2, t = lane & 3
+__device__ __forceinline__ void tmem_st_16x128b_x8(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x128b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+// commit that arrives on the same barrier offset in every CTA of `mask` (cluster pair sharing the X stages)
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+// bulk copy replicated into the same shared-memory offset (data and mbarrier) of every CTA in `mask`
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+      ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t tc_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void tc_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
+// one lane of a converged warp (warp-uniform operands then stay in uniform registers: no R2UR chain per MMA)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -72,6 +135,7 @@ constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kTileM >> 3) << 17) | ((uint
 // ---- activations: pre-swizzled copy of X so that a plain bulk copy lands in the UMMA layout -------
 // Xs[m_tile][k_atom][128 rows][128 B], 16-byte chunk c of row r stored at chunk (c ^ (r & 7)); rows >= M are zero.
 __global__ void swizzle_x_kernel(const __half* __restrict__ X, uint8_t* __restrict__ Xs, int M, int K, int m_tiles) {
+  pdl_launch_dependents();               // the GEMM's prologue, W ring and dequant may start; its X producer waits
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // one 16-byte chunk
   const int chunks_per_row = K / 8;
   const long long total = (long long)m_tiles * 128 * chunks_per_row;
@@ -84,23 +148,23 @@ __global__ void swizzle_x_kernel(const __half* __restrict__ X, uint8_t* __restri
   *reinterpret_cast<uint4*>(dst) = v;
 }
 
-// ---- dequant of one 16-row tile x 128 k into the swizzled A tile ----------------------------------
-__device__ __forceinline__ uint32_t a_addr(uint32_t a_base, int row, int k) {
-  return a_base + (k >> 6) * kAtomBytes + row * 128 + ((((k & 63) >> 3) ^ (row & 7)) << 4) + (k & 7) * 2;
-}
+// ---- dequant of one 16-row tile x 128 k into a TMEM A stage ----------------------------------------
 // bits: code * 2^s in each 16-bit half (two consecutive k).  magic 2^(10-s): (x | magic) - magic == code exactly.
-__device__ __forceinline__ void emit_pair(uint32_t a_base, int row, int k, uint32_t bits, int s, __half2 scale, __half2 nzs) {
+__device__ __forceinline__ uint32_t deq_pair(uint32_t bits, int s, __half2 scale, __half2 nzs) {
   const uint32_t mg = (uint32_t)((25 - s) << 10) * 0x00010001u;
   const uint32_t vb = bits | mg;
   const __half2 q = __hsub2(*reinterpret_cast<const __half2*>(&vb), *reinterpret_cast<const __half2*>(&mg));
   const __half2 w = __hfma2(q, scale, nzs);
-  asm volatile("st.shared.b32 [%0], %1;" ::"r"(a_addr(a_base, row, k)), "r"(*reinterpret_cast<const uint32_t*>(&w)) : "memory");
+  return *reinterpret_cast<const uint32_t*>(&w);
 }
 
+// Every lane (g = lane >> 2, t = lane & 3) owns, for rows g and g + 8 of the tile, the 16 code pairs i = 0..15 at
+// k = 8 i + 2 t + {0, 1} (layout.cuh field_src) — which is exactly where tcgen05.st.16x128b puts register pair
+// (2 i, 2 i + 1): lanes g / g + 8, column 4 i + t.  taddr = lane base of the tile | first column of the A stage.
 template <int BITS>
-__device__ __forceinline__ void dequant_tile(const uint8_t* rec, int tile, int rows_base, uint32_t a_base, int lane) {
+__device__ __forceinline__ void dequant_tile(const uint8_t* rec, int tile, uint32_t taddr, int lane) {
   constexpr int NW = words_per_tile(BITS);
-  const int g = lane >> 2, t = lane & 3;
+  const int g = lane >> 2;
   // this lane's words of `tile` inside the record: word i = tile*NW + j lives in uint4 (i>>2) of the lane, component i&3
   uint32_t w[NW];
   const uint32_t* rw = reinterpret_cast<const uint32_t*>(rec);
@@ -113,45 +177,65 @@ __device__ __forceinline__ void dequant_tile(const uint8_t* rec, int tile, int r
   const __half2 m0 = meta[g], m1 = meta[g + 8];
   const __half2 s0 = __half2half2(__low2half(m0)), z0 = __half2half2(__hneg(__high2half(m0)));
   const __half2 s1 = __half2half2(__low2half(m1)), z1 = __half2half2(__hneg(__high2half(m1)));
-  const int r0 = rows_base + g, r1 = rows_base + g + 8;
-  // regular MMA block: R0 (row g, k0), R1 (row g+8, k0), R2 (row g, k0+8), R3 (row g+8, k0+8)
-  auto block = [&](int kbase, uint32_t R0, uint32_t R1, uint32_t R2, uint32_t R3, int sl, int sh) {
-    emit_pair(a_base, r0, kbase + 2 * t, R0, sl, s0, z0);
-    emit_pair(a_base, r1, kbase + 2 * t, R1, sl, s1, z1);
-    emit_pair(a_base, r0, kbase + 8 + 2 * t, R2, sh, s0, z0);
-    emit_pair(a_base, r1, kbase + 8 + 2 * t, R3, sh, s1, z1);
-  };
+  uint32_t v[16];
   if (BITS == 4) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const uint32_t x0 = w[j], x8 = x0 >> 8;
-      block(16 * j, x0 & 0x000f000fu, x8 & 0x000f000fu, x0 & 0x00f000f0u, x8 & 0x00f000f0u, 0, 4);
+    for (int h8 = 0; h8 < 2; ++h8) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t x = w[(8 * h8 + i) >> 1], y = x >> 8;
+        const uint32_t msk = (i & 1) ? 0x00f000f0u : 0x000f000fu;
+        v[2 * i] = deq_pair(x & msk, 4 * (i & 1), s0, z0);
+        v[2 * i + 1] = deq_pair(y & msk, 4 * (i & 1), s1, z1);
+      }
+      tmem_st_16x128b_x8(taddr + 32 * h8, v);
     }
   } else if (BITS == 2) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint32_t x0 = w[j], x8 = x0 >> 8;
-      block(32 * j, x0 & 0x00030003u, x8 & 0x00030003u, x0 & 0x000c000cu, x8 & 0x000c000cu, 0, 2);
-      block(32 * j + 16, x0 & 0x00300030u, x8 & 0x00300030u, x0 & 0x00c000c0u, x8 & 0x00c000c0u, 4, 6);
+    for (int h8 = 0; h8 < 2; ++h8) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t x = w[(8 * h8 + i) >> 2], y = x >> 8;
+        const uint32_t msk = 0x00030003u << (2 * (i & 3));
+        v[2 * i] = deq_pair(x & msk, 2 * (i & 3), s0, z0);
+        v[2 * i + 1] = deq_pair(y & msk, 2 * (i & 3), s1, z1);
+      }
+      tmem_st_16x128b_x8(taddr + 32 * h8, v);
     }
   } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t x = w[i >> 1], y = x >> 6;
+      const uint32_t msk = (i & 1) ? 0x00380038u : 0x00070007u;
+      v[2 * i] = deq_pair(x & msk, 3 * (i & 1), s0, z0);
+      v[2 * i + 1] = deq_pair(y & msk, 3 * (i & 1), s1, z1);
+    }
+    tmem_st_16x128b_x8(taddr, v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t x = w[4 + (i >> 1)], y = x >> 6;
+      const uint32_t msk = (i & 1) ? 0x00380038u : 0x00070007u;
+      v[2 * i] = deq_pair(x & msk, 3 * (i & 1), s0, z0);
+      v[2 * i + 1] = deq_pair(y & msk, 3 * (i & 1), s1, z1);
+    }
+    // pairs 12..14: the sixth code of each half (at shift 6 after >> 6), words (0,1), (2,3), (4,5) = rows (g, g+8);
+    // pair 15: the split codes k = 120 + 2t + e, bit j of row g in word 2j, of row g+8 in word 2j+1 (bit 9 of each half)
     uint32_t e[6], f[6];
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
-      const uint32_t x0 = w[j], x6 = x0 >> 6;
-      block(16 * j, x0 & 0x00070007u, x6 & 0x00070007u, x0 & 0x00380038u, x6 & 0x00380038u, 0, 3);
-      e[j] = x6 & 0x01C001C0u;
-      f[j] = x6 & 0x02000200u;
+      e[j] = (w[j] >> 6) & 0x01C001C0u;
+      f[j] = (w[j] >> 6) & 0x02000200u;
     }
-    block(96, e[0], e[1], e[2], e[3], 6, 6);
-    emit_pair(a_base, r0, 112 + 2 * t, e[4], 6, s0, z0);
-    emit_pair(a_base, r1, 112 + 2 * t, e[5], 6, s1, z1);
-    // split codes k = 120 + 2t + h: bit j of row g in f[2j], of row g+8 in f[2j+1] (bit 9 of each half)
-    const uint32_t q0 = (f[0] >> 9) | (f[2] >> 8) | (f[4] >> 7);
-    const uint32_t q1 = (f[1] >> 9) | (f[3] >> 8) | (f[5] >> 7);
-    emit_pair(a_base, r0, 120 + 2 * t, q0, 0, s0, z0);
-    emit_pair(a_base, r1, 120 + 2 * t, q1, 0, s1, z1);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      v[8 + 2 * i] = deq_pair(e[2 * i], 6, s0, z0);
+      v[9 + 2 * i] = deq_pair(e[2 * i + 1], 6, s1, z1);
+    }
+    v[14] = deq_pair((f[0] >> 9) | (f[2] >> 8) | (f[4] >> 7), 0, s0, z0);
+    v[15] = deq_pair((f[1] >> 9) | (f[3] >> 8) | (f[5] >> 7), 0, s1, z1);
+    tmem_st_16x128b_x8(taddr + 32, v);
   }
+  tmem_wait_st();
 }
 
 struct TcArgs {
@@ -160,113 +244,191 @@ struct TcArgs {
   __half* y;
   const __half* bias;
   int bits, M, N, K;
+  int nws;                 // W ring depth
+  int dbg;                 // AMQB_TC_DBG ablation mask (1: no dequant, 2: no MMA, 4: tiny X copies) — timing experiments only
 };
 
+// CL = 2: the two CTAs of a cluster own neighbouring n tiles of the same m tile; each loads one of the two 64-k atoms
+// of every X stage and multicasts it to both, halving the L2 -> SM traffic of the activations (the larger stream).
+template <int CL>
 __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_constant__ TcArgs A) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  // [0, 1024): barriers + tmem slot | A ring | X ring | W ring
+  // [0, kTcHeader): barriers (kBar*) + tmem slot + debug trace | X ring | W ring
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  // wfull[4] 0..3, wempty[4] 4..7, xfull[3] 8..10, xempty[3] 11..13, afull[2] 14..15, aempty[2] 16..17, accfull 18
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 512);
-  uint8_t* a_ring = smem + 1024;
-  uint8_t* x_ring = a_ring + kAStages * kABytes;
+  uint8_t* x_ring = smem + kTcHeader;
   uint8_t* w_ring = x_ring + kXStages * kXBytes;
   const int rbytes = rec_bytes(A.bits);
   const int w_stage = 4 * rbytes;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform for the compiler
   const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+  long long (*trace)[40] = reinterpret_cast<long long (*)[40]>(smem + 1024);   // AMQB_TC_DBG & 16: clock64 of [role][kb]
+  auto tr = [&](int role, int kb) { if ((A.dbg & 16) && kb < 40) trace[role][kb] = clock64(); };
+  unsigned long long* stamps = reinterpret_cast<unsigned long long*>(smem + 640);   // AMQB_TC_DBG & 8: timeline of CTA (0,0)
+  auto stamp = [&](int i) {
+    if (A.dbg & 8) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); stamps[i] = t; }
+  };
+  if (tid == 0) stamp(0);
   const int NG = A.K / kBlockK;
 
   if (tid == 0) {
-    for (int i = 0; i < kWStages; ++i) { mbar_init(smem_u32(&bars[i]), 1); mbar_init(smem_u32(&bars[4 + i]), 8); }
-    for (int i = 0; i < kXStages; ++i) { mbar_init(smem_u32(&bars[8 + i]), 1); mbar_init(smem_u32(&bars[11 + i]), 1); }
-    for (int i = 0; i < kAStages; ++i) { mbar_init(smem_u32(&bars[14 + i]), 8); mbar_init(smem_u32(&bars[16 + i]), 1); }
-    mbar_init(smem_u32(&bars[18]), 1);
+    for (int i = 0; i < A.nws; ++i) { mbar_init(smem_u32(&bars[kBarWFull + i]), 1); mbar_init(smem_u32(&bars[kBarWEmpty + i]), 8); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(smem_u32(&bars[kBarFull + i]), 9); mbar_init(smem_u32(&bars[kBarDone + i]), CL); }
+    mbar_init(smem_u32(&bars[kBarAcc]), 1);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 128);
+  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) tc_cluster_sync();         // the peer's barriers are initialised before anything is multicast into it
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) stamp(1);
 
   if (warp == 0) {
-    // ===== producer
+    // ===== W producer: the n tile's four 32-row records of k block kb
+    if (lane == 0) {
+      int ws = 0; uint32_t ph = 0;
+      for (int kb = 0; kb < NG; ++kb) {
+        if (kb >= A.nws) mbar_wait_spin(smem_u32(&bars[kBarWEmpty + ws]), ph ^ 1);
+        mbar_expect_tx(smem_u32(&bars[kBarWFull + ws]), 4 * rbytes);
+        for (int r = 0; r < 4; ++r)
+          bulk_g2s(smem_u32(w_ring + (size_t)ws * w_stage + (size_t)r * rbytes),
+                   A.w + ((size_t)(n_tile * 4 + r) * NG + kb) * rbytes, rbytes, smem_u32(&bars[kBarWFull + ws]));
+        if (++ws == A.nws) { ws = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 3) {
+    // ===== X producer: two pre-swizzled 64-k atoms of the m tile per k block
     if (lane == 0) {
       const uint8_t* xsrc = A.xs + (size_t)m_tile * (A.K / 64) * kAtomBytes;
+      const uint32_t xbytes = (A.dbg & 4) ? 16u * CL : (uint32_t)kXBytes;
+      int st = 0; uint32_t ph = 0;
+      pdl_wait();                          // the pre-swizzle pass (launched just before, overlapped via PDL) is complete
       for (int kb = 0; kb < NG; ++kb) {
-        const int ws = kb % kWStages, xs = kb % kXStages;
-        if (kb >= kWStages) mbar_wait(smem_u32(&bars[4 + ws]), ((kb / kWStages) - 1) & 1);
-        mbar_expect_tx(smem_u32(&bars[ws]), 4 * rbytes);
-        for (int r = 0; r < 4; ++r)      // the n tile's four 32-row blocks: record (rb, kb)
-          bulk_g2s(smem_u32(w_ring + (size_t)ws * w_stage + (size_t)r * rbytes),
-                   A.w + ((size_t)(n_tile * 4 + r) * NG + kb) * rbytes, rbytes, smem_u32(&bars[ws]));
-        if (kb >= kXStages) mbar_wait(smem_u32(&bars[11 + xs]), ((kb / kXStages) - 1) & 1);
-        mbar_expect_tx(smem_u32(&bars[8 + xs]), kXBytes);
-        bulk_g2s(smem_u32(x_ring + (size_t)xs * kXBytes), xsrc + (size_t)(2 * kb) * kAtomBytes, kXBytes, smem_u32(&bars[8 + xs]));
+        if (kb >= kStages) mbar_wait_spin(smem_u32(&bars[kBarDone + st]), ph ^ 1);
+        tr(1, kb);
+        mbar_expect_tx(smem_u32(&bars[kBarFull + st]), xbytes);
+        if (CL == 1) {
+          bulk_g2s(smem_u32(x_ring + (size_t)st * kXBytes), xsrc + (size_t)(2 * kb) * kAtomBytes, xbytes, smem_u32(&bars[kBarFull + st]));
+        } else {
+          // done[st] counted both CTAs' commits: the stage is free in the peer too
+          const uint32_t r = tc_cluster_rank();
+          bulk_g2s_mc(smem_u32(x_ring + (size_t)st * kXBytes + (size_t)r * kAtomBytes), xsrc + (size_t)(2 * kb + r) * kAtomBytes,
+                      (A.dbg & 4) ? 16u : (uint32_t)kAtomBytes, smem_u32(&bars[kBarFull + st]), (uint16_t)3);
+        }
+        if (++st == kStages) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread)
-    if (lane == 0) {
-      for (int kb = 0; kb < NG; ++kb) {
-        const int as = kb % kAStages, xs = kb % kXStages;
-        mbar_wait(smem_u32(&bars[14 + as]), (kb / kAStages) & 1);
-        mbar_wait(smem_u32(&bars[8 + xs]), (kb / kXStages) & 1);
-        tc_fence_after();
-        const uint32_t a_base = smem_u32(a_ring + (size_t)as * kABytes);
-        const uint32_t x_base = smem_u32(x_ring + (size_t)xs * kXBytes);
-#pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          const uint32_t off = (k >> 2) * kAtomBytes + (k & 3) * 32;      // next 16 k: +32 B inside the atom
-          tc_mma_f16(tmem_base, umma_desc_sw128(a_base + off), umma_desc_sw128(x_base + off), kIdesc, (kb | k) != 0);
-        }
-        tc_commit(smem_u32(&bars[16 + as]));       // A stage free once these MMAs have read it
-        tc_commit(smem_u32(&bars[11 + xs]));       // X stage free
-      }
-      tc_commit(smem_u32(&bars[18]));              // accumulator complete
-    }
-  } else if (warp >= 4) {
-    // ===== dequant warps: warp-4 = tile index inside the 128-row n tile
-    const int tile8 = warp - 4;
+    // ===== MMA issuer.  The whole warp runs the loop (uniform control flow keeps descriptors in uniform registers);
+    // one elected lane issues.  tcgen05.mma issue back-pressures, so whatever else happens per k block is a bubble in
+    // the tensor pipe: one wait, one commit, and the wait for the next stage sits before the commit, while the
+    // queued MMAs still execute.
+    int st = 0; uint32_t ph = 0;
+    mbar_wait_spin(smem_u32(&bars[kBarFull]), 0);
+    if (lane == 0) { stamp(2); stamp(3); }
+    const uint64_t xdesc0 = umma_desc_sw128(smem_u32(x_ring));
     for (int kb = 0; kb < NG; ++kb) {
-      const int ws = kb % kWStages, as = kb % kAStages;
-      mbar_wait(smem_u32(&bars[ws]), (kb / kWStages) & 1);
-      if (kb >= kAStages) mbar_wait(smem_u32(&bars[16 + as]), ((kb / kAStages) - 1) & 1);
-      const uint8_t* rec = w_ring + (size_t)ws * w_stage + (size_t)(tile8 >> 1) * rbytes;
-      const uint32_t a_base = smem_u32(a_ring + (size_t)as * kABytes);
-      if (A.bits == 3) dequant_tile<3>(rec, tile8 & 1, tile8 * 16, a_base, lane);
-      else if (A.bits == 4) dequant_tile<4>(rec, tile8 & 1, tile8 * 16, a_base, lane);
-      else dequant_tile<2>(rec, tile8 & 1, tile8 * 16, a_base, lane);
-      fence_proxy_async();                          // generic-proxy stores -> visible to the tensor core (async proxy)
-      __syncwarp();
       if (lane == 0) {
-        mbar_arrive(smem_u32(&bars[14 + as]));      // A tile (this warp's rows) ready
-        mbar_arrive(smem_u32(&bars[4 + ws]));       // packed stage consumed
+        tr(2, kb); tr(3, kb);
+        if (kb == 8) stamp(4);
+        if (kb == 16) stamp(5);
+        if (kb == NG - 1) stamp(6);
       }
+      tc_fence_after();
+      const uint32_t a_tmem = tmem_base + kTmemA0 + st * kTmemAStage;
+      const uint64_t xdesc = xdesc0 + (uint64_t)(st * (kXBytes >> 4));     // start-address field (bytes >> 4), no carry
+      if (!(A.dbg & 2) && elect_one()) {
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k)                              // next 16 k: +32 B inside the 64-k atom
+          tc_mma_f16_ts(tmem_base, a_tmem + 8 * k, xdesc + (uint64_t)(((k >> 2) * kAtomBytes + (k & 3) * 32) >> 4), kIdesc,
+                        (kb | k) != 0);
+      }
+      __syncwarp();
+      if (lane == 0) tr(7, kb);
+      if (elect_one()) {                               // A and X stage free once these MMAs have read them
+        if (CL == 1) tc_commit(smem_u32(&bars[kBarDone + st]));
+        else tc_commit_mc(smem_u32(&bars[kBarDone + st]), (uint16_t)3);
+      }
+      if (++st == kStages) { st = 0; ph ^= 1; }
+      if (kb + 1 < NG) mbar_wait_spin(smem_u32(&bars[kBarFull + st]), ph);
+      __syncwarp();
+      if (lane == 0) tr(0, kb);
+    }
+    if (elect_one()) tc_commit(smem_u32(&bars[kBarAcc]));             // accumulator complete
+  } else if (warp >= 4) {
+    // ===== dequant warps.  A warp may only touch the TMEM lanes of its quarter (warp & 3) = one 32-row record of the
+    // n tile; of the four warps of a quarter, two take its two 16-row tiles on even k blocks and two on odd ones (a
+    // tile's dequant is a ~1 us dependent chain: two k blocks in flight per tile hide it).
+    const int q = warp & 3, tile = ((warp - 4) >> 2) & 1, par = (warp - 4) >> 3;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32 + tile * 16) << 16) + kTmemA0;
+    int ws = par; uint32_t wph = 0;
+    if (ws >= A.nws) { ws -= A.nws; wph ^= 1; }
+    int st = par; uint32_t ph = 0;
+    for (int kb = par; kb < NG; kb += 2) {
+      mbar_wait_spin(smem_u32(&bars[kBarWFull + ws]), wph);
+      if (q == 0 && tile == 0 && lane == 0) tr(4, kb);
+      if (kb >= kStages) {
+        mbar_wait_spin(smem_u32(&bars[kBarDone + st]), ph ^ 1);
+        tc_fence_after();
+      }
+      if (q == 0 && tile == 0 && lane == 0) tr(5, kb);
+      const uint8_t* rec = w_ring + (size_t)ws * w_stage + (size_t)q * rbytes;
+      const uint32_t taddr = lane_base + st * kTmemAStage;
+      if (A.dbg & 1) {}
+      else if (A.bits == 3) dequant_tile<3>(rec, tile, taddr, lane);
+      else if (A.bits == 4) dequant_tile<4>(rec, tile, taddr, lane);
+      else dequant_tile<2>(rec, tile, taddr, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (q == 0 && tile == 0 && lane == 0) tr(6, kb);
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&bars[kBarFull + st]));     // A tile (this warp's rows) in TMEM
+        mbar_arrive(smem_u32(&bars[kBarWEmpty + ws]));   // packed stage consumed
+      }
+      ws += 2;
+      if (ws >= A.nws) { ws -= A.nws; wph ^= 1; }
+      st += 2;
+      if (st >= kStages) { st -= kStages; ph ^= 1; }
     }
     // ===== epilogue: TMEM lane = output channel, column = token
-    mbar_wait(smem_u32(&bars[18]), 0);
+    mbar_wait_spin(smem_u32(&bars[kBarAcc]), 0);
     tc_fence_after();
-    const int q = warp & 3;                         // TMEM lane quarter this warp may access
-    const int chalf = (warp - 4) >> 2;              // columns [64*chalf, 64*chalf + 64)
+    if (tid == 128) stamp(7);
+    const int cq = (warp - 4) >> 2;                 // columns [32 cq, 32 cq + 32)
     const int n = n_tile * kTileN + q * 32 + lane;
     const float bv = A.bias ? __half2float(A.bias[n]) : 0.f;
-#pragma unroll 1
-    for (int c0 = 0; c0 < 64; c0 += 32) {
+    {
       uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(chalf * 64 + c0), r);
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 32), r);
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
-        const int m = m_tile * kTileM + chalf * 64 + c0 + c;
+        const int m = m_tile * kTileM + cq * 32 + c;
         if (m < A.M) A.y[(size_t)m * A.N + n] = __float2half_rn(__uint_as_float(r[c]) + bv);
       }
     }
   }
+  if (tid == 128) stamp(8);
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 128);
+  if (CL > 1) tc_cluster_sync();         // no CTA leaves while its peer may still multicast into it
+  if ((A.dbg & 16) && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
+    const long long t0 = trace[1][0];
+    for (int kb = 0; kb < NG && kb < 40; ++kb)
+      printf("kb %2d  Xissue %6lld | mma: Afull %6lld Xfull +%4lld issued +%4lld committed +%4lld | deq: Wfull %6lld Aempty %6lld done %6lld\n", kb,
+             trace[1][kb] - t0, trace[2][kb] - t0, trace[3][kb] - trace[2][kb], trace[7][kb] - trace[3][kb], trace[0][kb] - trace[7][kb],
+             trace[4][kb] - t0, trace[5][kb] - t0, trace[6][kb] - t0);
+  }
+  if ((A.dbg & 8) && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
+    stamp(9);
+    printf("tc timeline (ns from start): sync %llu | A0 %llu X0 %llu | kb8 %llu kb16 %llu kbLast %llu | acc %llu epi-end %llu all %llu\n",
+           stamps[1] - stamps[0], stamps[2] - stamps[0], stamps[3] - stamps[0], stamps[4] - stamps[0], stamps[5] - stamps[0],
+           stamps[6] - stamps[0], stamps[7] - stamps[0], stamps[8] - stamps[0], stamps[9] - stamps[0]);
+  }
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 }  // namespace amqb
@@ -313,13 +475,39 @@ int amqb_gemm_tc(int bits, const void* w_native, const void* x, void* y, const v
   TcArgs A{};
   A.w = (const uint8_t*)w_native; A.xs = (const uint8_t*)workspace; A.y = (__half*)y; A.bias = (const __half*)bias;
   A.bits = bits; A.M = M; A.N = N; A.K = K;
-  const size_t smem = 1024 + (size_t)kAStages * kABytes + (size_t)kXStages * kXBytes + (size_t)kWStages * 4 * rec_bytes(bits);
+  { const char* e = getenv("AMQB_TC_DBG"); A.dbg = e ? atoi(e) : 0; }
+  const size_t w_stage = 4 * (size_t)rec_bytes(bits);
+  size_t nws = (kTcSmemMax - kTcHeader - (size_t)kXStages * kXBytes) / w_stage;
+  if (nws > (size_t)kWStagesMax) nws = kWStagesMax;
+  A.nws = (int)nws;
+  const size_t smem = kTcHeader + (size_t)kXStages * kXBytes + nws * w_stage;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax);
+    cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax);
     attr = true;
   }
-  gemm_tc_kernel<<<dim3(N / kTileN, m_tiles), kTcThreads, smem, st>>>(A);
+  const int n_tiles = N / kTileN;
+  // cluster pair + X multicast halves the activations' L2 traffic but measured ~5% slower (the X ring is bound by the
+  // bulk-copy round trip, not by L2 bandwidth): opt-in, kept as the base for a cta_group::2 version
+  const bool pair = (n_tiles % 2 == 0) && getenv("AMQB_TC_CLUSTER") != nullptr;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(n_tiles, m_tiles);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // overlap with the pre-swizzle pass
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  at[1].id = cudaLaunchAttributeClusterDimension;
+  at[1].val.clusterDim.x = 2; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pair ? 2 : 1;
+  cudaError_t e = pair ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2>, A) : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<1>, A);
+  if (e != cudaSuccess) {
+    set_error("gemm_tc launch: %s", cudaGetErrorString(e));
+    return AMQB_ERR_LAUNCH;
+  }
   return check_launch("gemm_tc");
 }
 

@@ -172,17 +172,25 @@ def linear_forward(bits: int, w_native: torch.Tensor, x2: torch.Tensor, N: int, 
     return gemm_tc(bits, w_native, x2, N, K, bias)
 
 
+def gemm_workspace(M: int, K: int, bits: int, device) -> torch.Tensor:
+    """Scratch for `gemm_tc` (the pre-swizzled activations); reusable across calls of the same or smaller M, K."""
+    need = int(lib().amqb_gemm_workspace_bytes(M, K, bits))
+    return torch.empty(max(need, 256), dtype=torch.uint8, device=device)
+
+
 def gemm_tc(bits: int, w_native: torch.Tensor, x: torch.Tensor, N: int, K: int,
-            bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+            bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+            workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
     _req_cuda(w_native, x)
     x = x.contiguous()
     M = x.shape[0]
-    y = torch.empty((M, N), dtype=torch.float16, device=x.device)
+    y = out if out is not None else torch.empty((M, N), dtype=torch.float16, device=x.device)
+    if y.shape != (M, N) or y.dtype != torch.float16 or not y.is_contiguous():
+        raise ValueError("gemm_tc: out must be a contiguous fp16 [M, N] tensor")
     L = lib()
     if not hasattr(L, "amqb_gemm_tc"):
         raise RuntimeError("amq_b200: amqb_gemm_tc missing from libamqb.so")
-    need = int(L.amqb_gemm_workspace_bytes(M, K, bits))
-    wsb = torch.empty(max(need, 16), dtype=torch.uint8, device=x.device)
+    wsb = workspace if workspace is not None else gemm_workspace(M, K, bits, x.device)
     check(L.amqb_gemm_tc(bits, ptr(w_native), ptr(x), ptr(y), ptr(bias), M, N, K, ptr(wsb),
                          ctypes.c_size_t(wsb.numel()), cur_stream()), "gemm_tc")
     return y

@@ -21,15 +21,27 @@ def run(N, K, M, bits, seed=0, time_it=False):
     rel = float((y.float() - ref).abs().max() / ref.abs().max())
     msg = f"N={N} K={K} M={M} bits={bits} max-rel {rel:.2e}"
     if time_it:
-        for _ in range(3):
-            ops.gemm_tc(bits, nat, x, N, K, bias)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(20):
-            ops.gemm_tc(bits, nat, x, N, K, bias)
-        e1.record(); torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 20
+        # device time: 20 calls captured in one CUDA graph (a python loop of ~30 us calls would be host-bound)
+        ws = ops.gemm_workspace(M, K, bits, x.device) if hasattr(ops, "gemm_workspace") else None
+        y2 = torch.empty(M, N, device=dev, dtype=torch.float16)
+        def call():
+            ops.gemm_tc(bits, nat, x, N, K, bias, out=y2, workspace=ws)
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                call()
+            s.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=s):
+                for _ in range(20):
+                    call()
+            gr.replay(); s.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(s)
+            for _ in range(5):
+                gr.replay()
+            e1.record(s); s.synchronize()
+        ms = e0.elapsed_time(e1) / 100
         msg += f"  {ms*1e3:.1f} us  {2*M*N*K/ms/1e9:.1f} TFLOP/s"
     print(msg, flush=True)
     return rel
