@@ -200,8 +200,45 @@ class HQQLinear(nn.Module):
         weight = self.dequantize()
         return torch.matmul(x, weight.t() if transpose else weight)
 
+    # ---- backends (quantize.py:393-418 `set_backend`): "pytorch" = dequantise + library GEMM (the reference's
+    # forward_pytorch); "fused" (default) = the search-stage fast path of SURVEY §8f-3: W_q is transcoded once,
+    # integer-exactly, HQQ layout -> kernel-native records, and every forward is the dequant-fused decode GEMV
+    # (M <= 16) or the tcgen05 prefill GEMM, so no [N, K] fp16 weight is materialised per call.
+    backend = "fused"
+
+    @classmethod
+    def set_backend(cls, backend):
+        name = getattr(backend, "value", backend)
+        name = {"forward_pytorch": "pytorch", "forward_pytorch_backprop": "pytorch"}.get(name, name)
+        if name not in ("pytorch", "fused"):
+            raise ValueError(f"HQQLinear.set_backend: unknown backend {backend!r} (pytorch | fused)")
+        cls.backend = name
+
+    def native_weight(self):
+        """Kernel-native copy of (W_q, scale, zero); None when the layer does not meet the kernel's preconditions
+        (axis 1, group 128, N % 32 == 0, K % 128 == 0, 2/3/4 bits).  Rebuilt when W_q / meta are replaced."""
+        key = (self.W_q.data_ptr(), self.meta["scale"].data_ptr(), self.meta["zero"].data_ptr())
+        if getattr(self, "_native_key", None) == key:
+            return self._w_native
+        N, K = self.meta["shape"]
+        bits, G = int(self.meta["nbits"]), self.meta["group_size"]
+        self._native_key, self._w_native = key, None
+        if self.meta.get("axis", 1) == 1 and self.meta["nbits"] == bits and ops.native_supported(bits, N, K, G) \
+                and self.W_q.is_cuda:
+            scale = self.meta["scale"].reshape(N, -1).to(torch.float16)
+            zero = self.meta["zero"].reshape(N, -1).to(torch.float16)
+            self._w_native = ops.pack_native(bits, self.unpack_codes(), scale, zero)
+        return self._w_native
+
     def forward(self, x: Tensor) -> Tensor:
-        """forward_pytorch (quantize.py:892-898): fused CUDA dequant + library GEMM."""
+        """quantize.py:880-898.  Both backends compute x @ ((W_q - zero) * scale).T + bias; "pytorch" rounds the
+        weight to fp16 twice like the reference, "fused" once (inside the 1e-3 parity bound either way)."""
+        nat = self.native_weight() if (self.backend == "fused" and x.is_cuda and x.dtype == torch.float16) else None
+        if nat is not None:
+            N, K = self.meta["shape"]
+            x2 = x.reshape(-1, K)
+            out = ops.linear_forward(int(self.meta["nbits"]), nat, x2, N, K, self.bias)
+            return out.reshape(*x.shape[:-1], N)
         out = torch.matmul(x, self.dequantize().t())
         if self.bias is not None:
             out += self.bias

@@ -102,6 +102,45 @@ def test_hqq_to_kernel_modules_flow(amq, bits, tmp_path):
     assert set(blk2.state_dict()) - {"q_proj.weight"} == set(torch.load(cache, weights_only=True))
 
 
+@pytest.mark.parametrize("bits", [2, 3, 4])
+def test_hqqlinear_fused_backend(amq, bits):
+    """HQQLinear.forward on the search-stage shape (M = 2048 tokens) without materialising the fp16
+    weight: W_q is transcoded (codes bit-exact) to the kernel-native layout once and the tcgen05 GEMM / decode GEMV
+    run on it.  Must agree with the reference-style backend (dequantise + matmul) and with fp32."""
+    import torch.nn as nn
+    torch.manual_seed(bits)
+    N, K = 512, 1024
+    lin = nn.Linear(K, N, bias=True).half()
+    hq = amq.HQQLinear(lin, amq.BaseQuantizeConfig(nbits=bits, group_size=G), compute_dtype=torch.float16, device="cuda")
+    assert amq.HQQLinear.backend == "fused"
+    nat = hq.native_weight()
+    from amq_b200 import ops, _lib
+    assert nat is not None and nat.numel() == ops.native_bytes(bits, N, K)
+    assert torch.equal(ops.unpack_codes(nat, bits, _lib.LAYOUT_NATIVE, N, K, G), hq.unpack_codes())
+    assert hq.native_weight() is nat                       # cached until W_q / meta are replaced
+    W = hq.dequantize().float()
+    for shape in [(1, 2048, K), (3, K), (1, 1, K)]:
+        x = torch.randn(*shape, device="cuda").half()
+        y = hq(x)
+        ref = x.float() @ W.t() + hq.bias.float()
+        assert y.shape == x.shape[:-1] + (N,) and y.dtype == torch.float16
+        assert O.max_rel(y.reshape(-1, N).cpu(), ref.reshape(-1, N).cpu()) <= 1e-3
+        amq.HQQLinear.set_backend("pytorch")
+        try:
+            y_pt = hq(x)
+        finally:
+            amq.HQQLinear.set_backend("fused")
+        assert O.max_rel(y.reshape(-1, N).cpu(), y_pt.reshape(-1, N).float().cpu()) <= 2e-3
+    with pytest.raises(ValueError):
+        amq.HQQLinear.set_backend("aten")
+    # a shape the kernel does not take (N % 32 != 0): falls to the dequantise + matmul backend, still correct
+    hq48 = amq.HQQLinear(nn.Linear(256, 48, bias=False).half(), amq.BaseQuantizeConfig(nbits=bits, group_size=G),
+                         compute_dtype=torch.float16, device="cuda")
+    assert hq48.native_weight() is None
+    x = torch.randn(4, 256, device="cuda").half()
+    assert O.max_rel(hq48(x).cpu(), (x.float() @ hq48.dequantize().float().t()).cpu()) <= 2e-3
+
+
 def test_gptq_module_on_golden_reference_buffers(amq):
     """A GPTQLinear filled with the buffers the REFERENCE produced (golden) reproduces the oracle."""
     d = np.load(os.path.join(GOLD, "linear_3bit_N256_K512.npz"))
