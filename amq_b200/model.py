@@ -198,9 +198,7 @@ class QuantDecoder:
         check(Lb.amqb_argmax(ptr(self.logits), ptr(self.next_tokens), self.B, S.vocab, st), "argmax")
         self.launches_per_step += 2
 
-    def capture(self) -> None:
-        """Capture one decode step (+ feeding the argmax back as the next input, + position advance)
-        into a CUDA graph."""
+    def _capture(self, host_in: Optional[torch.Tensor] = None, host_out: Optional[torch.Tensor] = None):
         lib().amqb_set_pdl(int(self.pdl))
         s = torch.cuda.Stream(device=self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
@@ -212,19 +210,44 @@ class QuantDecoder:
             s.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=s):
+                if host_in is not None:
+                    self.tokens.copy_(host_in, non_blocking=True)      # memcpy node: pinned host -> device
                 self._step_launches()
                 self.tokens.copy_(self.next_tokens)
                 self.pos.add_(1)
-            self.graph = g
+                if host_out is not None:
+                    host_out.copy_(self.tokens, non_blocking=True)     # memcpy node: device -> pinned host
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
         self.pos.copy_(saved_pos)
+        return g
+
+    def capture(self) -> None:
+        """Capture one decode step (+ feeding the argmax back as the next input, + position advance)
+        into a CUDA graph."""
+        self.graph = self._capture()
 
     def step(self) -> None:
         """One token for every sequence of the batch: replay the captured graph."""
         if self.graph is None:
             self.capture()
         self.graph.replay()
+
+    def step_host(self, host_in: torch.Tensor, host_out: torch.Tensor) -> None:
+        """Host-facing step: this step's input ids are read from the pinned host tensor `host_in` [B] and the
+        generated ids land in the pinned host tensor `host_out` [B] before the call returns.  Both copies are
+        memcpy nodes of the captured graph (one launch + one synchronise per token on the host side)."""
+        if not (host_in.is_pinned() and host_out.is_pinned()):
+            raise ValueError("step_host: host_in / host_out must be pinned host tensors")
+        if host_in.shape != self.tokens.shape or host_out.shape != self.tokens.shape or \
+                host_in.dtype != self.tokens.dtype or host_out.dtype != self.tokens.dtype:
+            raise ValueError("step_host: host tensors must match the token buffer [B] int64")
+        key = (host_in.data_ptr(), host_out.data_ptr())
+        if getattr(self, "_io_key", None) != key:
+            self._io_graph, self._io_key = self._capture(host_in, host_out), key
+            self._io_bufs = (host_in, host_out)                         # keep the captured addresses alive
+        self._io_graph.replay()
+        torch.cuda.current_stream(self.dev).synchronize()
 
     def step_eager(self) -> None:
         lib().amqb_set_pdl(0)

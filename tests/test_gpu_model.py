@@ -98,3 +98,32 @@ def test_decode_step_matches_torch_reference(family, batch):
         m.step(); m2.step_eager()
     torch.cuda.synchronize()
     assert torch.equal(m.logits, m2.logits)
+
+
+def test_step_host_matches_device_loop():
+    """The host-facing step (pinned ids in / out as memcpy nodes of the captured graph) generates the same tokens
+    as the device-resident loop."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from amq_b200.arch import ModelShape, LINEARS
+    from amq_b200.model import QuantDecoder
+    shape = ModelShape("tiny-llama", 256, 512, 4, 4, 2, 512, head_dim=64)
+    arch = {n: [3, 4] for n in LINEARS}
+    B = 2
+    m = QuantDecoder(shape, arch, batch=B, max_seq=32, seed=3)
+    start = torch.tensor([5, 17], dtype=torch.int64)
+    m.reset(); m.tokens.copy_(start.to(m.dev))
+    want = []
+    for _ in range(5):
+        m.step()
+        want.append(m.tokens.cpu().clone())
+    host_in, host_out = start.clone().pin_memory(), torch.zeros(B, dtype=torch.int64).pin_memory()
+    m.reset()
+    got = []
+    for _ in range(5):
+        m.step_host(host_in, host_out)          # returns after the D2H copy has landed
+        got.append(host_out.clone())
+        host_in.copy_(host_out)
+    assert all(torch.equal(a, b) for a, b in zip(want, got))
+    with pytest.raises(ValueError):
+        m.step_host(start.clone(), host_out)    # not pinned
