@@ -161,17 +161,20 @@ __device__ __forceinline__ uint32_t deq_pair(uint32_t bits, int s, __half2 scale
 // Every lane (g = lane >> 2, t = lane & 3) owns, for rows g and g + 8 of the tile, the 16 code pairs i = 0..15 at
 // k = 8 i + 2 t + {0, 1} (layout.cuh field_src) — which is exactly where tcgen05.st.16x128b puts register pair
 // (2 i, 2 i + 1): lanes g / g + 8, column 4 i + t.  taddr = lane base of the tile | first column of the A stage.
+// Byte-field layout: the two elements of a pair sit in bytes (b, b + 2) of a word, so `(word >> 8 b) & mask16` is
+// the pair as code * 2^s in each 16-bit half.
 template <int BITS>
 __device__ __forceinline__ void dequant_tile(const uint8_t* rec, int tile, uint32_t taddr, int lane) {
-  constexpr int NW = words_per_tile(BITS);
+  constexpr int NWR = words_per_row(BITS);
   const int g = lane >> 2;
-  // this lane's words of `tile` inside the record: word i = tile*NW + j lives in uint4 (i>>2) of the lane, component i&3
-  uint32_t w[NW];
+  // this lane's words of `tile`: word index wi = (tile*2 + r)*NWR + j lives in uint4 (wi>>2) of the lane, component wi&3
+  uint32_t wg[NWR], wh[NWR];
   const uint32_t* rw = reinterpret_cast<const uint32_t*>(rec);
 #pragma unroll
-  for (int j = 0; j < NW; ++j) {
-    const int i = tile * NW + j;
-    w[j] = rw[((i >> 2) * 32 + lane) * 4 + (i & 3)];
+  for (int j = 0; j < NWR; ++j) {
+    const int i0 = (tile * 2) * NWR + j, i1 = (tile * 2 + 1) * NWR + j;
+    wg[j] = rw[((i0 >> 2) * 32 + lane) * 4 + (i0 & 3)];
+    wh[j] = rw[((i1 >> 2) * 32 + lane) * 4 + (i1 & 3)];
   }
   const __half2* meta = reinterpret_cast<const __half2*>(rec + rec_code_bytes(BITS)) + tile * 16;
   const __half2 m0 = meta[g], m1 = meta[g + 8];
@@ -179,60 +182,57 @@ __device__ __forceinline__ void dequant_tile(const uint8_t* rec, int tile, uint3
   const __half2 s1 = __half2half2(__low2half(m1)), z1 = __half2half2(__hneg(__high2half(m1)));
   uint32_t v[16];
   if (BITS == 4) {
+    // pair i = 4 j + 2 f + b
 #pragma unroll
     for (int h8 = 0; h8 < 2; ++h8) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint32_t x = w[(8 * h8 + i) >> 1], y = x >> 8;
-        const uint32_t msk = (i & 1) ? 0x00f000f0u : 0x000f000fu;
-        v[2 * i] = deq_pair(x & msk, 4 * (i & 1), s0, z0);
-        v[2 * i + 1] = deq_pair(y & msk, 4 * (i & 1), s1, z1);
+      for (int ii = 0; ii < 8; ++ii) {
+        const int i = 8 * h8 + ii, j = i >> 2, f = (i >> 1) & 1, b = i & 1;
+        const uint32_t msk = 0x000f000fu << (4 * f);
+        v[2 * ii] = deq_pair((wg[j] >> (8 * b)) & msk, 4 * f, s0, z0);
+        v[2 * ii + 1] = deq_pair((wh[j] >> (8 * b)) & msk, 4 * f, s1, z1);
       }
       tmem_st_16x128b_x8(taddr + 32 * h8, v);
     }
   } else if (BITS == 2) {
+    // pair i = 8 j + 2 f + b
 #pragma unroll
     for (int h8 = 0; h8 < 2; ++h8) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint32_t x = w[(8 * h8 + i) >> 2], y = x >> 8;
-        const uint32_t msk = 0x00030003u << (2 * (i & 3));
-        v[2 * i] = deq_pair(x & msk, 2 * (i & 3), s0, z0);
-        v[2 * i + 1] = deq_pair(y & msk, 2 * (i & 3), s1, z1);
+      for (int ii = 0; ii < 8; ++ii) {
+        const int f = ii >> 1, b = ii & 1;
+        const uint32_t msk = 0x00030003u << (2 * f);
+        v[2 * ii] = deq_pair((wg[h8] >> (8 * b)) & msk, 2 * f, s0, z0);
+        v[2 * ii + 1] = deq_pair((wh[h8] >> (8 * b)) & msk, 2 * f, s1, z1);
       }
       tmem_st_16x128b_x8(taddr + 32 * h8, v);
     }
   } else {
+    // full pairs i = 4 j + 2 f + b (i < 12); split pairs i = 12 + 2 w + b: code>>1 in bits 6-7 of word w,
+    // code&1 in bit 6 + w of word 2
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const uint32_t x = w[i >> 1], y = x >> 6;
-      const uint32_t msk = (i & 1) ? 0x00380038u : 0x00070007u;
-      v[2 * i] = deq_pair(x & msk, 3 * (i & 1), s0, z0);
-      v[2 * i + 1] = deq_pair(y & msk, 3 * (i & 1), s1, z1);
+    for (int ii = 0; ii < 8; ++ii) {
+      const int j = ii >> 2, f = (ii >> 1) & 1, b = ii & 1;
+      const uint32_t msk = 0x00070007u << (3 * f);
+      v[2 * ii] = deq_pair((wg[j] >> (8 * b)) & msk, 3 * f, s0, z0);
+      v[2 * ii + 1] = deq_pair((wh[j] >> (8 * b)) & msk, 3 * f, s1, z1);
     }
     tmem_st_16x128b_x8(taddr, v);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint32_t x = w[4 + (i >> 1)], y = x >> 6;
-      const uint32_t msk = (i & 1) ? 0x00380038u : 0x00070007u;
-      v[2 * i] = deq_pair(x & msk, 3 * (i & 1), s0, z0);
-      v[2 * i + 1] = deq_pair(y & msk, 3 * (i & 1), s1, z1);
-    }
-    // pairs 12..14: the sixth code of each half (at shift 6 after >> 6), words (0,1), (2,3), (4,5) = rows (g, g+8);
-    // pair 15: the split codes k = 120 + 2t + e, bit j of row g in word 2j, of row g+8 in word 2j+1 (bit 9 of each half)
-    uint32_t e[6], f[6];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      e[j] = (w[j] >> 6) & 0x01C001C0u;
-      f[j] = (w[j] >> 6) & 0x02000200u;
+    for (int ii = 0; ii < 4; ++ii) {
+      const int f = (ii >> 1) & 1, b = ii & 1;
+      const uint32_t msk = 0x00070007u << (3 * f);
+      v[2 * ii] = deq_pair((wg[2] >> (8 * b)) & msk, 3 * f, s0, z0);
+      v[2 * ii + 1] = deq_pair((wh[2] >> (8 * b)) & msk, 3 * f, s1, z1);
     }
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      v[8 + 2 * i] = deq_pair(e[2 * i], 6, s0, z0);
-      v[9 + 2 * i] = deq_pair(e[2 * i + 1], 6, s1, z1);
+    for (int ii = 0; ii < 4; ++ii) {
+      const int w = ii >> 1, b = ii & 1;
+      const uint32_t cg = (((wg[w] >> (8 * b)) & 0x00C000C0u) >> 5) | (((wg[2] >> (8 * b + 6 + w))) & 0x00010001u);
+      const uint32_t ch = (((wh[w] >> (8 * b)) & 0x00C000C0u) >> 5) | (((wh[2] >> (8 * b + 6 + w))) & 0x00010001u);
+      v[8 + 2 * ii] = deq_pair(cg, 0, s0, z0);
+      v[9 + 2 * ii] = deq_pair(ch, 0, s1, z1);
     }
-    v[14] = deq_pair((f[0] >> 9) | (f[2] >> 8) | (f[4] >> 7), 0, s0, z0);
-    v[15] = deq_pair((f[1] >> 9) | (f[3] >> 8) | (f[5] >> 7), 0, s1, z1);
     tmem_st_16x128b_x8(taddr + 32, v);
   }
   tmem_wait_st();

@@ -20,16 +20,23 @@ static int sm_count() {
 }
 
 // One launch: problems sharing M and prologue kind (bit widths may differ).
+static size_t xg_xsd_bytes(int n_g, int MB) { return ((size_t)n_g * MB * 8 * sizeof(float2) + 255) & ~size_t(255); }
+static size_t xg_variant_bytes(int n_g, int bits, int M) { return ((size_t)n_g * xp_group_bytes(bits, M) + 255) & ~size_t(255); }
+static size_t xg_variant_offset(int n_g, int bits, int M) {
+  size_t off = 0;
+  for (int b = 2; b < bits; ++b) off += xg_variant_bytes(n_g, b, M);
+  return off;
+}
 static size_t xg_run_bytes(int K, int M) {
-  const int n_g = K / kGroup, NB = M <= 8 ? 1 : 2;
-  return (((size_t)n_g * NB * 8 * 4 + 255) & ~size_t(255)) + (size_t)n_g * (8 + 9 + 8) * M * 32;
+  const int n_g = K / kGroup;
+  return xg_xsd_bytes(n_g, out_blocks(M)) + xg_variant_offset(n_g, 5, M);
 }
 
 static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, cudaStream_t st, void* workspace,
                         size_t workspace_bytes) {
   GemvLaunch L{};
   const int M = pr[0]->M, pro = pr[0]->prologue;
-  const int NB = M <= 8 ? 1 : 2;
+  const int MB = out_blocks(M);
   L.count = count;
   L.M = M;
   L.dbg = g_dbg;
@@ -63,12 +70,9 @@ static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, 
       if (P.build_mask == 0) {                      // later member of a run: share the first member's buffers
         int f = i - 1;
         while (L.prob[f].build_mask == 0) --f;
-        const int n_g = P.n_g;
         const uint8_t* base = (const uint8_t*)L.prob[f].xsg;
-        const size_t xs_b = ((size_t)n_g * NB * 8 * 4 + 255) & ~size_t(255);
-        const size_t voff[3] = {0, (size_t)n_g * 8 * M * 32, (size_t)n_g * 17 * M * 32};
         P.xsg = L.prob[f].xsg;
-        P.xg = base + xs_b + voff[P.bits - 2];
+        P.xg = base + xg_xsd_bytes(P.n_g, MB) + xg_variant_offset(P.n_g, P.bits, M);
         continue;
       }
       const size_t need = xg_run_bytes(P.K, M);
@@ -76,14 +80,11 @@ static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, 
         return fail(AMQB_ERR_WORKSPACE, "gemv: M > 1 needs a 256-byte aligned workspace of amqb_workspace_bytes()");
       uint8_t* base = (uint8_t*)workspace + off;
       off += (need + 255) & ~size_t(255);
-      const int n_g = P.n_g;
-      const size_t xs_b = ((size_t)n_g * NB * 8 * 4 + 255) & ~size_t(255);
+      const size_t xs_b = xg_xsd_bytes(P.n_g, MB);
       XgArgs X{};
-      X.x = P.x; X.gamma = P.gamma; X.eps = P.eps; X.ldx = P.ldx; X.K = P.K; X.M = M; X.NB = NB; X.mask = P.build_mask;
-      X.xsg = (float*)base;
-      X.xg[0] = base + xs_b;
-      X.xg[1] = base + xs_b + (size_t)n_g * 8 * M * 32;
-      X.xg[2] = base + xs_b + (size_t)n_g * 17 * M * 32;
+      X.x = P.x; X.gamma = P.gamma; X.eps = P.eps; X.ldx = P.ldx; X.K = P.K; X.M = M; X.MB = MB; X.mask = P.build_mask;
+      X.xsg = (float2*)base;
+      for (int b = 2; b <= 4; ++b) X.xg[b - 2] = base + xs_b + xg_variant_offset(P.n_g, b, M);
       int rc = pro == AMQB_PRO_NONE ? launch_xg0(X, pdl, st) : (pro == AMQB_PRO_RMSNORM ? launch_xg1(X, pdl, st) : launch_xg2(X, pdl, st));
       if (rc) return rc;
       P.xsg = X.xsg;
@@ -105,7 +106,7 @@ static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, 
   for (int i = 0; i < count; ++i) {
     DevProblem& P = L.prob[i];
     const int slice = (P.n_g + S - 1) / S;
-    const int per_group = mmas_per_group(P.bits) * M * 32;
+    const int per_group = xp_group_bytes(P.bits, M);
     int kc = kXprimeBudget / per_group;
     if (kc >= slice) kc = slice;
     else kc = (kc / kStageRecs) * kStageRecs;       // whole pipeline stages per chunk
@@ -138,10 +139,10 @@ static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, 
   L.stage_bytes = stage_recs * max_rec;
   L.xprime_bytes = (max_xp + 127) & ~127;
   L.xp_variants = (M == 1 && count > 1 && 3 * L.xprime_bytes <= 96 * 1024) ? 3 : 1;
-  L.xs_floats = (max_kc * NB * 8 + 31) & ~31;
+  L.xs_floats = (2 * max_kc * MB * 8 + 31) & ~31;
   const size_t fixed = 384 + (size_t)L.xs_floats * 4 + 16 * kCW * 4 + (size_t)L.xp_variants * L.xprime_bytes +
-                       (size_t)2 * kCW * 2 * NB * 128 * 4 + (size_t)acc_blocks * 2 * NB * 128 * 4 +
-                       (S > 1 ? (size_t)count * S * 2 * NB * 128 * 4 : 0) + 128;
+                       (size_t)2 * kCW * 2 * MB * 128 * 4 + (size_t)acc_blocks * 2 * MB * 128 * 4 +
+                       (S > 1 ? (size_t)count * S * 2 * MB * 128 * 4 : 0) + 128;
   if (fixed + 2 * (size_t)L.stage_bytes > (size_t)kSmemTarget)
     return fail(AMQB_ERR_UNSUPPORTED_SHAPE, "gemv: shared memory budget exceeded");
   int ns = (int)(((size_t)kSmemTarget - fixed) / L.stage_bytes);
@@ -171,7 +172,7 @@ int amqb_debug_set_timeline(void* buf) {
  * activations built once per launch by the pre-pass kernel. */
 size_t amqb_workspace_bytes(int max_N, int max_K, int max_M) {
   if (max_N <= 0 || max_K <= 0 || max_M <= 0) return 0;
-  if (max_M > 16) max_M = 16;
+  if (max_M > 8) max_M = 8;            // M = 9..16 run as two passes of <= 8 activation rows
   if (max_M == 1) return 256;
   const int K = ((max_K + kGroup - 1) / kGroup) * kGroup;
   return kMaxProblems * ((xg_run_bytes(K, max_M) + 255) & ~size_t(255));
@@ -182,6 +183,27 @@ int amqb_gemv_grouped(const amqb_gemv_problem* pr, int count, void* workspace, s
   if (!pr || count < 1 || count > kMaxProblems) return fail(AMQB_ERR_BAD_ARG, "gemv: bad argument");
   const int M = pr[0].M;
   if (M < 1 || M > 16) return fail(AMQB_ERR_BAD_ARG, "gemv: M must be 1..16 (use amqb_gemm_tc for prefill)");
+  if (M > 8) {
+    // three base-256 digits per activation row fill the 8 MMA columns x 3 at M = 8: larger batches run as
+    // two passes over the weights (rows [0, 8) and [8, M))
+    for (int i = 0; i < count; ++i)
+      if (pr[i].M != M || !pr[i].x || !pr[i].y) return fail(AMQB_ERR_BAD_ARG, "gemv: bad problem");
+    amqb_gemv_problem half[kMaxProblems];
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int i = 0; i < count; ++i) {
+        half[i] = pr[i];
+        half[i].M = pass == 0 ? 8 : M - 8;
+        if (pass == 1) {
+          half[i].x = (const __half*)pr[i].x + (size_t)8 * pr[i].ldx;
+          half[i].y = (__half*)pr[i].y + (size_t)8 * pr[i].ldy;
+          if (pr[i].residual) half[i].residual = (const __half*)pr[i].residual + (size_t)8 * pr[i].ldy;
+        }
+      }
+      const int rc = amqb_gemv_grouped(half, count, workspace, workspace_bytes, pdl, stream);
+      if (rc) return rc;
+    }
+    return AMQB_OK;
+  }
   for (int i = 0; i < count; ++i) {
     const amqb_gemv_problem& q = pr[i];
     if (q.M != M) return fail(AMQB_ERR_BAD_ARG, "gemv: all problems of a group must share M");

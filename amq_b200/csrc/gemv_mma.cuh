@@ -4,22 +4,27 @@
 //   gemv_4bit / gemv_kernel            /root/reference/amq/kernel/ft/quantization_new/gemv/gemv_cuda.cu:73-204,358-437
 // and the small-M half of gemm_4bit (M = 8..16, gemm_cuda.cu:952-963).
 //
-// Why tensor cores at batch 1: at 6.5 TB/s a B200 SM receives ~23 B/clk = 92 two-bit codes
-// per clock but issues only 128 lane-instructions per clock, i.e. ~1.4 instructions per code.
-// A SIMT unpack + convert + FMA costs >= 3.  Here a code pair becomes an fp16x2 MMA operand with
-// ONE `and` (the masked bits, read as fp16 (sub)normals, are code * 2^s * 2^-24 exactly; the
-// activation slot carries 2^-s) and the multiply-accumulate runs on the HMMA pipe (256 codes per
-// warp instruction), so the kernel stays HBM-bound.  Scale / zero are applied once per group on
-// the fp32 accumulator:  y[n] = sum_g  s[n,g] * (sum_k q x) - (zero*scale)[n,g] * sum_k x.
+// Why integer tensor cores at batch 1: at 6.5 TB/s a B200 SM receives ~23 B/clk = 92 two-bit codes
+// per clock but issues only 128 lane-instructions per clock (LOP3 at half rate), i.e. ~1 instruction
+// per code.  A SIMT unpack + convert + FMA costs >= 3.  Here FOUR codes become an IMMA operand
+// register with ONE `and` (byte-field layout: the masked byte is code * 2^s as a u8) and the
+// multiply-accumulate runs on the tensor pipe as mma.sync.m16n8k32.u8.s8 (512 codes per warp
+// instruction): 12 issue slots per 512 codes instead of 24 for an fp16 HMMA formulation.
+// The activations of a group are turned into integers once per launch: X = rint(x * 2^p) with p
+// chosen from the group's largest exponent (power-of-two step, 15..18 bits), every k slot
+// pre-multiplied by 2^(smax - s) and written as three signed base-256 digits into three columns of the
+// MMA's B operand (batch 1 uses 3 of the 8 columns, so the digits cost no extra MMAs).  The int32
+// accumulators therefore hold EXACT integer dot products; scale / zero are applied once per group
+// in fp32:   y[n] = sum_g  s[n,g] * delta_g * I[n,g] - (zero*scale)[n,g] * sum_k x.
 //
-// Structure: one CTA per SM, 16 consumer warps + 1 producer warp.  A CTA owns whole 32-row blocks
-// (all of K), so the only reduction is across its own warps through shared memory: no global
-// split-K, no atomics, no workspace, bit-identical reruns.  The producer streams the row block's
-// records (contiguous in the native layout) HBM -> smem with cp.async.bulk (TMA engine) through an
-// mbarrier ring; it starts before griddepcontrol.wait, so under programmatic dependent launch the
-// weights of the next linear are already in flight while the previous kernel drains.  When N is
-// too small to occupy the chip (k/v projections, tensor-parallel shards) K is split across a
-// thread-block CLUSTER and the partial sums are reduced through distributed shared memory.
+// Structure: one CTA per SM, 16 consumer warps + 1 producer warp + 1 reducer warp.  A CTA owns whole
+// 32-row blocks (all of K), so the only reduction is across its own warps through shared memory: no
+// global split-K, no atomics, no workspace, bit-identical reruns.  The producer streams the row
+// block's records (contiguous in the native layout) HBM -> smem with cp.async.bulk (TMA engine)
+// through an mbarrier ring; it starts before griddepcontrol.wait, so under programmatic dependent
+// launch the weights of the next linear are already in flight while the previous kernel drains.
+// When N is too small to occupy the chip (k/v projections, tensor-parallel shards) K is split across
+// a thread-block CLUSTER and the partial sums are reduced through distributed shared memory.
 #pragma once
 #include "common.cuh"
 
@@ -34,12 +39,23 @@ __device__ __forceinline__ long long gtime() {
 
 constexpr int kCW = 16;                      // consumer warps
 constexpr int kCThreads = kCW * 32;
-constexpr int kThreads = kCThreads + 64;     // + producer warp + reducer warp = 576 threads (96 registers)
+constexpr int kThreads = kCThreads + 64;     // + producer warp + reducer warp = 576 threads
 constexpr int kStageRecs = kCW;              // records per pipeline stage: one per consumer warp
 constexpr int kMaxProblems = 4;
 constexpr int kXprimeBudget = 72 * 1024;
 constexpr int kSmemTarget = 208 * 1024;
 constexpr int kMaxCluster = 8;
+constexpr uint32_t kMagicI = 0x4B400000u;    // int32 accumulators start at the bit pattern of 1.5 * 2^23 ...
+constexpr float kMagicF = 12582912.f;        // ... so that (float&)acc - 1.5 * 2^23 == the integer sum (|sum| < 2^22)
+
+// kernel kinds: how the activation digits are laid out over the B columns of the MMA
+constexpr int kKindM1 = 0;      // M == 1 (compile-time): columns 0..2 = digits (2^16, 2^8, 2^0), x' built in the CTA
+constexpr int kKindSmall = 1;   // M == 2: column 4 mm + digit
+constexpr int kKindWide = 2;    // M = 3..16: column block `digit * MB + hb` holds rows mm = 8 hb + g
+
+// number of 8-column output blocks and x' geometry
+AMQB_HD constexpr int out_blocks(int M) { return M <= 8 ? 1 : 2; }
+AMQB_HD constexpr int xp_group_bytes(int bits, int M) { return mmas_per_group(bits) * 3 * M * 32; }
 
 struct DevProblem {
   const uint8_t* w;
@@ -53,7 +69,7 @@ struct DevProblem {
   int n_rb, n_g;
   int kc;                // groups per x' chunk (K is walked chunk by chunk when x' would not fit)
   const uint8_t* xg;     // M > 1: this problem's x' variant, built once per launch by xprime_global_kernel
-  const float* xsg;      //        and the matching group sums (NULL at M = 1: built inside the CTA)
+  const float2* xsg;     //        and the matching (group sum, delta) pairs (NULL at M = 1: built inside the CTA)
   int rot;               // row block rb goes to cluster (rb + rot) % ncl: spreads the remainder blocks of
                          // consecutive problems over different CTAs
   int build_mask;        // bit b set: build the x' variant of bit width b when this problem starts (0: reuse)
@@ -68,12 +84,12 @@ struct GemvLaunch {
   int n_stages;          // ring depth
   int stage_bytes;
   int xprime_bytes;      // x' region
-  int xs_floats;         // floats in the xsum region
+  int xs_floats;         // floats in the (xsum, delta) region
   int accbuf_blocks;     // row blocks per CTA that need a smem accumulator (chunked K), else 0
   int copy_recs;         // records per cp.async.bulk (a stage is issued as several bulk copies)
   int dbg_delay_ns;      // debug: consumers idle this long after building x' (0 in production)
   int xp_variants;       // 3: x' kept per bit width so problems sharing x reuse it; 1: rebuilt per problem
-  long long* dbg;        // optional per-CTA timeline (8 x int64 per CTA), NULL in production
+  long long* dbg;        // optional per-CTA timeline (16 x int64 per CTA), NULL in production
 };
 
 // ---- cluster helpers ------------------------------------------------------------------------
@@ -106,38 +122,50 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
       "DONEC_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
 
+__device__ __forceinline__ void imma_16832(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 // ---------------------------------------------------------------------------------------------
-// x' builder.  One warp per (group, column) item; lane l owns k = 4l..4l+3 of the group, which
-// land in four consecutive k slots of one MMA (two half2 stores).  Also writes the group sum of x
-// (times 2^-24, folded into the zero-point term).
-__device__ __forceinline__ void place4(uint8_t* gbase, int M, int col, int m, int s0, int sh, __half2 lo, __half2 hi) {
-  const uint32_t scb = (uint32_t)((15 - sh) << 10) * 0x00010001u;   // half2(2^-sh, 2^-sh)
-  const __half2 sc = *reinterpret_cast<const __half2*>(&scb);
-  uint8_t* dst = gbase + ((size_t)(m * M + col) * 4 + ((s0 & 7) >> 1)) * 8 + (s0 >> 3) * 4;
-  *reinterpret_cast<__half2*>(dst) = __hmul2(lo, sc);
-  *reinterpret_cast<__half2*>(dst + 8) = __hmul2(hi, sc);
+// x' builder.  One warp per (group, activation row) item.  Lane (I = lane >> 2, t = lane & 3) loads
+// x[16 I + 2 t + {0,1}] and x[16 I + 8 + 2 t + {0,1}]: the four k of one A-fragment register of the
+// weight side (layout.cuh: bytes beta = 0..3 <-> pairs 2 I, 2 I + 1, elements 0, 1), so the lane's
+// four integers become the four bytes of one B-fragment word per digit.
+struct XItem {
+  int x18[4];      // rint(x * 2^(32 - e)) in byte order beta = 0..3, |.| < 2^18
+  int e;           // effective biased fp16 exponent of the group's largest magnitude (1..30)
+};
+
+// one slot register: V = X << up, three signed base-256 digits of the four values -> three words
+__device__ __forceinline__ void place_reg(uint8_t* gbase, int C, int col0, int cstride, int t, int m, int half, int up,
+                                          const int (&X)[4]) {
+  uint32_t D[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) D[i] = ((uint32_t)(X[i] << up) + 0x00808080u) ^ 0x00808080u;
+  const uint32_t p01 = __byte_perm(D[0], D[1], 0x5140), p23 = __byte_perm(D[2], D[3], 0x5140);
+  const uint32_t q01 = __byte_perm(D[0], D[1], 0x0062), q23 = __byte_perm(D[2], D[3], 0x0062);
+  const uint32_t wl = __byte_perm(p01, p23, 0x5410), wm = __byte_perm(p01, p23, 0x7632), wh = __byte_perm(q01, q23, 0x5410);
+  uint8_t* dst = gbase + ((size_t)(m * C + col0) * 4 + t) * 8 + half * 4;
+  *reinterpret_cast<uint32_t*>(dst) = wh;                                   // digit 0: weight 2^16
+  *reinterpret_cast<uint32_t*>(dst + (size_t)cstride * 32) = wm;            // digit 1: weight 2^8
+  *reinterpret_cast<uint32_t*>(dst + (size_t)cstride * 64) = wl;            // digit 2: weight 2^0
 }
 
 template <int bits>
-__device__ __forceinline__ void place_item(uint8_t* gbase, int M, int col, int lane, __half2 lo, __half2 hi) {
-  const int k0 = 4 * lane;
-  if (bits == 4) {
-    const int s0 = k0 & 15;
-    place4(gbase, M, col, k0 >> 4, s0, (s0 & 8) ? 4 : 0, lo, hi);
-  } else if (bits == 2) {
-    const int m = k0 >> 4, s0 = k0 & 15;
-    place4(gbase, M, col, m, s0, ((m & 1) ? 4 : 0) + ((s0 & 8) ? 2 : 0), lo, hi);
-  } else {
-    int m, s0, sh;
-    if (k0 < 96) { m = k0 >> 4; s0 = k0 & 15; sh = (s0 & 8) ? 3 : 0; }
-    else if (k0 < 112) { m = 6; s0 = k0 - 96; sh = 6; }
-    else if (k0 < 120) { m = 7; s0 = k0 - 112; sh = 6; }
-    else { m = 7; s0 = 8 + (k0 - 120); sh = 9; }   // split codes, bit 0 (weight 2^0 * 2^-9)
-    place4(gbase, M, col, m, s0, sh, lo, hi);
-    if (k0 >= 120) {                               // bits 1 and 2 of the split codes
-      place4(gbase, M, col, 8, k0 - 120, 8, lo, hi);
-      place4(gbase, M, col, 8, 8 + (k0 - 120), 7, lo, hi);
-    }
+__device__ __forceinline__ void place_item(uint8_t* gbase, int C, int col0, int cstride, int lane, const XItem& it) {
+  const int I = lane >> 2, t = lane & 3;
+  constexpr int down = 18 - x_int_bits(bits);          // X = rint-ish(x18 / 2^down)
+  int X[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) X[i] = down ? ((it.x18[i] + (1 << (down > 0 ? down - 1 : 0))) >> down) : it.x18[i];
+  const LaneReg r0 = lane_reg(bits, I, 0);
+  place_reg(gbase, C, col0, cstride, t, r0.m, r0.half, r0.up, X);
+  if (bits == 3 && I >= 6) {
+    const LaneReg r1 = lane_reg(bits, I, 1);
+    place_reg(gbase, C, col0, cstride, t, r1.m, r1.half, r1.up, X);
   }
 }
 
@@ -161,14 +189,55 @@ __device__ __forceinline__ void finish_item(uint2 a, uint2 b, float rs, __half2&
   }
 }
 
+// group statistics + integer conversion of one item; returns (sum of the group's x-hat, delta') for the epilogue
+__device__ __forceinline__ float2 quantize_item(__half2 lo, __half2 hi, XItem& it) {
+  const uint32_t ua = *reinterpret_cast<const uint32_t*>(&lo) & 0x7FFF7FFFu;
+  const uint32_t ub = *reinterpret_cast<const uint32_t*>(&hi) & 0x7FFF7FFFu;
+  uint32_t mx = __vmaxu2(ua, ub);
+  mx = max(mx & 0xFFFFu, mx >> 16);
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  int e = (int)(mx >> 10);
+  e = e > 30 ? 30 : (e < 1 ? 1 : e);
+  it.e = e;
+  const float F = __int_as_float((127 + 32 - e) << 23);          // |x| < 2^(e-14)  ->  |x * F| < 2^18
+  const float2 a = __half22float2(lo), b = __half22float2(hi);
+  it.x18[0] = __float2int_rn(a.x * F);     // beta 0: pair 2I,   element 0
+  it.x18[1] = __float2int_rn(b.x * F);     // beta 1: pair 2I+1, element 0
+  it.x18[2] = __float2int_rn(a.y * F);     // beta 2: pair 2I,   element 1
+  it.x18[3] = __float2int_rn(b.y * F);     // beta 3: pair 2I+1, element 1
+  const int tot = __reduce_add_sync(0xffffffffu, (it.x18[0] + it.x18[1]) + (it.x18[2] + it.x18[3]));
+  float2 r;
+  r.x = (float)tot * __int_as_float((127 + e - 32) << 23);       // sum of x-hat over the group
+  r.y = __int_as_float((127 + e - 36) << 23);                    // delta' = 2^(e - 36): dot = delta' * (2^16 c0 + 2^8 c1 + c2)
+  return r;
+}
+
+// (xsum, delta) entries of one item.  M1 / Small: entry 4 mm + d = (d == 0 ? xsum : 0, delta' * 2^(8 (2 - d))), entry
+// 4 mm + 3 = 0;  Wide: entry mm = (xsum, delta').  Entries of rows >= M are zeroed by the mm == 0 item.
+template <int KIND>
+__device__ __forceinline__ void store_xsd(float2* xsd_g, int M, int MB, int mm, int lane, float2 sd) {
+  if (KIND == kKindWide) {
+    if (lane == 0) xsd_g[mm] = sd;
+    if (mm == 0 && lane >= M && lane < MB * 8) xsd_g[lane] = make_float2(0.f, 0.f);
+  } else {
+    if (lane < 4) {
+      const float mul = lane == 0 ? 65536.f : (lane == 1 ? 256.f : (lane == 2 ? 1.f : 0.f));
+      xsd_g[4 * mm + lane] = make_float2(lane == 0 ? sd.x : 0.f, sd.y * mul);
+    } else if (mm == 0 && M == 1 && lane < 8) xsd_g[lane] = make_float2(0.f, 0.f);
+  }
+}
+
 // x' of groups [g_lo, g_lo + len) of problem P.  Warp cw builds exactly the groups it will consume
 // (local index gl with gl % kCW == cw: record i of every pipeline stage goes to warp i), so no
 // CTA-wide barrier is needed; only the RMSNorm statistic crosses warps.
-template <bool M1, int PRO>
-__device__ __forceinline__ void build_xprime(const DevProblem& P, int M, int NB, int S, int g_lo, int len, uint8_t* xp,
-                                             float* xs, float* sred, int cw, int lane, bool have_stats, float& rs1,
+template <int KIND, int PRO>
+__device__ __forceinline__ void build_xprime(const DevProblem& P, int M, int MB, int S, int g_lo, int len, uint8_t* xp,
+                                             float2* xsd, float* sred, int cw, int lane, bool have_stats, float& rs1,
                                              int mask, int variants, int var_stride) {
   constexpr int BATCH = 4;
+  constexpr bool M1 = KIND == kKindM1;
+  const int I = lane >> 2, t = lane & 3;
+  const int koff = 16 * I + 2 * t;            // this lane's first k inside a group (second pair at + 8)
   // RMSNorm, batch 1, unsplit K, few groups per warp: x is loaded once and its squares summed from
   // the registers that are then normalised (one pass, one barrier)
   const bool one_pass = PRO == AMQB_PRO_RMSNORM && !have_stats && M1 && S == 1 && (len + kCW - 1) / kCW <= BATCH;
@@ -186,10 +255,10 @@ __device__ __forceinline__ void build_xprime(const DevProblem& P, int M, int NB,
       for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
       if (lane == 0) sred[cw] = ss;
       named_bar_sync(1, kCThreads);
-      float t = 0.f;
+      float tt = 0.f;
 #pragma unroll
-      for (int w = 0; w < kCW; ++w) t += sred[w];
-      rs1 = rsqrtf(t / (float)P.K + P.eps);
+      for (int w = 0; w < kCW; ++w) tt += sred[w];
+      rs1 = rsqrtf(tt / (float)P.K + P.eps);
     } else {   // general case: per-column sum of squares over the FULL row, all warps cooperate
       for (int col = 0; col < M; ++col) {
         float ss = 0.f;
@@ -209,17 +278,26 @@ __device__ __forceinline__ void build_xprime(const DevProblem& P, int M, int NB,
   }
   const int my_groups = (len - cw + kCW - 1) / kCW;     // gl = cw, cw + kCW, ...
   const int items = my_groups > 0 ? my_groups * M : 0;
+  const int C = 3 * M;
   for (int it0 = 0; it0 < items || (one_pass && it0 == 0); it0 += BATCH) {
     uint2 a[BATCH], b[BATCH];
 #pragma unroll
     for (int u = 0; u < BATCH; ++u) {
       const int it = it0 + u;
+      a[u] = make_uint2(0u, 0u); b[u] = make_uint2(0u, 0u);
       if (it < items) {
         const int gi = M1 ? it : it / M, col = M1 ? 0 : it - gi * M;
-        const int kbase = (g_lo + cw + gi * kCW) * kGroup + 4 * lane;
-        a[u] = *reinterpret_cast<const uint2*>(P.x + (size_t)col * P.ldx + kbase);
-        if (PRO == AMQB_PRO_SILU_MUL) b[u] = *reinterpret_cast<const uint2*>(P.x + (size_t)col * P.ldx + P.K + kbase);
-        else if (PRO == AMQB_PRO_RMSNORM) b[u] = *reinterpret_cast<const uint2*>(P.gamma + kbase);
+        const __half* xr = P.x + (size_t)col * P.ldx + (g_lo + cw + gi * kCW) * kGroup + koff;
+        a[u].x = *reinterpret_cast<const uint32_t*>(xr);
+        a[u].y = *reinterpret_cast<const uint32_t*>(xr + 8);
+        if (PRO == AMQB_PRO_SILU_MUL) {
+          b[u].x = *reinterpret_cast<const uint32_t*>(xr + P.K);
+          b[u].y = *reinterpret_cast<const uint32_t*>(xr + P.K + 8);
+        } else if (PRO == AMQB_PRO_RMSNORM) {
+          const __half* gr = P.gamma + (g_lo + cw + gi * kCW) * kGroup + koff;
+          b[u].x = *reinterpret_cast<const uint32_t*>(gr);
+          b[u].y = *reinterpret_cast<const uint32_t*>(gr + 8);
+        }
       }
     }
     if (one_pass) {
@@ -235,17 +313,15 @@ __device__ __forceinline__ void build_xprime(const DevProblem& P, int M, int NB,
       for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
       if (lane == 0) sred[cw] = ss;
       named_bar_sync(1, kCThreads);
-      float t = 0.f;
+      float tt = 0.f;
 #pragma unroll
-      for (int w = 0; w < kCW; ++w) t += sred[w];
-      rs1 = rsqrtf(t / (float)P.K + P.eps);
+      for (int w = 0; w < kCW; ++w) tt += sred[w];
+      rs1 = rsqrtf(tt / (float)P.K + P.eps);
     }
-    float sums[BATCH];
 #pragma unroll
     for (int u = 0; u < BATCH; ++u) {
       const int it = it0 + u;
-      sums[u] = 0.f;
-      if (it < items) {
+      if (it < items) {                      // warp-uniform
         const int gi = M1 ? it : it / M, col = M1 ? 0 : it - gi * M;
         const int gl = cw + gi * kCW;
         float rs = rs1;
@@ -257,45 +333,30 @@ __device__ __forceinline__ void build_xprime(const DevProblem& P, int M, int NB,
         }
         __half2 lo, hi;
         finish_item<PRO>(a[u], b[u], rs, lo, hi);
+        XItem xi;
+        const float2 sd = quantize_item(lo, hi, xi);
+        const int col0 = KIND == kKindWide ? col : 3 * col, cstride = KIND == kKindWide ? M : 1;
         // one activation load / normalisation feeds every bit-width variant the group of problems needs
-        if (mask & 8) place_item<3>(xp + (size_t)(variants == 3 ? 1 : 0) * var_stride + (size_t)gl * 9 * M * 32, M, col, lane, lo, hi);
-        if (mask & 16) place_item<4>(xp + (size_t)(variants == 3 ? 2 : 0) * var_stride + (size_t)gl * 8 * M * 32, M, col, lane, lo, hi);
-        if (mask & 4) place_item<2>(xp + (size_t)gl * 8 * M * 32, M, col, lane, lo, hi);
-        const float2 f0 = __half22float2(lo), f1 = __half22float2(hi);
-        sums[u] = (f0.x + f0.y) + (f1.x + f1.y);
-      }
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1)
-#pragma unroll
-      for (int u = 0; u < BATCH; ++u) sums[u] += __shfl_xor_sync(0xffffffffu, sums[u], o);
-    if (lane == 0) {
-#pragma unroll
-      for (int u = 0; u < BATCH; ++u) {
-        const int it = it0 + u;
-        if (it < items) {
-          const int gi = M1 ? it : it / M, col = M1 ? 0 : it - gi * M;
-          xs[(cw + gi * kCW) * NB * 8 + col] = sums[u] * 5.9604644775390625e-08f;   // 2^-24
-        }
+        if (mask & 4) place_item<2>(xp + (size_t)gl * xp_group_bytes(2, M), C, col0, cstride, lane, xi);
+        if (mask & 8) place_item<3>(xp + (size_t)(variants == 3 ? 1 : 0) * var_stride + (size_t)gl * xp_group_bytes(3, M), C, col0, cstride, lane, xi);
+        if (mask & 16) place_item<4>(xp + (size_t)(variants == 3 ? 2 : 0) * var_stride + (size_t)gl * xp_group_bytes(4, M), C, col0, cstride, lane, xi);
+        store_xsd<KIND>(xsd + (size_t)gl * MB * 8, M, MB, col, lane, sd);
       }
     }
   }
-  if (!M1)
-    for (int gl = cw; gl < len; gl += kCW)
-      for (int i = M + lane; i < NB * 8; i += 32) xs[gl * NB * 8 + i] = 0.f;   // padded columns read by the epilogue
   __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------
-// M > 1: the permuted / pre-scaled activations are built ONCE per launch into global memory (one CTA
-// per activation row) instead of once per CTA; the GEMV CTAs then fetch their chunks with bulk copies.
+// M > 1: the integer activations are built ONCE per launch into global memory (one CTA per
+// activation row) instead of once per CTA; the GEMV CTAs then fetch their chunks with bulk copies.
 struct XgArgs {
   const __half* x;
   const __half* gamma;
   float eps;
-  int ldx, K, M, NB, mask;
-  uint8_t* xg[3];        // x' of the 2 / 3 / 4-bit variants: [group][mmas][M][32 B]
-  float* xsg;            // [group][NB*8] group sums * 2^-24 (padded columns zero)
+  int ldx, K, M, MB, mask;
+  uint8_t* xg[3];        // x' of the 2 / 3 / 4-bit variants: [group][mma][3 M columns][t][8 B]
+  float2* xsg;           // [group][MB*8] (group sum, delta') (padded rows zero)
 };
 
 template <int PRO>
@@ -304,7 +365,8 @@ __global__ void __launch_bounds__(kCThreads) xprime_global_kernel(const XgArgs A
   pdl_launch_dependents();
   pdl_wait();
   const int col = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_g = A.K / kGroup;
+  const int n_g = A.K / kGroup, M = A.M;
+  const int koff = 16 * (lane >> 2) + 2 * (lane & 3);
   float rs = 1.f;
   if (PRO == AMQB_PRO_RMSNORM) {
     float ss = 0.f;
@@ -319,27 +381,34 @@ __global__ void __launch_bounds__(kCThreads) xprime_global_kernel(const XgArgs A
     for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     if (lane == 0) sred[warp] = ss;
     __syncthreads();
-    float t = 0.f;
+    float tt = 0.f;
 #pragma unroll
-    for (int w = 0; w < kCW; ++w) t += sred[w];
-    rs = rsqrtf(t / (float)A.K + A.eps);
+    for (int w = 0; w < kCW; ++w) tt += sred[w];
+    rs = rsqrtf(tt / (float)A.K + A.eps);
   }
+  const bool wide = M > 2;
+  const int C = 3 * M, col0 = wide ? col : 3 * col, cstride = wide ? M : 1;
   for (int gl = warp; gl < n_g; gl += kCW) {
-    const int kbase = gl * kGroup + 4 * lane;
-    uint2 a = *reinterpret_cast<const uint2*>(A.x + (size_t)col * A.ldx + kbase), b = make_uint2(0u, 0u);
-    if (PRO == AMQB_PRO_SILU_MUL) b = *reinterpret_cast<const uint2*>(A.x + (size_t)col * A.ldx + A.K + kbase);
-    else if (PRO == AMQB_PRO_RMSNORM) b = *reinterpret_cast<const uint2*>(A.gamma + kbase);
+    const __half* xr = A.x + (size_t)col * A.ldx + gl * kGroup + koff;
+    uint2 a, b = make_uint2(0u, 0u);
+    a.x = *reinterpret_cast<const uint32_t*>(xr);
+    a.y = *reinterpret_cast<const uint32_t*>(xr + 8);
+    if (PRO == AMQB_PRO_SILU_MUL) {
+      b.x = *reinterpret_cast<const uint32_t*>(xr + A.K);
+      b.y = *reinterpret_cast<const uint32_t*>(xr + A.K + 8);
+    } else if (PRO == AMQB_PRO_RMSNORM) {
+      b.x = *reinterpret_cast<const uint32_t*>(A.gamma + gl * kGroup + koff);
+      b.y = *reinterpret_cast<const uint32_t*>(A.gamma + gl * kGroup + koff + 8);
+    }
     __half2 lo, hi;
     finish_item<PRO>(a, b, rs, lo, hi);
-    if (A.mask & 4) place_item<2>(A.xg[0] + (size_t)gl * 8 * A.M * 32, A.M, col, lane, lo, hi);
-    if (A.mask & 8) place_item<3>(A.xg[1] + (size_t)gl * 9 * A.M * 32, A.M, col, lane, lo, hi);
-    if (A.mask & 16) place_item<4>(A.xg[2] + (size_t)gl * 8 * A.M * 32, A.M, col, lane, lo, hi);
-    const float2 f0 = __half22float2(lo), f1 = __half22float2(hi);
-    float sum = (f0.x + f0.y) + (f1.x + f1.y);
-#pragma unroll
-    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane == 0) A.xsg[gl * A.NB * 8 + col] = sum * 5.9604644775390625e-08f;
-    if (col == 0 && lane >= A.M && lane < A.NB * 8) A.xsg[gl * A.NB * 8 + lane] = 0.f;     // padded columns
+    XItem xi;
+    const float2 sd = quantize_item(lo, hi, xi);
+    if (A.mask & 4) place_item<2>(A.xg[0] + (size_t)gl * xp_group_bytes(2, M), C, col0, cstride, lane, xi);
+    if (A.mask & 8) place_item<3>(A.xg[1] + (size_t)gl * xp_group_bytes(3, M), C, col0, cstride, lane, xi);
+    if (A.mask & 16) place_item<4>(A.xg[2] + (size_t)gl * xp_group_bytes(4, M), C, col0, cstride, lane, xi);
+    if (wide) store_xsd<kKindWide>(A.xsg + (size_t)gl * A.MB * 8, M, A.MB, col, lane, sd);
+    else store_xsd<kKindSmall>(A.xsg + (size_t)gl * A.MB * 8, M, A.MB, col, lane, sd);
   }
 }
 
@@ -363,95 +432,110 @@ static int launch_xprime_global(const XgArgs& A, int pdl, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int BITS, int NB, bool M1>
-__device__ __forceinline__ void process_record(const uint8_t* rec, const uint8_t* xpg, const float* xsg, int M,
-                                               int lane, float (&acc)[2][NB][4]) {
-  constexpr int NW = words_per_tile(BITS), NV = vecs_per_rec(BITS), NM = mmas_per_group(BITS);
-  if (M1) M = 1;                              // compile-time addressing of the B fragments at batch 1
+template <int BITS, int MB, int KIND>
+__device__ __forceinline__ void process_record(const uint8_t* rec, const uint8_t* xpg, const float2* xsd, int M,
+                                               int lane, float (&acc)[2][MB][4]) {
+  constexpr int NWR = words_per_row(BITS), NV = vecs_per_rec(BITS), NM = mmas_per_group(BITS);
+  if (KIND == kKindM1) M = 1;                 // compile-time addressing of the B fragments at batch 1
   const int g = lane >> 2, t = lane & 3;
-  uint32_t w[2 * NW];
+  uint32_t w[4 * NWR];                        // [tile][row half][word]
   const uint4* cv = reinterpret_cast<const uint4*>(rec);
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     const uint4 q = cv[v * 32 + lane];
     w[4 * v] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w;
   }
-  uint32_t bf[NM][NB][2];
-#pragma unroll
-  for (int m = 0; m < NM; ++m)
-#pragma unroll
-    for (int nb = 0; nb < NB; ++nb) {
-      const int col = nb * 8 + g;
-      uint2 b = make_uint2(0u, 0u);
-      if (col < M) b = *reinterpret_cast<const uint2*>(xpg + ((size_t)(m * M + col) * 4 + t) * 8);
-      bf[m][nb][0] = b.x; bf[m][nb][1] = b.y;
-    }
   const __half2* meta = reinterpret_cast<const __half2*>(rec + rec_code_bytes(BITS));
+  const int C = 3 * M;
+  auto afrag = [&](int tile, int m, uint32_t (&a)[4]) {
+    const uint32_t* Wg = w + (tile * 2) * NWR;
+    const uint32_t* Wh = Wg + NWR;
+    a[0] = Wg[rho_word(BITS, 2 * m)] & rho_mask(BITS, 2 * m);
+    a[1] = Wh[rho_word(BITS, 2 * m)] & rho_mask(BITS, 2 * m);
+    a[2] = Wg[rho_word(BITS, 2 * m + 1)] & rho_mask(BITS, 2 * m + 1);
+    a[3] = Wh[rho_word(BITS, 2 * m + 1)] & rho_mask(BITS, 2 * m + 1);
+  };
+  if (KIND != kKindWide) {
+    // columns: 4 mm + digit (digit 3 unused: those lanes re-read digit 2 and are multiplied by a zero delta)
+    int mm = g >> 2;
+    if (mm > M - 1) mm = M - 1;
+    const int dg = (g & 3) > 2 ? 2 : (g & 3);
+    const uint8_t* bsrc = xpg + ((size_t)(3 * mm + dg) * 4 + t) * 8;
+    uint32_t bf[NM][2];
 #pragma unroll
-  for (int tile = 0; tile < 2; ++tile) {
-    const uint32_t* wt = w + tile * NW;
-    float c[2][NB][4];
-#pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-      for (int nb = 0; nb < NB; ++nb)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) c[a][nb][i] = 0.f;
-    auto issue = [&](int m, const uint32_t (&a)[4]) {
-#pragma unroll
-      for (int nb = 0; nb < NB; ++nb) mma_m16n8k16(c[m & 1][nb], a, bf[m][nb][0], bf[m][nb][1], c[m & 1][nb]);
-    };
-    if (BITS == 4) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t x0 = wt[j], x8 = x0 >> 8;
-        const uint32_t a[4] = {x0 & 0x000f000fu, x8 & 0x000f000fu, x0 & 0x00f000f0u, x8 & 0x00f000f0u};
-        issue(j, a);
-      }
-    } else if (BITS == 2) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t x0 = wt[j], x8 = x0 >> 8;
-        const uint32_t a0[4] = {x0 & 0x00030003u, x8 & 0x00030003u, x0 & 0x000c000cu, x8 & 0x000c000cu};
-        issue(2 * j, a0);
-        const uint32_t a1[4] = {x0 & 0x00300030u, x8 & 0x00300030u, x0 & 0x00c000c0u, x8 & 0x00c000c0u};
-        issue(2 * j + 1, a1);
-      }
-    } else {
-      uint32_t e[6], f[6];
-#pragma unroll
-      for (int j = 0; j < 6; ++j) {
-        const uint32_t x0 = wt[j], x6 = x0 >> 6;
-        const uint32_t a[4] = {x0 & 0x00070007u, x6 & 0x00070007u, x0 & 0x00380038u, x6 & 0x00380038u};
-        issue(j, a);
-        e[j] = x6 & 0x01C001C0u;
-        f[j] = x6 & 0x02000200u;
-      }
-      const uint32_t a6[4] = {e[0], e[1], e[2], e[3]};
-      issue(6, a6);
-      const uint32_t a7[4] = {e[4], e[5], f[0], f[1]};
-      issue(7, a7);
-      const uint32_t a8[4] = {f[2], f[3], f[4], f[5]};
-      issue(8, a8);
+    for (int m = 0; m < NM; ++m) {
+      const uint2 b = *reinterpret_cast<const uint2*>(bsrc + (size_t)m * C * 32);
+      bf[m][0] = b.x; bf[m][1] = b.y;
     }
-    // group epilogue: acc += scale * c - (zero*scale) * xsum      (both still carry 2^-24)
-    const float2 m0 = __half22float2(meta[tile * 16 + g]);
-    const float2 m1 = __half22float2(meta[tile * 16 + g + 8]);
+    const float4 xd = *reinterpret_cast<const float4*>(xsd + 2 * t);     // (xsum, delta) of columns 2t, 2t+1
+    int c[2][4];
 #pragma unroll
-    for (int nb = 0; nb < NB; ++nb) {
-      float v[4];
+    for (int tile = 0; tile < 2; ++tile)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = c[0][nb][i] + c[1][nb][i];
-      if (M1) {
-        const float xs0 = xsg[0];
-        acc[tile][nb][0] = fmaf(-m0.y, xs0, fmaf(m0.x, v[0], acc[tile][nb][0]));
-        acc[tile][nb][2] = fmaf(-m1.y, xs0, fmaf(m1.x, v[2], acc[tile][nb][2]));
-      } else {
-        const float2 xs = *reinterpret_cast<const float2*>(xsg + nb * 8 + 2 * t);
-        acc[tile][nb][0] = fmaf(-m0.y, xs.x, fmaf(m0.x, v[0], acc[tile][nb][0]));
-        acc[tile][nb][1] = fmaf(-m0.y, xs.y, fmaf(m0.x, v[1], acc[tile][nb][1]));
-        acc[tile][nb][2] = fmaf(-m1.y, xs.x, fmaf(m1.x, v[2], acc[tile][nb][2]));
-        acc[tile][nb][3] = fmaf(-m1.y, xs.y, fmaf(m1.x, v[3], acc[tile][nb][3]));
+      for (int i = 0; i < 4; ++i) c[tile][i] = (int)kMagicI;
+#pragma unroll
+    for (int m = 0; m < NM; ++m)
+#pragma unroll
+      for (int tile = 0; tile < 2; ++tile) {
+        uint32_t a[4];
+        afrag(tile, m, a);
+        imma_16832(c[tile], a, bf[m][0], bf[m][1]);
+      }
+#pragma unroll
+    for (int tile = 0; tile < 2; ++tile) {
+      // group epilogue: acc += scale * delta * I - (zero*scale) * xsum
+      const float2 m0 = __half22float2(meta[tile * 16 + g]);
+      const float2 m1 = __half22float2(meta[tile * 16 + g + 8]);
+      const float f0 = __int_as_float(c[tile][0]) - kMagicF, f1 = __int_as_float(c[tile][1]) - kMagicF;
+      const float f2 = __int_as_float(c[tile][2]) - kMagicF, f3 = __int_as_float(c[tile][3]) - kMagicF;
+      const float v0 = fmaf(f0, xd.y, f1 * xd.w), v1 = fmaf(f2, xd.y, f3 * xd.w);
+      acc[tile][0][0] = fmaf(-m0.y, xd.x, fmaf(m0.x, v0, acc[tile][0][0]));
+      acc[tile][0][2] = fmaf(-m1.y, xd.x, fmaf(m1.x, v1, acc[tile][0][2]));
+    }
+  } else {
+    // columns of MMA (digit d, block hb): activation rows mm = 8 hb + g  (x' column d * M + mm)
+    int bofs[MB];
+#pragma unroll
+    for (int hb = 0; hb < MB; ++hb) {
+      int mm = hb * 8 + g;
+      if (mm > M - 1) mm = M - 1;
+      bofs[hb] = (mm * 4 + t) * 8;
+    }
+#pragma unroll
+    for (int tile = 0; tile < 2; ++tile) {
+      int c[3][MB][4];
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int hb = 0; hb < MB; ++hb)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) c[d][hb][i] = (int)kMagicI;
+#pragma unroll
+      for (int m = 0; m < NM; ++m) {
+        uint32_t a[4];
+        afrag(tile, m, a);
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+#pragma unroll
+          for (int hb = 0; hb < MB; ++hb) {
+            const uint2 b = *reinterpret_cast<const uint2*>(xpg + (size_t)(m * C + d * M) * 32 + bofs[hb]);
+            imma_16832(c[d][hb], a, b.x, b.y);
+          }
+      }
+      const float2 m0 = __half22float2(meta[tile * 16 + g]);
+      const float2 m1 = __half22float2(meta[tile * 16 + g + 8]);
+#pragma unroll
+      for (int hb = 0; hb < MB; ++hb) {
+        const float4 xd = *reinterpret_cast<const float4*>(xsd + hb * 8 + 2 * t);   // (xsum, delta) of rows 2t, 2t+1
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float dk = (i & 1) ? xd.w : xd.y, xs = (i & 1) ? xd.z : xd.x;
+          const float2 sc = i < 2 ? m0 : m1;
+          const float fh = __int_as_float(c[0][hb][i]) - kMagicF, fm = __int_as_float(c[1][hb][i]) - kMagicF,
+                      fl = __int_as_float(c[2][hb][i]) - kMagicF;
+          const float v = fmaf(fh, 65536.f * dk, fmaf(fm, 256.f * dk, fl * dk));
+          acc[tile][hb][i] = fmaf(-sc.y, xs, fmaf(sc.x, v, acc[tile][hb][i]));
+        }
       }
     }
   }
@@ -469,18 +553,19 @@ __device__ __forceinline__ void store_out(const DevProblem& P, int n, int col, f
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int NB, bool M1, int PRO>
+template <int MB, int KIND, int PRO>
 __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_constant__ GemvLaunch L) {
+  constexpr bool M1 = KIND == kKindM1;
   extern __shared__ __align__(1024) uint8_t smem[];
-  // smem map: [0,256) barriers | xs | sred | x' | red[2] | accbuf | part[4][S] | ring
+  // smem map: [0,384) barriers | (xsum, delta) | sred | x' | red[2] | accbuf | part[4][S] | ring
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);      // [0,NS) full, [NS,2NS) empty, [24,28) cluster-reduce, 28..32 misc
-  float* xs = reinterpret_cast<float*>(smem + 384);
-  float* sred = xs + L.xs_floats;                           // 16 * kCW floats
+  float2* xsd = reinterpret_cast<float2*>(smem + 384);
+  float* sred = reinterpret_cast<float*>(smem + 384) + L.xs_floats;     // 16 * kCW floats
   uint8_t* xp = reinterpret_cast<uint8_t*>(sred + 16 * kCW);
-  float* red = reinterpret_cast<float*>(xp + (size_t)L.xp_variants * L.xprime_bytes);   // [2][kCW][2*NB*128]
-  float* accbuf = red + 2 * kCW * 2 * NB * 128;                        // [accbuf_blocks][2*NB*128]
-  float* part = accbuf + (size_t)L.accbuf_blocks * 2 * NB * 128;       // [count][S][2*NB*128] (S > 1)
-  uint8_t* ring = reinterpret_cast<uint8_t*>(part + (L.S > 1 ? L.count * L.S * 2 * NB * 128 : 0));
+  float* red = reinterpret_cast<float*>(xp + (size_t)L.xp_variants * L.xprime_bytes);   // [2][kCW][2*MB*128]
+  float* accbuf = red + 2 * kCW * 2 * MB * 128;                        // [accbuf_blocks][2*MB*128]
+  float* part = accbuf + (size_t)L.accbuf_blocks * 2 * MB * 128;       // [count][S][2*MB*128] (S > 1)
+  uint8_t* ring = reinterpret_cast<uint8_t*>(part + (L.S > 1 ? L.count * L.S * 2 * MB * 128 : 0));
   ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ring) + 127) & ~uintptr_t(127));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -488,7 +573,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
   const int rank = S > 1 ? (int)cluster_ctarank() : 0;
   const int cid = blockIdx.x >> L.log2S, ncl = gridDim.x >> L.log2S;
   const int NS = L.n_stages;
-  const int M = L.M;
+  const int M = M1 ? 1 : L.M;
 
   AMQB_STAMP(0);
   if (tid == 0) {
@@ -559,25 +644,24 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
         for (int rb = first_rb(cid, P.rot, ncl); rb < P.n_rb; rb += ncl, ++nblk, ++j) {
           const int buf = nblk & 1, use = nblk >> 1;
             mbar_wait(smem_u32(&bars[28 + buf]), use & 1);
-            const float* rbase = red + (size_t)buf * kCW * 2 * NB * 128;
-            constexpr int EPT = M1 ? 1 : 8 * NB;                 // output elements per lane
+            const float* rbase = red + (size_t)buf * kCW * 2 * MB * 128;
+            constexpr int EPT = M1 ? 1 : 8 * MB;                 // output elements per lane
 #pragma unroll
             for (int q = 0; q < EPT; ++q) {
               const int e = M1 ? lane : q * 32 + lane;
               float v = 0.f;
 #pragma unroll
-              for (int w = 0; w < kCW; ++w) v += rbase[w * 2 * NB * 128 + e];
-              v *= 16777216.f;                                   // undo the 2^-24 of the subnormal code encoding
+              for (int w = 0; w < kCW; ++w) v += rbase[w * 2 * MB * 128 + e];
               int row, col;
               if (M1) { row = e; col = 0; }
               else {
-                const int ci = e & 3, ln = (e >> 2) & 31, tn = e >> 7;   // tn = tile*NB + nb
-                const int tile = tn / NB, nb = tn - tile * NB;
+                const int ci = e & 3, ln = (e >> 2) & 31, tn = e >> 7;   // tn = tile*MB + hb
+                const int tile = tn / MB, hb = tn - tile * MB;
                 row = tile * 16 + (ln >> 2) + 8 * (ci >> 1);
-                col = nb * 8 + 2 * (ln & 3) + (ci & 1);
+                col = hb * 8 + 2 * (ln & 3) + (ci & 1);
               }
               if (chunked) {
-                float* ab = accbuf + (size_t)j * 2 * NB * 128 + e;
+                float* ab = accbuf + (size_t)j * 2 * MB * 128 + e;
                 if (!first_chunk) v += *ab;
                 if (!last_chunk) *ab = v;
               }
@@ -586,7 +670,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
                   if (col < M) store_out(P, rb * 32 + row, col, v);
                 } else {
                   // K was split across the cluster: partial sums meet in rank 0's shared memory (DSMEM)
-                  float* pslot = part + (size_t)(p * S + rank) * 2 * NB * 128 + e;
+                  float* pslot = part + (size_t)(p * S + rank) * 2 * MB * 128 + e;
                   if (rank != 0) st_dsmem_f32(smem_u32(pslot), 0, v);
                   else *pslot = v;
                 }
@@ -605,14 +689,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
                   if (M1) { row = e; col = 0; }
                   else {
                     const int ci = e & 3, ln = (e >> 2) & 31, tn = e >> 7;
-                    const int tile = tn / NB, nb = tn - tile * NB;
+                    const int tile = tn / MB, hb = tn - tile * MB;
                     row = tile * 16 + (ln >> 2) + 8 * (ci >> 1);
-                    col = nb * 8 + 2 * (ln & 3) + (ci & 1);
+                    col = hb * 8 + 2 * (ln & 3) + (ci & 1);
                   }
                   if (col < M) {
-                    float t = 0.f;
-                    for (int r = 0; r < S; ++r) t += part[(size_t)(p * S + r) * 2 * NB * 128 + e];
-                    store_out(P, rb * 32 + row, col, t);
+                    float tt = 0.f;
+                    for (int r = 0; r < S; ++r) tt += part[(size_t)(p * S + r) * 2 * MB * 128 + e];
+                    store_out(P, rb * 32 + row, col, tt);
                   }
                 }
               }
@@ -628,7 +712,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
   // ===== consumers
   pdl_wait();                        // x / residual come from the previous kernel
   AMQB_STAMP(1);
-  float acc[2][NB][4];
+  float acc[2][MB][4];
   int s = 0, ph = 0, nblk = 0;
   const __half* cur_x = nullptr;     // x' cache: problems of a group that share x (q/k/v, gate/up)
   int cur_K = 0, built_mask = 0, stat_par = 0, run_mask = 0;
@@ -637,7 +721,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
   for (int p = 0; p < L.count; ++p) {
     const DevProblem& P = L.prob[p];
     const uint32_t rbytes = rec_bytes(P.bits);
-    const int NM = mmas_per_group(P.bits);
+    const int gbytes = xp_group_bytes(P.bits, M);
     const int g_lo = (P.n_g * rank) >> L.log2S, g_hi = (P.n_g * (rank + 1)) >> L.log2S;
     const bool chunked = (g_hi - g_lo) > P.kc;
     AMQB_STAMP(4 + 4 * p);
@@ -648,7 +732,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
     uint8_t* xpv = xp + (L.xp_variants == 3 ? (size_t)(P.bits - 2) * L.xprime_bytes : 0);
     for (int c_lo = g_lo; c_lo < g_hi; c_lo += P.kc) {
       const int c_hi = (c_lo + P.kc) < g_hi ? (c_lo + P.kc) : g_hi;
-      const bool first_chunk = c_lo == g_lo, last_chunk = c_hi == g_hi;
       // x' variants to (re)build now: chunked K or a single variant buffer -> this problem's own; else
       // whatever the host scheduled at this problem (all bit widths of the problems sharing this x)
       if (P.xg) {
@@ -656,41 +739,40 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
         named_bar_sync(1, kCThreads);              // every warp is done with the previous chunk's x'
         const uint32_t xb = smem_u32(&bars[32]);
         if (tid == 0) {
-          const uint32_t bx = (uint32_t)(c_hi - c_lo) * NM * M * 32, bs = (uint32_t)(c_hi - c_lo) * NB * 8 * 4;
+          const uint32_t bx = (uint32_t)(c_hi - c_lo) * gbytes, bs = (uint32_t)(c_hi - c_lo) * MB * 8 * 8;
           mbar_expect_tx(xb, bx + bs);
-          bulk_g2s(smem_u32(xpv), P.xg + (size_t)c_lo * NM * M * 32, bx, xb);
-          bulk_g2s(smem_u32(xs), P.xsg + (size_t)c_lo * NB * 8, bs, xb);
+          bulk_g2s(smem_u32(xpv), P.xg + (size_t)c_lo * gbytes, bx, xb);
+          bulk_g2s(smem_u32(xsd), P.xsg + (size_t)c_lo * MB * 8, bs, xb);
         }
         mbar_wait(xb, xphase);
         xphase ^= 1;
       } else {
-      const int want = (chunked || L.xp_variants != 3) ? (1 << P.bits) : ((run_mask | (1 << P.bits)) & ~built_mask);
-      if (want)
-        build_xprime<M1, PRO>(P, M, NB, S, c_lo, c_hi - c_lo, xp, xs, sred + ((M1 && stat_par) ? kCW : 0), warp, lane,
-                              same_x && built_mask != 0, rs1, want, L.xp_variants, L.xprime_bytes);
-      built_mask |= want | (1 << P.bits);
+        const int want = (chunked || L.xp_variants != 3) ? (1 << P.bits) : ((run_mask | (1 << P.bits)) & ~built_mask);
+        if (want)
+          build_xprime<KIND, PRO>(P, M, MB, S, c_lo, c_hi - c_lo, xp, xsd, sred + ((M1 && stat_par) ? kCW : 0), warp, lane,
+                                  same_x && built_mask != 0, rs1, want, L.xp_variants, L.xprime_bytes);
+        built_mask |= want | (1 << P.bits);
       }
       if (L.dbg_delay_ns) { const long long t_end = gtime() + L.dbg_delay_ns; while (gtime() < t_end) {} }
       AMQB_STAMP(5 + 4 * p);
-      int j = 0;
-      for (int rb = first_rb(cid, P.rot, ncl); rb < P.n_rb; rb += ncl, ++nblk, ++j) {
+      for (int rb = first_rb(cid, P.rot, ncl); rb < P.n_rb; rb += ncl, ++nblk) {
 #pragma unroll
         for (int a = 0; a < 2; ++a)
 #pragma unroll
-          for (int nb = 0; nb < NB; ++nb)
+          for (int hb = 0; hb < MB; ++hb)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc[a][nb][i] = 0.f;
+            for (int i = 0; i < 4; ++i) acc[a][hb][i] = 0.f;
         for (int g = c_lo; g < c_hi; g += kStageRecs) {
           const int nrec = (c_hi - g) < kStageRecs ? (c_hi - g) : kStageRecs;
           mbar_wait(smem_u32(&bars[s]), ph);
           if (warp < nrec) {
             const uint8_t* rec = ring + (size_t)s * L.stage_bytes + (size_t)warp * rbytes;
             const int gl = g - c_lo + warp;
-            const uint8_t* xpg = xpv + (size_t)gl * NM * M * 32;
-            const float* xsg = xs + gl * NB * 8;
-            if (P.bits == 3) process_record<3, NB, M1>(rec, xpg, xsg, M, lane, acc);
-            else if (P.bits == 4) process_record<4, NB, M1>(rec, xpg, xsg, M, lane, acc);
-            else process_record<2, NB, M1>(rec, xpg, xsg, M, lane, acc);
+            const uint8_t* xpg = xpv + (size_t)gl * gbytes;
+            const float2* xsg = xsd + gl * MB * 8;
+            if (P.bits == 3) process_record<3, MB, KIND>(rec, xpg, xsg, M, lane, acc);
+            else if (P.bits == 4) process_record<4, MB, KIND>(rec, xpg, xsg, M, lane, acc);
+            else process_record<2, MB, KIND>(rec, xpg, xsg, M, lane, acc);
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bars[NS + s]));
@@ -698,23 +780,39 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
         }
         AMQB_STAMP(6 + 4 * p);
         // ---- (chunk of a) row block done.  Every warp deposits its partial sums in a double-buffered
-        // shared-memory area and moves straight on; ONE warp (rotating) waits for all deposits, sums
-        // them in fixed order and stores / hands off.  mbarriers only: no CTA-wide barrier on this path.
+        // shared-memory area and moves straight on; ONE warp waits for all deposits, sums them in
+        // fixed order and stores / hands off.  mbarriers only: no CTA-wide barrier on this path.
         const int buf = nblk & 1, use = nblk >> 1;
         if (use > 0) mbar_wait(smem_u32(&bars[30 + buf]), (use - 1) & 1);       // red[buf] free again
-        float* myred = red + (size_t)(buf * kCW + warp) * 2 * NB * 128;
-        if (M1) {
-          if ((lane & 3) == 0) {
+        float* myred = red + (size_t)(buf * kCW + warp) * 2 * MB * 128;
+        if (KIND != kKindWide) {
+          // the digits of one output sit in lanes t and t^1: fold them, lanes with even t hold row totals of mm = t >> 1
 #pragma unroll
-            for (int a = 0; a < 2; ++a) { myred[a * 16 + (lane >> 2)] = acc[a][0][0]; myred[a * 16 + (lane >> 2) + 8] = acc[a][0][2]; }
+          for (int a = 0; a < 2; ++a) {
+            acc[a][0][0] += __shfl_xor_sync(0xffffffffu, acc[a][0][0], 1);
+            acc[a][0][2] += __shfl_xor_sync(0xffffffffu, acc[a][0][2], 1);
+          }
+          if (M1) {
+            if ((lane & 3) == 0) {
+#pragma unroll
+              for (int a = 0; a < 2; ++a) { myred[a * 16 + (lane >> 2)] = acc[a][0][0]; myred[a * 16 + (lane >> 2) + 8] = acc[a][0][2]; }
+            }
+          } else if ((lane & 1) == 0) {
+            // same element order as the wide deposit (float4 per (tile, lane)): column mm -> lane t = 0, component 2 rh + mm
+            const int mm = (lane & 3) >> 1;
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+              myred[(a * 32 + (lane & ~3)) * 4 + mm] = acc[a][0][0];
+              myred[(a * 32 + (lane & ~3)) * 4 + 2 + mm] = acc[a][0][2];
+            }
           }
         } else {
 #pragma unroll
           for (int a = 0; a < 2; ++a)
 #pragma unroll
-            for (int nb = 0; nb < NB; ++nb)
-              reinterpret_cast<float4*>(myred)[(a * NB + nb) * 32 + lane] =
-                  make_float4(acc[a][nb][0], acc[a][nb][1], acc[a][nb][2], acc[a][nb][3]);
+            for (int hb = 0; hb < MB; ++hb)
+              reinterpret_cast<float4*>(myred)[(a * MB + hb) * 32 + lane] =
+                  make_float4(acc[a][hb][0], acc[a][hb][1], acc[a][hb][2], acc[a][hb][3]);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars[28 + buf]));
@@ -726,9 +824,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
 }
 
 
-template <int NB, bool M1, int PRO>
+template <int MB, int KIND, int PRO>
 static int launch_variant(const GemvLaunch& L, int grid, size_t smem, int pdl, cudaStream_t st) {
-  auto kern = gemv_mma_kernel<NB, M1, PRO>;
+  auto kern = gemv_mma_kernel<MB, KIND, PRO>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
@@ -766,9 +864,9 @@ static int launch_variant(const GemvLaunch& L, int grid, size_t smem, int pdl, c
 // one translation unit per prologue kind instantiates this (gemv_pro0.cu / gemv_pro1.cu / gemv_pro2.cu)
 template <int PRO>
 static int launch_pro(const GemvLaunch& L, int grid, size_t smem, int pdl, cudaStream_t st) {
-  if (L.M == 1) return launch_variant<1, true, PRO>(L, grid, smem, pdl, st);
-  if (L.M <= 8) return launch_variant<1, false, PRO>(L, grid, smem, pdl, st);
-  return launch_variant<2, false, PRO>(L, grid, smem, pdl, st);
+  if (L.M == 1) return launch_variant<1, kKindM1, PRO>(L, grid, smem, pdl, st);
+  if (L.M == 2) return launch_variant<1, kKindSmall, PRO>(L, grid, smem, pdl, st);
+  return launch_variant<1, kKindWide, PRO>(L, grid, smem, pdl, st);     // M = 3..8 (larger M: two passes, gemv_api.cu)
 }
 
 int launch_pro0(const GemvLaunch& L, int grid, size_t smem, int pdl, cudaStream_t st);

@@ -10,13 +10,26 @@
 //        = exactly (bits + 0.25) bits per weight: AMQ's own accounting
 //          (amq/utils/func.py:101-114).
 //
-// Inside a record, lane L (g = L>>2, t = L&3) owns 2*nw 32-bit words (nw per
-// tile, tile 0 first), stored as uint4 vector v of lane L at
-// (v*32 + L)*16 bytes.  Every word is laid out so that ONE bitwise AND yields
-// an mma.sync.m16n8k16 A-fragment register: two codes sit 16 bits apart (the
-// even / odd k slot of the fragment) at a bit offset s with s + bits <= 11, so
-// the masked 16-bit lanes, read as fp16 (sub)normals, equal code * 2^s * 2^-24
-// exactly.  The matching activation slot is pre-scaled by 2^-s.
+// Inside a record, lane L (g = L>>2, t = L&3) owns, for each of the two tiles, rows g and g+8 and
+// of each row the 32 codes  k = 8 i + 2 t + e   (pair i = 0..15, e = 0/1)  — the ownership of an
+// mma.sync A fragment and of tcgen05.st.16x128b alike.  The lane's words are ordered
+//   [tile][row half r (g, g+8)][word j]       (nw/2 words per row),   word index w = (tile*2 + r)*nw/2 + j,
+// stored as component (w & 3) of uint4 vector (w >> 2) of the lane at byte ((w>>2)*32 + L)*16.
+//
+// BYTE-FIELD rule: every code (or code fragment) lives inside ONE byte, so that a single AND of a
+// word with a byte-replicated mask is an mma.sync.m16n8k32 (u8 x s8 -> s32, IMMA) A-fragment
+// register holding four k slots, each equal to  field * 2^s  (s = bit offset of the field inside
+// its byte).  The matching activation slot is pre-multiplied by 2^(smax - s) (integer, exact), so
+// all slots of a group accumulate  2^smax * code * X  in one int32 accumulator.
+// Byte beta of a word holds pair i = i0(word, field) + (beta & 1), element e = beta >> 1; the two
+// elements of a pair therefore sit 16 bits apart, which is what the fp16 dequantiser of the prefill
+// kernel wants (one AND with a 16-bit-replicated mask gives a code pair).
+//   4-bit  byte = [c:0-3][c:4-7]                      pair i = 4 j + 2 f + b
+//   2-bit  byte = [c:0-1][c:2-3][c:4-5][c:6-7]        pair i = 8 j + 2 f + b
+//   3-bit  byte = [c:0-2][c:3-5][x:6-7]               pair i = 4 j + 2 f + b   (f = 0, 1; j = 0..2)
+//          the 8 "split" codes of a row (pairs 12..15) are stored as code>>1 in bits 6-7 of the
+//          bytes of words 0 and 1 (pair 12 + 2 j + b) and code&1 in bit 6 (pairs 12, 13) / bit 7
+//          (pairs 14, 15) of the bytes of word 2: exactly 3.0 bits per code, nothing wasted.
 #pragma once
 #include <stdint.h>
 
@@ -31,70 +44,98 @@ namespace amqb {
 constexpr int kGroup = 128;      // k per group (AMQ: group_size 128 everywhere)
 constexpr int kRowsPerRec = 32;  // two m16 tiles
 
-AMQB_HD constexpr int words_per_tile(int bits) { return bits == 2 ? 4 : (bits == 3 ? 6 : 8); }
-AMQB_HD constexpr int vecs_per_rec(int bits) { return bits; }            // 2*nw/4
-AMQB_HD constexpr int mmas_per_group(int bits) { return bits == 3 ? 9 : 8; }
+AMQB_HD constexpr int words_per_tile(int bits) { return 2 * bits; }       // both rows (g, g+8) of a tile
+AMQB_HD constexpr int words_per_row(int bits) { return bits; }
+AMQB_HD constexpr int vecs_per_rec(int bits) { return bits; }             // 2 tiles * words_per_tile / 4
+AMQB_HD constexpr int mmas_per_group(int bits) { return bits == 3 ? 5 : 4; }   // m16n8k32 per tile and group
 AMQB_HD constexpr int rec_code_bytes(int bits) { return bits * 512; }
 AMQB_HD constexpr int rec_bytes(int bits) { return bits * 512 + 128; }
+// integer activation format of the decode kernel: slot value = X << (smax - s), |X| < 2^xbits, xbits + smax = 22
+AMQB_HD constexpr int shift_max(int bits) { return bits == 2 ? 6 : (bits == 3 ? 7 : 4); }
+AMQB_HD constexpr int x_int_bits(int bits) { return 22 - shift_max(bits); }
 
-// Where one code bit-field of a native word comes from.
+// Where one bit-field of a native word comes from.
 struct FieldSrc {
-  int row;    // 0..15 inside the tile
   int k;      // 0..127 inside the group
   int lsb;    // first bit of the code stored in this field
-  int nbits;  // bits of the code stored here (bits, or 1 for a 3-bit leftover)
-  int pos;    // bit position inside the 16-bit half
+  int nbits;  // bits of the code stored here (0: no such field)
+  int pos;    // bit position inside the byte
 };
 
-// Field f of 16-bit half h (0 = even slot) of word j of lane (g, t).
-// Returns the number of fields per half via n_fields().
-AMQB_HD constexpr int n_fields(int bits) { return bits == 2 ? 8 : (bits == 3 ? 6 : 4); }
+AMQB_HD constexpr int n_fields(int bits) { return bits == 4 ? 2 : 4; }
 
-AMQB_HD FieldSrc field_src(int bits, int j, int h, int f, int g, int t) {
+// Field f of byte beta of word j (of one row) of a lane with t = lane & 3.
+AMQB_HD FieldSrc field_src(int bits, int j, int beta, int f, int t) {
   FieldSrc s{};
-  const int kk = 2 * t + h;
+  const int b = beta & 1, e = beta >> 1;
+  int i = 0;
   if (bits == 4) {
-    // word j <-> MMA j (k = 16j + slot).  nibble f: rows g (f<2) / g+8, slots kk (f even) / 8+kk
-    s.row = g + 8 * (f >> 1);
-    s.k = 16 * j + 8 * (f & 1) + kk;
-    s.lsb = 0; s.nbits = 4; s.pos = 4 * f;
+    i = 4 * j + 2 * f + b; s.lsb = 0; s.nbits = 4; s.pos = 4 * f;
   } else if (bits == 2) {
-    // word j <-> MMAs 2j, 2j+1.  field f (2 bits at 2f): f&3 -> (mma parity, slot half), f>>2 -> row half
-    const int fl = f & 3;
-    s.row = g + 8 * (f >> 2);
-    s.k = 16 * (2 * j + (fl >> 1)) + 8 * (fl & 1) + kk;
-    s.lsb = 0; s.nbits = 2; s.pos = 2 * f;
+    i = 8 * j + 2 * f + b; s.lsb = 0; s.nbits = 2; s.pos = 2 * f;
   } else {
-    // 3-bit: half = A[0:3) B[3:6) C[6:9) D[9:12) E[12:15) F[15]
-    s.lsb = 0; s.nbits = 3; s.pos = 3 * f;
-    if (f < 4) {              // A,B: row g ; C,D: row g+8 ; A,C: slots kk ; B,D: slots 8+kk ; MMA j
-      s.row = g + 8 * (f >> 1);
-      s.k = 16 * j + 8 * (f & 1) + kk;
-    } else if (f == 4) {      // E_j: row g + 8*(j&1), k = 96 + 8*(j>>1) + kk
-      s.row = g + 8 * (j & 1);
-      s.k = 96 + 8 * (j >> 1) + kk;
-    } else {                  // F_j: bit (j>>1) of the split code k = 120 + kk, row g + 8*(j&1)
-      s.row = g + 8 * (j & 1);
-      s.k = 120 + kk;
-      s.lsb = j >> 1; s.nbits = 1; s.pos = 15;
-    }
+    if (f < 2) { i = 4 * j + 2 * f + b; s.lsb = 0; s.nbits = 3; s.pos = 3 * f; }
+    else if (j < 2) {
+      if (f == 2) { i = 12 + 2 * j + b; s.lsb = 1; s.nbits = 2; s.pos = 6; }
+      else s.nbits = 0;
+    } else { i = 12 + 2 * (f - 2) + b; s.lsb = 0; s.nbits = 1; s.pos = 4 + f; }
   }
+  s.k = 8 * i + 2 * t + e;
   return s;
 }
 
-// Activation side: MMA m (0..mmas-1), k slot s (0..15) of a group multiplies
-// x[k_of] * 2^-shift.
+// IMMA side.  Per row the masked registers are numbered rho = 0..2*mmas-1; MMA m of a tile takes
+// rho = 2m (k slots 0..15: a0 / a1) and rho = 2m+1 (k slots 16..31: a2 / a3).
+//   4-bit  rho = 2 j + f            mask 0x0F0F0F0F << 4 f                  s = 4 f
+//   2-bit  rho = 4 j + f            mask 0x03030303 << 2 f                  s = 2 f
+//   3-bit  rho = 3 j + f (j < 2, f < 3; j = 2, f < 2), 8 = (word 2, bit 6), 9 = (word 2, bit 7)
+//          masks 0x07.., 0x38.., 0xC0.. (s = 0, 3, 5: the 2-bit fragment stands for code>>1) , 0x40.. (6), 0x80.. (7)
+// Activation side: k slot sl (0..31) of MMA m multiplies x[k] * 2^(smax - shift).
 struct SlotSrc { int k; int shift; };
 
-AMQB_HD SlotSrc slot_src(int bits, int m, int s) {
+AMQB_HD SlotSrc slot_src(int bits, int m, int sl) {
   SlotSrc r{};
-  if (bits == 4) { r.k = 16 * m + s; r.shift = (s < 8) ? 0 : 4; }
-  else if (bits == 2) { r.k = 16 * m + s; r.shift = ((m & 1) ? 4 : 0) + ((s < 8) ? 0 : 2); }
+  const int half = sl >> 4, t = (sl >> 2) & 3, beta = sl & 3, b = beta & 1, e = beta >> 1;
+  const int rho = 2 * m + half;
+  int i = 0;
+  if (bits == 4) { const int j = rho >> 1, f = rho & 1; i = 4 * j + 2 * f + b; r.shift = 4 * f; }
+  else if (bits == 2) { const int j = rho >> 2, f = rho & 3; i = 8 * j + 2 * f + b; r.shift = 2 * f; }
   else {
-    if (m < 6) { r.k = 16 * m + s; r.shift = (s < 8) ? 0 : 3; }
-    else if (m == 6) { r.k = 96 + s; r.shift = 6; }
-    else if (m == 7) { if (s < 8) { r.k = 112 + s; r.shift = 6; } else { r.k = 120 + (s - 8); r.shift = 9; } }
-    else { if (s < 8) { r.k = 120 + s; r.shift = 8; } else { r.k = 120 + (s - 8); r.shift = 7; } }
+    if (rho < 8) {
+      const int j = rho / 3, f = rho - 3 * j;
+      if (f < 2) { i = 4 * j + 2 * f + b; r.shift = 3 * f; }
+      else { i = 12 + 2 * j + b; r.shift = 5; }
+    } else { i = 12 + 2 * (rho - 8) + b; r.shift = rho - 2; }
+  }
+  r.k = 8 * i + 2 * t + e;
+  return r;
+}
+
+// weight side of the decode kernel: masked register rho of a row = word rho_word & rho_mask
+AMQB_HD constexpr int rho_word(int bits, int rho) {
+  return bits == 4 ? (rho >> 1) : (bits == 2 ? (rho >> 2) : (rho < 8 ? rho / 3 : 2));
+}
+AMQB_HD constexpr uint32_t rho_mask(int bits, int rho) {
+  return bits == 4 ? ((rho & 1) ? 0xF0F0F0F0u : 0x0F0F0F0Fu)
+       : bits == 2 ? (0x03030303u << (2 * (rho & 3)))
+       : rho == 8 ? 0x40404040u : rho == 9 ? 0x80808080u
+       : (rho % 3 == 0 ? 0x07070707u : (rho % 3 == 1 ? 0x38383838u : 0xC0C0C0C0u));
+}
+
+// activation side of the decode kernel: builder lane (I = lane >> 2, t = lane & 3) holds x[16 I + 2 t + {0, 1}] and
+// x[16 I + 8 + 2 t + {0, 1}] as bytes beta = 0..3 (k = 16 I + 8 (beta & 1) + 2 t + (beta >> 1)) and writes them,
+// multiplied by 2^up, into k slots  half * 16 + 4 t + beta  of MMA m: one register, two for the 3-bit split codes.
+struct LaneReg { int m, half, up; };
+AMQB_HD constexpr int lane_regs(int bits, int I) { return (bits == 3 && I >= 6) ? 2 : 1; }
+AMQB_HD LaneReg lane_reg(int bits, int I, int idx) {
+  LaneReg r{};
+  if (bits == 4) { r.m = I >> 1; r.half = I & 1; r.up = 4 - 4 * (I & 1); }
+  else if (bits == 2) { r.m = I >> 1; r.half = I & 1; r.up = 6 - 2 * (I & 3); }
+  else if (I < 6) { const int j = I >> 1, f = I & 1, rho = 3 * j + f; r.m = rho >> 1; r.half = rho & 1; r.up = 7 - 3 * f; }
+  else {
+    const int w = I - 6;      // code>>1 in bits 6-7 of word w (rho = 2 / 5), code&1 in bit 6 / 7 of word 2 (rho = 8 / 9)
+    if (idx == 0) { r.m = w ? 2 : 1; r.half = w; r.up = 2; }
+    else { r.m = 4; r.half = w; r.up = 1 - w; }
   }
   return r;
 }

@@ -89,43 +89,39 @@ __global__ void unpack_ft_kernel(const uint16_t* __restrict__ qw, uint8_t* __res
   codes[idx] = (uint8_t)((qw[word] >> (4 * nib)) & 0xF);
 }
 
-// Native: thread = (record, tile, lane) owns rows g, g+8 x 32 k's each.
+// Native: thread = (record, tile, row half, lane) owns one row x 32 k's (layout.cuh).
 __global__ void unpack_native_kernel(int bits, const uint8_t* __restrict__ wn, uint8_t* __restrict__ codes,
                                      int N, int K) {
   const int NG = K / kGroup;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)(N / kRowsPerRec) * NG * 64;
+  const long long total = (long long)(N / kRowsPerRec) * NG * 128;
   if (tid >= total) return;
   const int lane = (int)(tid & 31);
-  const int tile = (int)((tid >> 5) & 1);
-  const long long rec = tid >> 6;
+  const int r = (int)((tid >> 5) & 1);
+  const int tile = (int)((tid >> 6) & 1);
+  const long long rec = tid >> 7;
   const int rb = (int)(rec / NG), grp = (int)(rec - (long long)rb * NG);
   const int g = lane >> 2, t = lane & 3;
-  const int nw = words_per_tile(bits);
+  const int nwr = words_per_row(bits);
   const uint32_t* base = reinterpret_cast<const uint32_t*>(wn + (size_t)rec * rec_bytes(bits));
   const int nf = n_fields(bits);
-  // zero the split codes first (3-bit leftovers are OR-ed bit by bit)
-  if (bits == 3) {
-    for (int h = 0; h < 2; ++h)
-      for (int rr = 0; rr < 2; ++rr) {
-        const int row = rb * 32 + tile * 16 + g + 8 * rr;
-        codes[(size_t)row * K + grp * kGroup + 120 + 2 * t + h] = 0;
-      }
-  }
-  for (int j = 0; j < nw; ++j) {
-    const int i = tile * nw + j;            // word index inside the lane's 2*nw words
-    const uint32_t w = base[((i >> 2) * 32 + lane) * 4 + (i & 3)];
-    for (int h = 0; h < 2; ++h) {
-      const uint32_t half = (w >> (16 * h)) & 0xFFFFu;
+  uint8_t q[32];                           // this lane's codes, index 2 i + e  (k = 8 i + 2 t + e)
+  for (int i = 0; i < 32; ++i) q[i] = 0;
+  for (int j = 0; j < nwr; ++j) {
+    const int wi = (tile * 2 + r) * nwr + j;          // word index inside the lane's 4*nwr words
+    const uint32_t w = base[((wi >> 2) * 32 + lane) * 4 + (wi & 3)];
+    for (int beta = 0; beta < 4; ++beta) {
+      const uint32_t byte = (w >> (8 * beta)) & 0xFFu;
       for (int f = 0; f < nf; ++f) {
-        const FieldSrc s = field_src(bits, j, h, f, g, t);
-        const uint32_t v = (half >> s.pos) & ((1u << s.nbits) - 1u);
-        const size_t o = (size_t)(rb * 32 + tile * 16 + s.row) * K + grp * kGroup + s.k;
-        if (s.nbits == bits) codes[o] = (uint8_t)v;
-        else codes[o] |= (uint8_t)(v << s.lsb);
+        const FieldSrc s = field_src(bits, j, beta, f, t);
+        if (s.nbits == 0) continue;
+        const uint32_t v = (byte >> s.pos) & ((1u << s.nbits) - 1u);
+        q[((s.k >> 3) << 1) | (s.k & 1)] |= (uint8_t)(v << s.lsb);
       }
     }
   }
+  uint8_t* out = codes + (size_t)(rb * 32 + tile * 16 + g + 8 * r) * K + grp * kGroup;
+  for (int i = 0; i < 16; ++i) { out[8 * i + 2 * t] = q[2 * i]; out[8 * i + 2 * t + 1] = q[2 * i + 1]; }
 }
 
 // ------------------------------------------------------------------ pack native
@@ -133,27 +129,30 @@ __global__ void unpack_native_kernel(int bits, const uint8_t* __restrict__ wn, u
 __global__ void pack_native_codes_kernel(int bits, const uint8_t* __restrict__ codes, uint8_t* __restrict__ wn,
                                          int N, int K) {
   const int NG = K / kGroup;
-  const int wpr = 8 * bits * 32 / 2;   // words per record = 2*nw*32 (nw = 2*bits)
+  const int wpr = bits * 128;          // words per record = 4 * words_per_row * 32 lanes
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)(N / kRowsPerRec) * NG * wpr;
   if (tid >= total) return;
   const long long rec = tid / wpr;
-  const int wi = (int)(tid - rec * wpr);      // = (v*32 + lane)*4 + c
-  const int c = wi & 3, lane = (wi >> 2) & 31, v = wi >> 7;
-  const int i = v * 4 + c;
-  const int nw = words_per_tile(bits);
-  const int tile = i / nw, j = i - tile * nw;
+  const int wi0 = (int)(tid - rec * wpr);      // = (v*32 + lane)*4 + c
+  const int c = wi0 & 3, lane = (wi0 >> 2) & 31, v = wi0 >> 7;
+  const int wi = v * 4 + c;                    // word index inside the lane
+  const int nwr = words_per_row(bits);
+  const int tr = wi / nwr, j = wi - tr * nwr;
+  const int tile = tr >> 1, r = tr & 1;
   const int rb = (int)(rec / NG), grp = (int)(rec - (long long)rb * NG);
   const int g = lane >> 2, t = lane & 3;
   const int nf = n_fields(bits);
+  const uint8_t* src = codes + (size_t)(rb * 32 + tile * 16 + g + 8 * r) * K + grp * kGroup;
   uint32_t w = 0;
-  for (int h = 0; h < 2; ++h)
+  for (int beta = 0; beta < 4; ++beta)
     for (int f = 0; f < nf; ++f) {
-      const FieldSrc s = field_src(bits, j, h, f, g, t);
-      const uint32_t q = codes[(size_t)(rb * 32 + tile * 16 + s.row) * K + grp * kGroup + s.k];
-      w |= ((q >> s.lsb) & ((1u << s.nbits) - 1u)) << (s.pos + 16 * h);
+      const FieldSrc s = field_src(bits, j, beta, f, t);
+      if (s.nbits == 0) continue;
+      const uint32_t q = src[s.k];
+      w |= ((q >> s.lsb) & ((1u << s.nbits) - 1u)) << (s.pos + 8 * beta);
     }
-  reinterpret_cast<uint32_t*>(wn + (size_t)rec * rec_bytes(bits))[wi] = w;
+  reinterpret_cast<uint32_t*>(wn + (size_t)rec * rec_bytes(bits))[wi0] = w;
 }
 
 // meta_mode 0: GPTQ  fp32 scales[K/G,N], zeros[K/G,N] (= zero*scale)
@@ -342,7 +341,7 @@ int amqb_unpack_codes(int bits, int layout, const void* packed, uint8_t* codes_o
     }
     case AMQB_LAYOUT_NATIVE: {
       if (!native_shape_ok(N, K, G)) return fail(AMQB_ERR_UNSUPPORTED_SHAPE, "unpack native: N % 32, K % 128, G == 128");
-      const long long threads = (long long)(N / 32) * (K / 128) * 64;
+      const long long threads = (long long)(N / 32) * (K / 128) * 128;
       unpack_native_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(bits, (const uint8_t*)packed, codes_out, N, K);
       break;
     }

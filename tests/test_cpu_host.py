@@ -38,6 +38,15 @@ def test_library_exports_every_declared_symbol():
     assert lib.amqb_native_bytes(3, 100, 4096) == 0 and lib.amqb_native_bytes(5, 64, 128) == 0
 
 
+def test_native_layout_index_math(tmp_path):
+    """Host emulation of the byte-field layout (layout.cuh): pack -> masked IMMA registers x integer activation
+    slots == 2^smax * sum(code * X) for every row and bit width; every code bit stored exactly once."""
+    exe = str(tmp_path / "layout_check")
+    subprocess.run(["g++", "-O1", "-std=c++17", os.path.join(ROOT, "tests", "native", "layout_check.cpp"), "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "layout ok" in out.stdout, out.stdout + out.stderr
+
+
 def test_no_cpu_fallback():
     import amq_b200
     from amq_b200 import ops
