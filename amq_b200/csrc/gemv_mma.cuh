@@ -35,7 +35,8 @@ __device__ __forceinline__ long long gtime() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-#define AMQB_STAMP(i) do { if (L.dbg && tid == 0) L.dbg[blockIdx.x * 16 + (i)] = gtime(); } while (0)
+// debug timeline: per-CTA SM clock stamps (slot 0 = entry) written by thread 0
+#define AMQB_STAMP(i) do { if (L.dbg && tid == 0) L.dbg[blockIdx.x * 16 + (i)] = clock64(); } while (0)
 
 constexpr int kCW = 16;                      // consumer warps
 constexpr int kCThreads = kCW * 32;
@@ -134,38 +135,44 @@ __device__ __forceinline__ void imma_16832(int (&c)[4], const uint32_t (&a)[4], 
 // x[16 I + 2 t + {0,1}] and x[16 I + 8 + 2 t + {0,1}]: the four k of one A-fragment register of the
 // weight side (layout.cuh: bytes beta = 0..3 <-> pairs 2 I, 2 I + 1, elements 0, 1), so the lane's
 // four integers become the four bytes of one B-fragment word per digit.
-struct XItem {
-  int x18[4];      // rint(x * 2^(32 - e)) in byte order beta = 0..3, |.| < 2^18
-  int e;           // effective biased fp16 exponent of the group's largest magnitude (1..30)
+// The builder runs once per launch in every CTA on the launch's critical path and is bound by the
+// half-rate integer pipe, so it is written for instruction count: float -> biased integer with one FFMA
+// (magic constant), one IADD turns it into "digits + 128", three PRMT levels transpose 4 values x 3 digits.
+
+// per-lane constants of one x' variant (bit width): where the lane's register(s) go and their scaling
+struct XLane {
+  int off0, fexp0;        // register 0: byte offset inside the group's x' block; exponent of the multiplier is fexp - e
+  int off1, fexp1;        // second register of the 3-bit split-code lanes (off1 < 0: none)
 };
-
-// one slot register: V = X << up, three signed base-256 digits of the four values -> three words
-__device__ __forceinline__ void place_reg(uint8_t* gbase, int C, int col0, int cstride, int t, int m, int half, int up,
-                                          const int (&X)[4]) {
-  uint32_t D[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) D[i] = ((uint32_t)(X[i] << up) + 0x00808080u) ^ 0x00808080u;
-  const uint32_t p01 = __byte_perm(D[0], D[1], 0x5140), p23 = __byte_perm(D[2], D[3], 0x5140);
-  const uint32_t q01 = __byte_perm(D[0], D[1], 0x0062), q23 = __byte_perm(D[2], D[3], 0x0062);
-  const uint32_t wl = __byte_perm(p01, p23, 0x5410), wm = __byte_perm(p01, p23, 0x7632), wh = __byte_perm(q01, q23, 0x5410);
-  uint8_t* dst = gbase + ((size_t)(m * C + col0) * 4 + t) * 8 + half * 4;
-  *reinterpret_cast<uint32_t*>(dst) = wh;                                   // digit 0: weight 2^16
-  *reinterpret_cast<uint32_t*>(dst + (size_t)cstride * 32) = wm;            // digit 1: weight 2^8
-  *reinterpret_cast<uint32_t*>(dst + (size_t)cstride * 64) = wl;            // digit 2: weight 2^0
-}
-
-template <int bits>
-__device__ __forceinline__ void place_item(uint8_t* gbase, int C, int col0, int cstride, int lane, const XItem& it) {
+__device__ __forceinline__ XLane make_xlane(int bits, int lane, int C, int col0) {
   const int I = lane >> 2, t = lane & 3;
-  constexpr int down = 18 - x_int_bits(bits);          // X = rint-ish(x18 / 2^down)
-  int X[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) X[i] = down ? ((it.x18[i] + (1 << (down > 0 ? down - 1 : 0))) >> down) : it.x18[i];
+  XLane x;
   const LaneReg r0 = lane_reg(bits, I, 0);
-  place_reg(gbase, C, col0, cstride, t, r0.m, r0.half, r0.up, X);
+  x.off0 = ((r0.m * C + col0) * 4 + t) * 8 + r0.half * 4;
+  x.fexp0 = 127 + x_int_bits(bits) + 14 + r0.up;
+  x.off1 = -1; x.fexp1 = 127;
   if (bits == 3 && I >= 6) {
     const LaneReg r1 = lane_reg(bits, I, 1);
-    place_reg(gbase, C, col0, cstride, t, r1.m, r1.half, r1.up, X);
+    x.off1 = ((r1.m * C + col0) * 4 + t) * 8 + r1.half * 4;
+    x.fexp1 = 127 + x_int_bits(bits) + 14 + r1.up;
+  }
+  return x;
+}
+
+// one slot register: V_i = rint(x_i * 2^(fexp - 127 - e)), three signed base-256 digits of the four values -> three words
+__device__ __forceinline__ void emit_reg(uint8_t* dst, int dstride, const float (&xf)[4], int fexp, int e, bool valid) {
+  const float Fm = __int_as_float((fexp - e) << 23);
+  uint32_t D[4];                      // V + 0x808080: byte d of D = digit d + 128
+#pragma unroll
+  for (int i = 0; i < 4; ++i) D[i] = (uint32_t)__float_as_int(fmaf(xf[i], Fm, kMagicF)) - (kMagicI - 0x00808080u);
+  const uint32_t p01 = __byte_perm(D[0], D[1], 0x5140), p23 = __byte_perm(D[2], D[3], 0x5140);
+  const uint32_t q01 = __byte_perm(D[0], D[1], 0x0062), q23 = __byte_perm(D[2], D[3], 0x0062);
+  const uint32_t wl = __byte_perm(p01, p23, 0x5410) ^ 0x80808080u, wm = __byte_perm(p01, p23, 0x7632) ^ 0x80808080u,
+                 wh = __byte_perm(q01, q23, 0x5410) ^ 0x80808080u;
+  if (valid) {
+    *reinterpret_cast<uint32_t*>(dst) = wh;                    // digit 0: weight 2^16
+    *reinterpret_cast<uint32_t*>(dst + dstride) = wm;          // digit 1: weight 2^8
+    *reinterpret_cast<uint32_t*>(dst + 2 * dstride) = wl;      // digit 2: weight 2^0
   }
 }
 
@@ -189,8 +196,9 @@ __device__ __forceinline__ void finish_item(uint2 a, uint2 b, float rs, __half2&
   }
 }
 
-// group statistics + integer conversion of one item; returns (sum of the group's x-hat, delta') for the epilogue
-__device__ __forceinline__ float2 quantize_item(__half2 lo, __half2 hi, XItem& it) {
+// group statistics of one item: effective exponent e of the largest magnitude, the four values as floats in
+// byte order (beta 0..3 = pair 2I el 0, pair 2I+1 el 0, pair 2I el 1, pair 2I+1 el 1), and (sum of x-hat, delta')
+__device__ __forceinline__ float2 item_stats(__half2 lo, __half2 hi, float (&xf)[4], int& e_out) {
   const uint32_t ua = *reinterpret_cast<const uint32_t*>(&lo) & 0x7FFF7FFFu;
   const uint32_t ub = *reinterpret_cast<const uint32_t*>(&hi) & 0x7FFF7FFFu;
   uint32_t mx = __vmaxu2(ua, ub);
@@ -198,151 +206,130 @@ __device__ __forceinline__ float2 quantize_item(__half2 lo, __half2 hi, XItem& i
   mx = __reduce_max_sync(0xffffffffu, mx);
   int e = (int)(mx >> 10);
   e = e > 30 ? 30 : (e < 1 ? 1 : e);
-  it.e = e;
-  const float F = __int_as_float((127 + 32 - e) << 23);          // |x| < 2^(e-14)  ->  |x * F| < 2^18
+  e_out = e;
   const float2 a = __half22float2(lo), b = __half22float2(hi);
-  it.x18[0] = __float2int_rn(a.x * F);     // beta 0: pair 2I,   element 0
-  it.x18[1] = __float2int_rn(b.x * F);     // beta 1: pair 2I+1, element 0
-  it.x18[2] = __float2int_rn(a.y * F);     // beta 2: pair 2I,   element 1
-  it.x18[3] = __float2int_rn(b.y * F);     // beta 3: pair 2I+1, element 1
-  const int tot = __reduce_add_sync(0xffffffffu, (it.x18[0] + it.x18[1]) + (it.x18[2] + it.x18[3]));
+  xf[0] = a.x; xf[1] = b.x; xf[2] = a.y; xf[3] = b.y;
+  // sum of x over the group in 18-bit fixed point relative to the group's largest exponent (exact integer adds)
+  const float F18 = __int_as_float((127 + 32 - e) << 23);          // |x| < 2^(e-14)  ->  |x * F18| < 2^18
+  uint32_t sum = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) sum += (uint32_t)__float_as_int(fmaf(xf[i], F18, kMagicF));
+  const int tot = (int)(__reduce_add_sync(0xffffffffu, sum) - 128u * kMagicI);   // mod 2^32
   float2 r;
-  r.x = (float)tot * __int_as_float((127 + e - 32) << 23);       // sum of x-hat over the group
-  r.y = __int_as_float((127 + e - 36) << 23);                    // delta' = 2^(e - 36): dot = delta' * (2^16 c0 + 2^8 c1 + c2)
+  r.x = (float)tot * __int_as_float((127 + e - 32) << 23);         // sum of x-hat over the group
+  r.y = __int_as_float((127 + e - 36) << 23);                      // delta' = 2^(e - 36): dot = delta' * (2^16 c0 + 2^8 c1 + c2)
   return r;
 }
 
 // (xsum, delta) entries of one item.  M1 / Small: entry 4 mm + d = (d == 0 ? xsum : 0, delta' * 2^(8 (2 - d))), entry
 // 4 mm + 3 = 0;  Wide: entry mm = (xsum, delta').  Entries of rows >= M are zeroed by the mm == 0 item.
 template <int KIND>
-__device__ __forceinline__ void store_xsd(float2* xsd_g, int M, int MB, int mm, int lane, float2 sd) {
+__device__ __forceinline__ void store_xsd(float2* xsd_g, int M, int MB, int mm, int lane, float2 sd, bool valid) {
   if (KIND == kKindWide) {
-    if (lane == 0) xsd_g[mm] = sd;
-    if (mm == 0 && lane >= M && lane < MB * 8) xsd_g[lane] = make_float2(0.f, 0.f);
+    if (valid && lane == 0) xsd_g[mm] = sd;
+    if (valid && mm == 0 && lane >= M && lane < MB * 8) xsd_g[lane] = make_float2(0.f, 0.f);
   } else {
-    if (lane < 4) {
-      const float mul = lane == 0 ? 65536.f : (lane == 1 ? 256.f : (lane == 2 ? 1.f : 0.f));
-      xsd_g[4 * mm + lane] = make_float2(lane == 0 ? sd.x : 0.f, sd.y * mul);
-    } else if (mm == 0 && M == 1 && lane < 8) xsd_g[lane] = make_float2(0.f, 0.f);
+    // lane d < 3 of the item's four entries: 2^(8 (2 - d)) as a float is exponent 127 + 16 - 8 d
+    const float mul = lane < 3 ? __int_as_float((143 - 8 * lane) << 23) : 0.f;
+    if (valid && lane < 4) xsd_g[4 * mm + lane] = make_float2(lane == 0 ? sd.x : 0.f, sd.y * mul);
+    if (valid && KIND == kKindM1 && lane >= 4 && lane < 8) xsd_g[lane] = make_float2(0.f, 0.f);
   }
 }
 
-// x' of groups [g_lo, g_lo + len) of problem P.  Warp cw builds exactly the groups it will consume
-// (local index gl with gl % kCW == cw: record i of every pipeline stage goes to warp i), so no
-// CTA-wide barrier is needed; only the RMSNorm statistic crosses warps.
-template <int KIND, int PRO>
-__device__ __forceinline__ void build_xprime(const DevProblem& P, int M, int MB, int S, int g_lo, int len, uint8_t* xp,
+// everything one item writes: all requested bit-width variants + its (xsum, delta) entries
+template <int KIND>
+__device__ __forceinline__ void emit_item(__half2 lo, __half2 hi, const XLane (&xl)[3], int mask, uint8_t* const (&vbase)[3],
+                                          const int (&gbytes)[3], int gl, int dstride, float2* xsd_g, int M, int MB, int mm,
+                                          int lane, bool valid) {
+  float xf[4];
+  int e;
+  const float2 sd = item_stats(lo, hi, xf, e);
+#pragma unroll
+  for (int v = 0; v < 3; ++v)
+    if (mask & (4 << v)) {                               // warp-uniform
+      uint8_t* g = vbase[v] + (size_t)gl * gbytes[v];
+      emit_reg(g + xl[v].off0, dstride, xf, xl[v].fexp0, e, valid);
+      if (v == 1) emit_reg(g + (xl[v].off1 < 0 ? 0 : xl[v].off1), dstride, xf, xl[v].fexp1, e, valid && xl[v].off1 >= 0);
+    }
+  store_xsd<KIND>(xsd_g, M, MB, mm, lane, sd, valid);
+}
+
+template <int PRO>
+__device__ __forceinline__ void load_item(const DevProblem& P, int col, int group, int koff, uint2& a, uint2& b) {
+  const __half* xr = P.x + (size_t)col * P.ldx + group * kGroup + koff;
+  a.x = *reinterpret_cast<const uint32_t*>(xr);
+  a.y = *reinterpret_cast<const uint32_t*>(xr + 8);
+  b = make_uint2(0u, 0u);
+  if (PRO == AMQB_PRO_SILU_MUL) {
+    b.x = *reinterpret_cast<const uint32_t*>(xr + P.K);
+    b.y = *reinterpret_cast<const uint32_t*>(xr + P.K + 8);
+  } else if (PRO == AMQB_PRO_RMSNORM) {
+    const __half* gr = P.gamma + group * kGroup + koff;
+    b.x = *reinterpret_cast<const uint32_t*>(gr);
+    b.y = *reinterpret_cast<const uint32_t*>(gr + 8);
+  }
+}
+
+// Batch 1: x' of groups [g_lo, g_lo + len) of problem P, built inside the CTA.  Warp cw builds exactly the groups
+// it will consume (local index gl with gl % kCW == cw: record i of every pipeline stage goes to warp i), so no
+// CTA-wide barrier is needed; only the RMSNorm statistic crosses warps.  Two items per iteration, branch-free
+// (predicated stores), so the two dependency chains interleave.
+template <int PRO>
+__device__ __forceinline__ void build_xprime(const DevProblem& P, int S, int g_lo, int len, uint8_t* xp,
                                              float2* xsd, float* sred, int cw, int lane, bool have_stats, float& rs1,
-                                             int mask, int variants, int var_stride) {
-  constexpr int BATCH = 4;
-  constexpr bool M1 = KIND == kKindM1;
-  const int I = lane >> 2, t = lane & 3;
-  const int koff = 16 * I + 2 * t;            // this lane's first k inside a group (second pair at + 8)
-  // RMSNorm, batch 1, unsplit K, few groups per warp: x is loaded once and its squares summed from
-  // the registers that are then normalised (one pass, one barrier)
-  const bool one_pass = PRO == AMQB_PRO_RMSNORM && !have_stats && M1 && S == 1 && (len + kCW - 1) / kCW <= BATCH;
-  if (PRO == AMQB_PRO_RMSNORM && !have_stats && !one_pass) {
-    if (M1 && S == 1) {
+                                             int mask, int variants, int var_stride, long long* dbgp = nullptr) {
+  const int koff = 16 * (lane >> 2) + 2 * (lane & 3);     // this lane's first k inside a group (second pair at + 8)
+  if (dbgp) dbgp[3] = clock64();
+  if (PRO == AMQB_PRO_RMSNORM && !have_stats) {
+    float ss = 0.f;
+    if (S == 1) {
       // every warp sums the squares of the groups it owns; together the warps cover the whole row
-      float ss = 0.f;
       for (int gl = cw; gl < len; gl += kCW) {
         const uint2 v = *reinterpret_cast<const uint2*>(P.x + (g_lo + gl) * kGroup + 4 * lane);
         const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
         const float2 b2 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
         ss += a.x * a.x + a.y * a.y + b2.x * b2.x + b2.y * b2.y;
       }
-#pragma unroll
-      for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-      if (lane == 0) sred[cw] = ss;
-      named_bar_sync(1, kCThreads);
-      float tt = 0.f;
-#pragma unroll
-      for (int w = 0; w < kCW; ++w) tt += sred[w];
-      rs1 = rsqrtf(tt / (float)P.K + P.eps);
-    } else {   // general case: per-column sum of squares over the FULL row, all warps cooperate
-      for (int col = 0; col < M; ++col) {
-        float ss = 0.f;
-        const uint2* xr = reinterpret_cast<const uint2*>(P.x + (size_t)col * P.ldx);
-        for (int i = cw * 32 + lane; i < P.K / 4; i += kCThreads) {
-          const uint2 v = xr[i];
-          const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
-          const float2 b2 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
-          ss += a.x * a.x + a.y * a.y + b2.x * b2.x + b2.y * b2.y;
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        if (lane == 0) sred[col * kCW + cw] = ss;
+    } else {   // K split across the cluster: the statistic still spans the FULL row
+      const uint2* xr = reinterpret_cast<const uint2*>(P.x);
+      for (int i = cw * 32 + lane; i < P.K / 4; i += kCThreads) {
+        const uint2 v = xr[i];
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+        const float2 b2 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+        ss += a.x * a.x + a.y * a.y + b2.x * b2.x + b2.y * b2.y;
       }
-      named_bar_sync(1, kCThreads);
     }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) sred[cw] = ss;
+    named_bar_sync(1, kCThreads);
+    float tt = 0.f;
+#pragma unroll
+    for (int w = 0; w < kCW; ++w) tt += sred[w];
+    rs1 = rsqrtf(tt / (float)P.K + P.eps);
   }
-  const int my_groups = (len - cw + kCW - 1) / kCW;     // gl = cw, cw + kCW, ...
-  const int items = my_groups > 0 ? my_groups * M : 0;
-  const int C = 3 * M;
-  for (int it0 = 0; it0 < items || (one_pass && it0 == 0); it0 += BATCH) {
-    uint2 a[BATCH], b[BATCH];
+  XLane xl[3];
+  uint8_t* vbase[3];
+  int gbytes[3];
 #pragma unroll
-    for (int u = 0; u < BATCH; ++u) {
-      const int it = it0 + u;
-      a[u] = make_uint2(0u, 0u); b[u] = make_uint2(0u, 0u);
-      if (it < items) {
-        const int gi = M1 ? it : it / M, col = M1 ? 0 : it - gi * M;
-        const __half* xr = P.x + (size_t)col * P.ldx + (g_lo + cw + gi * kCW) * kGroup + koff;
-        a[u].x = *reinterpret_cast<const uint32_t*>(xr);
-        a[u].y = *reinterpret_cast<const uint32_t*>(xr + 8);
-        if (PRO == AMQB_PRO_SILU_MUL) {
-          b[u].x = *reinterpret_cast<const uint32_t*>(xr + P.K);
-          b[u].y = *reinterpret_cast<const uint32_t*>(xr + P.K + 8);
-        } else if (PRO == AMQB_PRO_RMSNORM) {
-          const __half* gr = P.gamma + (g_lo + cw + gi * kCW) * kGroup + koff;
-          b[u].x = *reinterpret_cast<const uint32_t*>(gr);
-          b[u].y = *reinterpret_cast<const uint32_t*>(gr + 8);
-        }
-      }
-    }
-    if (one_pass) {
-      float ss = 0.f;
-#pragma unroll
-      for (int u = 0; u < BATCH; ++u)
-        if (u < items) {
-          const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&a[u].x));
-          const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&a[u].y));
-          ss += x0.x * x0.x + x0.y * x0.y + x1.x * x1.x + x1.y * x1.y;
-        }
-#pragma unroll
-      for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-      if (lane == 0) sred[cw] = ss;
-      named_bar_sync(1, kCThreads);
-      float tt = 0.f;
-#pragma unroll
-      for (int w = 0; w < kCW; ++w) tt += sred[w];
-      rs1 = rsqrtf(tt / (float)P.K + P.eps);
-    }
-#pragma unroll
-    for (int u = 0; u < BATCH; ++u) {
-      const int it = it0 + u;
-      if (it < items) {                      // warp-uniform
-        const int gi = M1 ? it : it / M, col = M1 ? 0 : it - gi * M;
-        const int gl = cw + gi * kCW;
-        float rs = rs1;
-        if (PRO == AMQB_PRO_RMSNORM && !(M1 && S == 1)) {
-          float ss = 0.f;
-#pragma unroll
-          for (int w = 0; w < kCW; ++w) ss += sred[col * kCW + w];
-          rs = rsqrtf(ss / (float)P.K + P.eps);
-        }
-        __half2 lo, hi;
-        finish_item<PRO>(a[u], b[u], rs, lo, hi);
-        XItem xi;
-        const float2 sd = quantize_item(lo, hi, xi);
-        const int col0 = KIND == kKindWide ? col : 3 * col, cstride = KIND == kKindWide ? M : 1;
-        // one activation load / normalisation feeds every bit-width variant the group of problems needs
-        if (mask & 4) place_item<2>(xp + (size_t)gl * xp_group_bytes(2, M), C, col0, cstride, lane, xi);
-        if (mask & 8) place_item<3>(xp + (size_t)(variants == 3 ? 1 : 0) * var_stride + (size_t)gl * xp_group_bytes(3, M), C, col0, cstride, lane, xi);
-        if (mask & 16) place_item<4>(xp + (size_t)(variants == 3 ? 2 : 0) * var_stride + (size_t)gl * xp_group_bytes(4, M), C, col0, cstride, lane, xi);
-        store_xsd<KIND>(xsd + (size_t)gl * MB * 8, M, MB, col, lane, sd);
-      }
-    }
+  for (int v = 0; v < 3; ++v) {
+    xl[v] = make_xlane(v + 2, lane, 3, 0);
+    vbase[v] = xp + (size_t)(variants == 3 ? v : 0) * var_stride;
+    gbytes[v] = xp_group_bytes(v + 2, 1);
+  }
+  const int items = len > cw ? (len - cw + kCW - 1) / kCW : 0;      // gl = cw, cw + kCW, ...
+  for (int it = 0; it < items; it += 2) {
+    const bool v1 = it + 1 < items;
+    const int gl0 = cw + it * kCW, gl1 = v1 ? gl0 + kCW : gl0;
+    uint2 a0, b0, a1, b1;
+    load_item<PRO>(P, 0, g_lo + gl0, koff, a0, b0);
+    load_item<PRO>(P, 0, g_lo + gl1, koff, a1, b1);
+    __half2 lo0, hi0, lo1, hi1;
+    finish_item<PRO>(a0, b0, rs1, lo0, hi0);
+    finish_item<PRO>(a1, b1, rs1, lo1, hi1);
+    if (dbgp && it == 0) dbgp[14] = clock64() + ((*reinterpret_cast<uint32_t*>(&lo0) ^ *reinterpret_cast<uint32_t*>(&lo1)) == 0x12345678u);
+    emit_item<kKindM1>(lo0, hi0, xl, mask, vbase, gbytes, gl0, 32, xsd + (size_t)gl0 * 8, 1, 1, 0, lane, true);
+    emit_item<kKindM1>(lo1, hi1, xl, mask, vbase, gbytes, gl1, 32, xsd + (size_t)gl1 * 8, 1, 1, 0, lane, v1);
   }
   __syncwarp();
 }
@@ -388,6 +375,11 @@ __global__ void __launch_bounds__(kCThreads) xprime_global_kernel(const XgArgs A
   }
   const bool wide = M > 2;
   const int C = 3 * M, col0 = wide ? col : 3 * col, cstride = wide ? M : 1;
+  XLane xl[3];
+  int gbytes[3];
+#pragma unroll
+  for (int v = 0; v < 3; ++v) { xl[v] = make_xlane(v + 2, lane, C, col0); gbytes[v] = xp_group_bytes(v + 2, M); }
+  uint8_t* const vbase[3] = {A.xg[0], A.xg[1], A.xg[2]};
   for (int gl = warp; gl < n_g; gl += kCW) {
     const __half* xr = A.x + (size_t)col * A.ldx + gl * kGroup + koff;
     uint2 a, b = make_uint2(0u, 0u);
@@ -402,13 +394,9 @@ __global__ void __launch_bounds__(kCThreads) xprime_global_kernel(const XgArgs A
     }
     __half2 lo, hi;
     finish_item<PRO>(a, b, rs, lo, hi);
-    XItem xi;
-    const float2 sd = quantize_item(lo, hi, xi);
-    if (A.mask & 4) place_item<2>(A.xg[0] + (size_t)gl * xp_group_bytes(2, M), C, col0, cstride, lane, xi);
-    if (A.mask & 8) place_item<3>(A.xg[1] + (size_t)gl * xp_group_bytes(3, M), C, col0, cstride, lane, xi);
-    if (A.mask & 16) place_item<4>(A.xg[2] + (size_t)gl * xp_group_bytes(4, M), C, col0, cstride, lane, xi);
-    if (wide) store_xsd<kKindWide>(A.xsg + (size_t)gl * A.MB * 8, M, A.MB, col, lane, sd);
-    else store_xsd<kKindSmall>(A.xsg + (size_t)gl * A.MB * 8, M, A.MB, col, lane, sd);
+    float2* xsd_g = A.xsg + (size_t)gl * A.MB * 8;
+    if (wide) emit_item<kKindWide>(lo, hi, xl, A.mask, vbase, gbytes, gl, cstride * 32, xsd_g, M, A.MB, col, lane, true);
+    else emit_item<kKindSmall>(lo, hi, xl, A.mask, vbase, gbytes, gl, cstride * 32, xsd_g, M, A.MB, col, lane, true);
   }
 }
 
@@ -596,6 +584,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
   if (warp == kCW) {
     // ===== producer: weights do not depend on the previous kernel, so no griddepcontrol.wait here
     if (lane == 0) {
+      if (L.dbg_delay_ns < -1) { const long long t_end = gtime() - L.dbg_delay_ns; while (gtime() < t_end) {} }
       const uint64_t pol = policy_evict_first();
       int s = 0, ph = 0;
       bool wrapped = false;
@@ -713,7 +702,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
   pdl_wait();                        // x / residual come from the previous kernel
   AMQB_STAMP(1);
   float acc[2][MB][4];
-  int s = 0, ph = 0, nblk = 0;
+  int s = 0, ph = 0, nblk = 0, dbg_round = 0;
   const __half* cur_x = nullptr;     // x' cache: problems of a group that share x (q/k/v, gate/up)
   int cur_K = 0, built_mask = 0, stat_par = 0, run_mask = 0;
   uint32_t xphase = 0;
@@ -748,12 +737,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
         xphase ^= 1;
       } else {
         const int want = (chunked || L.xp_variants != 3) ? (1 << P.bits) : ((run_mask | (1 << P.bits)) & ~built_mask);
-        if (want)
-          build_xprime<KIND, PRO>(P, M, MB, S, c_lo, c_hi - c_lo, xp, xsd, sred + ((M1 && stat_par) ? kCW : 0), warp, lane,
-                                  same_x && built_mask != 0, rs1, want, L.xp_variants, L.xprime_bytes);
+        if (want && M1)
+          build_xprime<PRO>(P, S, c_lo, c_hi - c_lo, xp, xsd, sred + (stat_par ? kCW : 0), warp, lane,
+                            same_x && built_mask != 0, rs1, want, L.xp_variants, L.xprime_bytes,
+                            (L.dbg && tid == 0) ? L.dbg + blockIdx.x * 16 : nullptr);
         built_mask |= want | (1 << P.bits);
       }
-      if (L.dbg_delay_ns) { const long long t_end = gtime() + L.dbg_delay_ns; while (gtime() < t_end) {} }
+      if (L.dbg_delay_ns > 0) { const long long t_end = gtime() + L.dbg_delay_ns; while (gtime() < t_end) {} }
       AMQB_STAMP(5 + 4 * p);
       for (int rb = first_rb(cid, P.rot, ncl); rb < P.n_rb; rb += ncl, ++nblk) {
 #pragma unroll
@@ -777,6 +767,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bars[NS + s]));
           if (++s == NS) { s = 0; ph ^= 1; }
+          if (L.dbg && tid == 0 && dbg_round < 8) L.dbg[blockIdx.x * 16 + 8 + dbg_round++] = clock64();
         }
         AMQB_STAMP(6 + 4 * p);
         // ---- (chunk of a) row block done.  Every warp deposits its partial sums in a double-buffered

@@ -18,8 +18,9 @@ for w in pool[:20]:
     ops.gemv_grouped([ops.make_problem(bits, w, x, y, N, K)], ws)
 torch.cuda.synchronize()
 L = _lib.lib()
-for trial in range(3):
-    dbg = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
+print(f"--- bits {bits} N {N} K {K} M {M}")
+for trial in range(2):
+    dbg = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
     L.amqb_debug_set_timeline(ctypes.c_void_p(dbg.data_ptr()))
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -27,12 +28,17 @@ for trial in range(3):
     e1.record()
     torch.cuda.synchronize()
     L.amqb_debug_set_timeline(None)
-    d = dbg.cpu().view(148, 8).double()
+    d = dbg.cpu().view(148, 16).double()
     d = d[d[:, 0] > 0]
-    t0 = d[:, 0].min()
-    names = ["entry", "after pdl_wait", "x' built", "last block: records done", "last block: stored", "-", "exit"]
-    print(f"trial {trial}: event time {e0.elapsed_time(e1)*1e3:.1f} us")
-    for i, nme in enumerate(names):
-        if i == 5: continue
-        col = d[:, i] - t0
-        print(f"  {nme:26s} min {col.min()/1e3:7.2f}  median {col.median()/1e3:7.2f}  max {col.max()/1e3:7.2f} us")
+    t0 = d[:, 0:1]                     # SM clocks are per-SM: everything relative to the CTA's own entry stamp
+    d = torch.where(d > 0, (d - t0) / 1.965 + 1e-3, torch.zeros_like(d))   # ns at 1965 MHz
+    t0 = 0.0
+    names = {0: "entry", 1: "after pdl_wait", 4: "problem start", 3: "builder entry", 14: "x data arrived", 5: "x' built", 8: "round 0 done", 9: "round 1 done", 10: "round 2 done",
+             11: "round 3 done", 12: "round 4 done", 13: "round 5 done", 6: "last block: records done", 7: "last block: deposited", 2: "consumer exit"}
+    print(f"trial {trial}: event time {e0.elapsed_time(e1)*1e3:.1f} us, {d.shape[0]} CTAs")
+    for i, nme in names.items():
+        col = d[:, i]
+        col = col[col > 0] - t0
+        if col.numel() == 0:
+            continue
+        print(f"  {nme:26s} n={col.numel():3d} min {col.min()/1e3:7.2f}  median {col.median()/1e3:7.2f}  max {col.max()/1e3:7.2f} us")
