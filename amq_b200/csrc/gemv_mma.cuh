@@ -35,8 +35,16 @@ __device__ __forceinline__ long long gtime() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-// debug timeline: per-CTA SM clock stamps (slot 0 = entry) written by thread 0
+// debug timeline: per-CTA SM clock stamps (slot 0 = entry) written by thread 0.  Compiled in only with
+// -DAMQB_TIMELINE (AMQB_TIMELINE=1 python -m amq_b200.build --force): the stamps cost issue slots on the
+// launch's critical path.
+#ifdef AMQB_TIMELINE
 #define AMQB_STAMP(i) do { if (L.dbg && tid == 0) L.dbg[blockIdx.x * 16 + (i)] = clock64(); } while (0)
+#define AMQB_DBG(...) __VA_ARGS__
+#else
+#define AMQB_STAMP(i) do { } while (0)
+#define AMQB_DBG(...)
+#endif
 
 constexpr int kCW = 16;                      // consumer warps
 constexpr int kCThreads = kCW * 32;
@@ -277,9 +285,10 @@ __device__ __forceinline__ void load_item(const DevProblem& P, int col, int grou
 template <int PRO>
 __device__ __forceinline__ void build_xprime(const DevProblem& P, int S, int g_lo, int len, uint8_t* xp,
                                              float2* xsd, float* sred, int cw, int lane, bool have_stats, float& rs1,
-                                             int mask, int variants, int var_stride, long long* dbgp = nullptr) {
+                                             int mask, int variants, int var_stride, const XLane (&xl)[3],
+                                             long long* dbgp = nullptr) {
   const int koff = 16 * (lane >> 2) + 2 * (lane & 3);     // this lane's first k inside a group (second pair at + 8)
-  if (dbgp) dbgp[3] = clock64();
+  AMQB_DBG(if (dbgp) dbgp[3] = clock64();)
   if (PRO == AMQB_PRO_RMSNORM && !have_stats) {
     float ss = 0.f;
     if (S == 1) {
@@ -308,12 +317,10 @@ __device__ __forceinline__ void build_xprime(const DevProblem& P, int S, int g_l
     for (int w = 0; w < kCW; ++w) tt += sred[w];
     rs1 = rsqrtf(tt / (float)P.K + P.eps);
   }
-  XLane xl[3];
   uint8_t* vbase[3];
   int gbytes[3];
 #pragma unroll
   for (int v = 0; v < 3; ++v) {
-    xl[v] = make_xlane(v + 2, lane, 3, 0);
     vbase[v] = xp + (size_t)(variants == 3 ? v : 0) * var_stride;
     gbytes[v] = xp_group_bytes(v + 2, 1);
   }
@@ -327,7 +334,7 @@ __device__ __forceinline__ void build_xprime(const DevProblem& P, int S, int g_l
     __half2 lo0, hi0, lo1, hi1;
     finish_item<PRO>(a0, b0, rs1, lo0, hi0);
     finish_item<PRO>(a1, b1, rs1, lo1, hi1);
-    if (dbgp && it == 0) dbgp[14] = clock64() + ((*reinterpret_cast<uint32_t*>(&lo0) ^ *reinterpret_cast<uint32_t*>(&lo1)) == 0x12345678u);
+    AMQB_DBG(if (dbgp && it == 0) dbgp[14] = clock64() + ((*reinterpret_cast<uint32_t*>(&lo0) ^ *reinterpret_cast<uint32_t*>(&lo1)) == 0x12345678u);)
     emit_item<kKindM1>(lo0, hi0, xl, mask, vbase, gbytes, gl0, 32, xsd + (size_t)gl0 * 8, 1, 1, 0, lane, true);
     emit_item<kKindM1>(lo1, hi1, xl, mask, vbase, gbytes, gl1, 32, xsd + (size_t)gl1 * 8, 1, 1, 0, lane, v1);
   }
@@ -564,17 +571,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
   const int M = M1 ? 1 : L.M;
 
   AMQB_STAMP(0);
-  if (tid == 0) {
-    for (int s = 0; s < NS; ++s) {
-      mbar_init(smem_u32(&bars[s]), 1);            // full: producer's expect_tx arrive
-      mbar_init(smem_u32(&bars[NS + s]), kCW);     // empty: one arrive per consumer warp
-    }
-    for (int p = 0; p < kMaxProblems; ++p) mbar_init(smem_u32(&bars[24 + p]), S > 1 ? S - 1 : 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&bars[28 + i]), kCW);   // red_full[buf]: every consumer warp deposited its partial sums
-      mbar_init(smem_u32(&bars[30 + i]), 1);     // red_free[buf]: the reducing warp is done with the buffer
-    }
-    mbar_init(smem_u32(&bars[32]), 1);           // x' chunk landed (M > 1 path)
+  if (tid < 40) {                     // one barrier per thread: [0,NS) full, [NS,2NS) empty, 24.. misc
+    int cnt = 0;
+    if (tid < NS) cnt = 1;                                   // full: producer's expect_tx arrive
+    else if (tid < 2 * NS) cnt = kCW;                        // empty: one arrive per consumer warp
+    else if (tid >= 24 && tid < 28) cnt = S > 1 ? S - 1 : 1; // cluster reduce, one per problem
+    else if (tid == 28 || tid == 29) cnt = kCW;              // red_full[buf]: every consumer warp deposited its partial sums
+    else if (tid == 30 || tid == 31) cnt = 1;                // red_free[buf]: the reducing warp is done with the buffer
+    else if (tid == 32) cnt = 1;                             // x' chunk landed (M > 1 path)
+    if (cnt) mbar_init(smem_u32(&bars[tid]), cnt);
     fence_mbar_init();
   }
   if (S > 1) cluster_sync_all();   // barriers initialised and peers' shared memory live before any DSMEM traffic
@@ -584,7 +589,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
   if (warp == kCW) {
     // ===== producer: weights do not depend on the previous kernel, so no griddepcontrol.wait here
     if (lane == 0) {
-      if (L.dbg_delay_ns < -1) { const long long t_end = gtime() - L.dbg_delay_ns; while (gtime() < t_end) {} }
+      AMQB_DBG(if (L.dbg_delay_ns < -1) { const long long t_end = gtime() - L.dbg_delay_ns; while (gtime() < t_end) {} })
       const uint64_t pol = policy_evict_first();
       int s = 0, ph = 0;
       bool wrapped = false;
@@ -699,10 +704,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
   }
 
   // ===== consumers
+  // everything that does not depend on x is computed BEFORE griddepcontrol.wait (it overlaps the previous kernel's
+  // drain): the per-lane constants of the x' builder for the three bit widths, pinned by an empty asm so the compiler
+  // cannot sink them below the wait
+  XLane xl[3];
+#pragma unroll
+  for (int v = 0; v < 3; ++v) {
+    xl[v] = make_xlane(v + 2, lane, 3, 0);
+    asm volatile("" :: "r"(xl[v].off0), "r"(xl[v].fexp0), "r"(xl[v].off1), "r"(xl[v].fexp1));
+  }
   pdl_wait();                        // x / residual come from the previous kernel
   AMQB_STAMP(1);
   float acc[2][MB][4];
-  int s = 0, ph = 0, nblk = 0, dbg_round = 0;
+  int s = 0, ph = 0, nblk = 0;
+  AMQB_DBG(int dbg_round = 0;)
   const __half* cur_x = nullptr;     // x' cache: problems of a group that share x (q/k/v, gate/up)
   int cur_K = 0, built_mask = 0, stat_par = 0, run_mask = 0;
   uint32_t xphase = 0;
@@ -723,7 +738,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
       const int c_hi = (c_lo + P.kc) < g_hi ? (c_lo + P.kc) : g_hi;
       // x' variants to (re)build now: chunked K or a single variant buffer -> this problem's own; else
       // whatever the host scheduled at this problem (all bit widths of the problems sharing this x)
-      if (P.xg) {
+      if (!M1 && P.xg) {
         // M > 1: x' of this chunk was built once for the whole grid; fetch it like the weights (TMA bulk copy)
         named_bar_sync(1, kCThreads);              // every warp is done with the previous chunk's x'
         const uint32_t xb = smem_u32(&bars[32]);
@@ -739,11 +754,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
         const int want = (chunked || L.xp_variants != 3) ? (1 << P.bits) : ((run_mask | (1 << P.bits)) & ~built_mask);
         if (want && M1)
           build_xprime<PRO>(P, S, c_lo, c_hi - c_lo, xp, xsd, sred + (stat_par ? kCW : 0), warp, lane,
-                            same_x && built_mask != 0, rs1, want, L.xp_variants, L.xprime_bytes,
-                            (L.dbg && tid == 0) ? L.dbg + blockIdx.x * 16 : nullptr);
+                            same_x && built_mask != 0, rs1, want, L.xp_variants, L.xprime_bytes, xl
+                            AMQB_DBG(, (L.dbg && tid == 0) ? L.dbg + blockIdx.x * 16 : nullptr));
         built_mask |= want | (1 << P.bits);
       }
-      if (L.dbg_delay_ns > 0) { const long long t_end = gtime() + L.dbg_delay_ns; while (gtime() < t_end) {} }
+      AMQB_DBG(if (L.dbg_delay_ns > 0) { const long long t_end = gtime() + L.dbg_delay_ns; while (gtime() < t_end) {} })
       AMQB_STAMP(5 + 4 * p);
       for (int rb = first_rb(cid, P.rot, ncl); rb < P.n_rb; rb += ncl, ++nblk) {
 #pragma unroll
@@ -767,7 +782,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bars[NS + s]));
           if (++s == NS) { s = 0; ph ^= 1; }
-          if (L.dbg && tid == 0 && dbg_round < 8) L.dbg[blockIdx.x * 16 + 8 + dbg_round++] = clock64();
+          AMQB_DBG(if (L.dbg && tid == 0 && dbg_round < 8) L.dbg[blockIdx.x * 16 + 8 + dbg_round++] = clock64();)
         }
         AMQB_STAMP(6 + 4 * p);
         // ---- (chunk of a) row block done.  Every warp deposits its partial sums in a double-buffered
