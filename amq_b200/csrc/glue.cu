@@ -52,49 +52,85 @@ __global__ void embed_kernel(const int64_t* __restrict__ ids, const __half* __re
 // grid (Hq, B), 16 warps.  Lane l of a warp owns head-dim elements [EPL*l, EPL*l+EPL); warp w owns
 // positions w, w+16, ...  (8 in flight per warp: one pass covers 128 cached positions).
 constexpr int kAttnWarps = 16;
+__device__ __forceinline__ float ld_dep(const __half* p) {
+  unsigned short v;
+  asm volatile("ld.global.u16 %0, [%1];" : "=h"(v) : "l"(p) : "memory");
+  return __half2float(__ushort_as_half(v));
+}
 template <int D>
 __global__ void __launch_bounds__(kAttnWarps * 32)
 attn_decode_kernel(const __half* __restrict__ qkv, __half* __restrict__ kc, __half* __restrict__ vc,
                    __half* __restrict__ out, const int* __restrict__ pos_dev, int Hq, int Hkv, int max_seq,
                    float theta, const float* __restrict__ rope_tab) {
   constexpr int EPL = D / 32;     // elements per lane
+  constexpr int UNR = 8;
   pdl_launch_dependents();
-  pdl_wait();
   const int h = blockIdx.x, b = blockIdx.y;
   const int rep = Hq / Hkv, hk = h / rep;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Everything below up to griddepcontrol.wait reads only data that no kernel of this decode step writes before this
+  // one (the position counter, the RoPE table, the cache rows of EARLIER positions), so it overlaps the q|k|v GEMV's
+  // drain: after the wait only q, k, v of this step are loaded.
   const int pos = pos_dev[0];
   const int ld = (Hq + 2 * Hkv) * D;
   const __half* qp = qkv + (size_t)b * ld + h * D;
   const __half* kp = qkv + (size_t)b * ld + (Hq + hk) * D;
   const __half* vp = qkv + (size_t)b * ld + (Hq + Hkv + hk) * D;
+  __half* kcb = kc + ((size_t)b * Hkv + hk) * max_seq * D;
+  __half* vcb = vc + ((size_t)b * Hkv + hk) * max_seq * D;
+  float cs[EPL], sn[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) {
+    const int ih = (EPL * lane + e) % (D / 2);
+    if (rope_tab) {                       // [max_seq][D/2] float2(cos, sin), built once by amqb_rope_table
+      const float2 t2 = reinterpret_cast<const float2*>(rope_tab)[(size_t)pos * (D / 2) + ih];
+      cs[e] = t2.x; sn[e] = t2.y;
+    } else {
+      const float inv = __powf(theta, -2.f * (float)ih / (float)D);
+      sincosf((float)pos * inv, &sn[e], &cs[e]);
+    }
+    // fp16-rounded cos / sin as HF (LlamaRotaryEmbedding casts to the activation dtype)
+    cs[e] = __half2float(__float2half_rn(cs[e]));
+    sn[e] = __half2float(__float2half_rn(sn[e]));
+  }
+  // first pass of cached rows (positions warp, warp + 16, ... < pos), raw fp16 bits: 8 rows in flight per warp
+  uint2 kraw[UNR][EPL == 4 ? 1 : EPL], vraw[UNR][EPL == 4 ? 1 : EPL];
+#pragma unroll
+  for (int u = 0; u < UNR; ++u) {
+    const int j = warp + kAttnWarps * u;
+    if (EPL == 4) {
+      kraw[u][0] = make_uint2(0u, 0u); vraw[u][0] = make_uint2(0u, 0u);
+      if (j < pos) {
+        kraw[u][0] = *reinterpret_cast<const uint2*>(kcb + (size_t)j * D + 4 * lane);
+        vraw[u][0] = *reinterpret_cast<const uint2*>(vcb + (size_t)j * D + 4 * lane);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        kraw[u][e].x = 0u; vraw[u][e].x = 0u;
+        if (j < pos) {
+          kraw[u][e].x = __half_as_ushort(kcb[(size_t)j * D + EPL * lane + e]);
+          vraw[u][e].x = __half_as_ushort(vcb[(size_t)j * D + EPL * lane + e]);
+        }
+      }
+    }
+  }
+  pdl_wait();
   // RoPE, HF rotate_half convention: pair (i, i + D/2), angle pos * theta^(-2i/D)
   float q[EPL], kn[EPL], vn[EPL];
 #pragma unroll
   for (int e = 0; e < EPL; ++e) {
     const int i = EPL * lane + e;
-    const int ih = i % (D / 2);
-    float sn, cs;
-    if (rope_tab) {                       // [max_seq][D/2] float2(cos, sin), built once by amqb_rope_table
-      const float2 t2 = reinterpret_cast<const float2*>(rope_tab)[(size_t)pos * (D / 2) + ih];
-      cs = t2.x; sn = t2.y;
-    } else {
-      const float inv = __powf(theta, -2.f * (float)ih / (float)D);
-      sincosf((float)pos * inv, &sn, &cs);
-    }
-    // fp16-rounded cos / sin as HF (LlamaRotaryEmbedding casts to the activation dtype)
-    cs = __half2float(__float2half_rn(cs));
-    sn = __half2float(__float2half_rn(sn));
     const int ip = i < D / 2 ? i + D / 2 : i - D / 2;
     const float sgn = i < D / 2 ? -1.f : 1.f;
-    q[e] = __half2float(qp[i]) * cs + sgn * __half2float(qp[ip]) * sn;
-    kn[e] = __half2float(kp[i]) * cs + sgn * __half2float(kp[ip]) * sn;
+    // ld_dep: these are the ONLY loads that depend on the previous kernel; volatile asm keeps them below the wait
+    // (qkv is const __restrict__, which would otherwise let the compiler hoist them above it)
+    q[e] = ld_dep(qp + i) * cs[e] + sgn * ld_dep(qp + ip) * sn[e];
+    kn[e] = ld_dep(kp + i) * cs[e] + sgn * ld_dep(kp + ip) * sn[e];
     q[e] = __half2float(__float2half_rn(q[e]));
     kn[e] = __half2float(__float2half_rn(kn[e]));
-    vn[e] = __half2float(vp[i]);
+    vn[e] = ld_dep(vp + i);
   }
-  __half* kcb = kc + ((size_t)b * Hkv + hk) * max_seq * D;
-  __half* vcb = vc + ((size_t)b * Hkv + hk) * max_seq * D;
   if (h % rep == 0 && warp == 0) {
 #pragma unroll
     for (int e = 0; e < EPL; ++e) {
@@ -108,7 +144,6 @@ attn_decode_kernel(const __half* __restrict__ qkv, __half* __restrict__ kc, __ha
   for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
   // positions j = warp, warp+16, ... ; eight at a time so the loads and the butterfly reductions of
   // independent positions overlap (the loop is latency-bound, not bandwidth-bound)
-  constexpr int UNR = 8;
   for (int j0 = warp; j0 <= pos; j0 += kAttnWarps * UNR) {
     float kj[UNR][EPL], vj[UNR][EPL], sc[UNR];
 #pragma unroll
@@ -116,8 +151,12 @@ attn_decode_kernel(const __half* __restrict__ qkv, __half* __restrict__ kc, __ha
       const int j = j0 + kAttnWarps * u;
       if (j < pos) {
         if (EPL == 4) {
-          const uint2 kk = *reinterpret_cast<const uint2*>(kcb + (size_t)j * D + 4 * lane);
-          const uint2 vv = *reinterpret_cast<const uint2*>(vcb + (size_t)j * D + 4 * lane);
+          uint2 kk, vv;
+          if (j0 == warp) { kk = kraw[u][0]; vv = vraw[u][0]; }       // prefetched before the wait
+          else {
+            kk = *reinterpret_cast<const uint2*>(kcb + (size_t)j * D + 4 * lane);
+            vv = *reinterpret_cast<const uint2*>(vcb + (size_t)j * D + 4 * lane);
+          }
           const float2 k0 = __half22float2(*reinterpret_cast<const __half2*>(&kk.x)), k1 = __half22float2(*reinterpret_cast<const __half2*>(&kk.y));
           const float2 v0 = __half22float2(*reinterpret_cast<const __half2*>(&vv.x)), v1 = __half22float2(*reinterpret_cast<const __half2*>(&vv.y));
           kj[u][0] = k0.x; kj[u][1] = k0.y; kj[u][EPL - 2] = k1.x; kj[u][EPL - 1] = k1.y;
@@ -125,8 +164,13 @@ attn_decode_kernel(const __half* __restrict__ qkv, __half* __restrict__ kc, __ha
         } else {
 #pragma unroll
           for (int e = 0; e < EPL; ++e) {
-            kj[u][e] = __half2float(kcb[(size_t)j * D + EPL * lane + e]);
-            vj[u][e] = __half2float(vcb[(size_t)j * D + EPL * lane + e]);
+            if (j0 == warp) {
+              kj[u][e] = __half2float(__ushort_as_half((unsigned short)kraw[u][e].x));
+              vj[u][e] = __half2float(__ushort_as_half((unsigned short)vraw[u][e].x));
+            } else {
+              kj[u][e] = __half2float(kcb[(size_t)j * D + EPL * lane + e]);
+              vj[u][e] = __half2float(vcb[(size_t)j * D + EPL * lane + e]);
+            }
           }
         }
       } else {
@@ -233,7 +277,7 @@ lm_head_kernel(const __half* __restrict__ W, const __half* __restrict__ x, const
     float acc[MAXM];
 #pragma unroll
     for (int m = 0; m < MAXM; ++m) acc[m] = 0.f;
-#pragma unroll 4
+#pragma unroll 16
     for (int i = lane; i < K / 8; i += 32) {
       uint4 wv;
       asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
