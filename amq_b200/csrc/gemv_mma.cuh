@@ -353,9 +353,12 @@ struct XgArgs {
   float2* xsg;           // [group][MB*8] (group sum, delta') (padded rows zero)
 };
 
+// grid (activation row, chunk of kXgWarps groups), one warp per group; every CTA recomputes the row's RMSNorm
+// statistic (K elements over 128 threads) rather than adding a second grid-wide dependency
+constexpr int kXgWarps = 4;
 template <int PRO>
-__global__ void __launch_bounds__(kCThreads) xprime_global_kernel(const XgArgs A) {
-  __shared__ float sred[kCW];
+__global__ void __launch_bounds__(kXgWarps * 32) xprime_global_kernel(const XgArgs A) {
+  __shared__ float sred[kXgWarps];
   pdl_launch_dependents();
   pdl_wait();
   const int col = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -365,7 +368,7 @@ __global__ void __launch_bounds__(kCThreads) xprime_global_kernel(const XgArgs A
   if (PRO == AMQB_PRO_RMSNORM) {
     float ss = 0.f;
     const uint2* xr = reinterpret_cast<const uint2*>(A.x + (size_t)col * A.ldx);
-    for (int i = threadIdx.x; i < A.K / 4; i += kCThreads) {
+    for (int i = threadIdx.x; i < A.K / 4; i += kXgWarps * 32) {
       const uint2 v = xr[i];
       const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
       const float2 b2 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
@@ -377,7 +380,7 @@ __global__ void __launch_bounds__(kCThreads) xprime_global_kernel(const XgArgs A
     __syncthreads();
     float tt = 0.f;
 #pragma unroll
-    for (int w = 0; w < kCW; ++w) tt += sred[w];
+    for (int w = 0; w < kXgWarps; ++w) tt += sred[w];
     rs = rsqrtf(tt / (float)A.K + A.eps);
   }
   const bool wide = M > 2;
@@ -387,7 +390,7 @@ __global__ void __launch_bounds__(kCThreads) xprime_global_kernel(const XgArgs A
 #pragma unroll
   for (int v = 0; v < 3; ++v) { xl[v] = make_xlane(v + 2, lane, C, col0); gbytes[v] = xp_group_bytes(v + 2, M); }
   uint8_t* const vbase[3] = {A.xg[0], A.xg[1], A.xg[2]};
-  for (int gl = warp; gl < n_g; gl += kCW) {
+  for (int gl = blockIdx.y * kXgWarps + warp; gl < n_g; gl += gridDim.y * kXgWarps) {
     const __half* xr = A.x + (size_t)col * A.ldx + gl * kGroup + koff;
     uint2 a, b = make_uint2(0u, 0u);
     a.x = *reinterpret_cast<const uint32_t*>(xr);
@@ -410,8 +413,8 @@ __global__ void __launch_bounds__(kCThreads) xprime_global_kernel(const XgArgs A
 template <int PRO>
 static int launch_xprime_global(const XgArgs& A, int pdl, cudaStream_t st) {
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(A.M);
-  cfg.blockDim = dim3(kCThreads);
+  cfg.gridDim = dim3(A.M, (A.K / kGroup + kXgWarps - 1) / kXgWarps);
+  cfg.blockDim = dim3(kXgWarps * 32);
   cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -782,7 +785,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bars[NS + s]));
           if (++s == NS) { s = 0; ph ^= 1; }
-          AMQB_DBG(if (L.dbg && tid == 0 && dbg_round < 8) L.dbg[blockIdx.x * 16 + 8 + dbg_round++] = clock64();)
+          AMQB_DBG(if (L.dbg && L.count == 1 && tid == 0 && dbg_round < 8) L.dbg[blockIdx.x * 16 + 8 + dbg_round++] = clock64();)
         }
         AMQB_STAMP(6 + 4 * p);
         // ---- (chunk of a) row block done.  Every warp deposits its partial sums in a double-buffered

@@ -29,11 +29,12 @@ for g in gs[6:]:
     ops.gemv_grouped(g, ws, pdl=True)
 L.amqb_debug_set_timeline(None)
 torch.cuda.synchronize()
-d = bufs[-1].cpu().view(148, 16).double(); d = d[d[:, 0] > 0]; t0 = d[:, 0].min()
+d = bufs[-1].cpu().view(148, 16).double(); d = d[d[:, 0] > 0]
+d = torch.where(d > 0, (d - d[:, 0:1]) / 1.965e3 + 1e-6, torch.zeros_like(d))      # us since the CTA's own entry (SM clock, 1965 MHz)
 names = {0: "entry", 1: "pdl_wait done", 2: "exit"}
 for p in range(len(bits)):
     names.update({4 + 4 * p: f"p{p} start", 5 + 4 * p: f"p{p} x' built", 6 + 4 * p: f"p{p} records done", 7 + 4 * p: f"p{p} deposited"})
 for k in sorted(names, key=lambda k: (k if k != 2 else 99)):
-    c = (d[:, k] - t0) / 1e3
-    c = c[d[:, k] > 0]
+    c = d[:, k]
+    c = c[c > 0]
     if len(c): print(f"  {names[k]:20s} min {c.min():6.2f} med {c.median():6.2f} max {c.max():6.2f}  (n={len(c)})")
