@@ -264,13 +264,15 @@ __device__ __forceinline__ void emit_item(__half2 lo, __half2 hi, const XLane (&
 
 template <int PRO>
 __device__ __forceinline__ void load_item(const DevProblem& P, int col, int group, int koff, uint2& a, uint2& b) {
+  // activations are read through L2 (ld.global.cg): inside the persistent decode kernel another CTA wrote them
+  // earlier in the same launch, and the SM's L1 may still hold the previous contents of the buffer
   const __half* xr = P.x + (size_t)col * P.ldx + group * kGroup + koff;
-  a.x = *reinterpret_cast<const uint32_t*>(xr);
-  a.y = *reinterpret_cast<const uint32_t*>(xr + 8);
+  a.x = __ldcg(reinterpret_cast<const uint32_t*>(xr));
+  a.y = __ldcg(reinterpret_cast<const uint32_t*>(xr + 8));
   b = make_uint2(0u, 0u);
   if (PRO == AMQB_PRO_SILU_MUL) {
-    b.x = *reinterpret_cast<const uint32_t*>(xr + P.K);
-    b.y = *reinterpret_cast<const uint32_t*>(xr + P.K + 8);
+    b.x = __ldcg(reinterpret_cast<const uint32_t*>(xr + P.K));
+    b.y = __ldcg(reinterpret_cast<const uint32_t*>(xr + P.K + 8));
   } else if (PRO == AMQB_PRO_RMSNORM) {
     const __half* gr = P.gamma + group * kGroup + koff;
     b.x = *reinterpret_cast<const uint32_t*>(gr);
@@ -294,7 +296,7 @@ __device__ __forceinline__ void build_xprime(const DevProblem& P, int S, int g_l
     if (S == 1) {
       // every warp sums the squares of the groups it owns; together the warps cover the whole row
       for (int gl = cw; gl < len; gl += kCW) {
-        const uint2 v = *reinterpret_cast<const uint2*>(P.x + (g_lo + gl) * kGroup + 4 * lane);
+        const uint2 v = __ldcg(reinterpret_cast<const uint2*>(P.x + (g_lo + gl) * kGroup + 4 * lane));
         const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
         const float2 b2 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
         ss += a.x * a.x + a.y * a.y + b2.x * b2.x + b2.y * b2.y;
@@ -302,7 +304,7 @@ __device__ __forceinline__ void build_xprime(const DevProblem& P, int S, int g_l
     } else {   // K split across the cluster: the statistic still spans the FULL row
       const uint2* xr = reinterpret_cast<const uint2*>(P.x);
       for (int i = cw * 32 + lane; i < P.K / 4; i += kCThreads) {
-        const uint2 v = xr[i];
+        const uint2 v = __ldcg(xr + i);
         const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
         const float2 b2 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
         ss += a.x * a.x + a.y * a.y + b2.x * b2.x + b2.y * b2.y;
@@ -546,7 +548,7 @@ __device__ __forceinline__ int first_rb(int cid, int rot, int ncl) {
 
 __device__ __forceinline__ void store_out(const DevProblem& P, int n, int col, float v) {
   if (P.bias) v += __half2float(P.bias[n]);
-  if (P.residual) v += __half2float(P.residual[(size_t)col * P.ldy + n]);
+  if (P.residual) v += __half2float(__ushort_as_half(__ldcg(reinterpret_cast<const unsigned short*>(P.residual) + (size_t)col * P.ldy + n)));
   P.y[(size_t)col * P.ldy + n] = __float2half_rn(v);
 }
 

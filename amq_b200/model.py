@@ -15,13 +15,14 @@ captured once in a CUDA graph with programmatic dependent launch between the ker
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, List, Optional
 
 import numpy as np
 import torch
 
 from . import ops
-from ._lib import PRO_NONE, PRO_RMSNORM, PRO_SILU_MUL, check, cur_stream, lib, ptr
+from ._lib import PRO_NONE, PRO_RMSNORM, PRO_SILU_MUL, MegaShape, check, cur_stream, lib, ptr
 from .arch import LINEARS, ModelShape
 
 GROUP = 128
@@ -49,7 +50,7 @@ class QuantDecoder:
 
     def __init__(self, shape: ModelShape, arch: Dict[str, List[int]], batch: int = 1, max_seq: int = 256,
                  device: str = "cuda:0", seed: int = 0, n_block: Optional[int] = None, pdl: bool = True,
-                 tp_rank: int = 0, tp_world: int = 1):
+                 tp_rank: int = 0, tp_world: int = 1, persistent: Optional[bool] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("amq_b200.QuantDecoder needs a CUDA device (no CPU path)")
         self.shape = shape
@@ -109,6 +110,13 @@ class QuantDecoder:
         self.allreduce = None          # set by amq_b200.tp for tensor-parallel runs
         self.launches_per_step = 0
         self._build_problems()
+        # batch 1 on one GPU: all decoder layers run as ONE persistent launch (csrc/decode_mega.cu); anything else
+        # (batches, tensor-parallel shards, shapes its shared-memory plan does not take) uses the per-linear launches
+        if persistent is None:
+            persistent = os.environ.get("AMQB_PERSISTENT", "1") != "0"
+        self.persistent = bool(persistent) and batch == 1 and tp_world == 1 and self._persistent_supported()
+        if self.persistent:
+            self._build_layer_table()
 
     # ---------------------------------------------------------------- static launch descriptors
     def _build_problems(self) -> None:
@@ -164,6 +172,40 @@ class QuantDecoder:
             self._plan.append({"qkv": (ops.GemvProblem * 3)(*qkv), "o": (ops.GemvProblem * 1)(*o),
                                "gu": (ops.GemvProblem * 2)(*gu), "down": (ops.GemvProblem * 1)(*down), "L": L})
 
+    # ---------------------------------------------------------------- persistent decode kernel (batch 1)
+    def _persistent_supported(self) -> bool:
+        S = self.shape
+        x_single = (max(S.inter, S.hidden) // GROUP) * 480
+        x_multi = 3 * (((S.hidden // GROUP) * 480 + 127) // 128 * 128)
+        fixed = 384 + self.n_block * 208 + 2 * (max(S.inter, S.hidden) // GROUP) * 8 * 4 + max(x_single, x_multi) + 4096 + 512
+        return (S.head_dim in (64, 128) and S.hidden % GROUP == 0 and S.inter % GROUP == 0 and self.q_dim % GROUP == 0
+                and self.q_dim % 32 == 0 and self.kv_dim % 32 == 0 and fixed + 2 * 16 * 2176 <= 227 * 1024 and self.Hq <= 132)
+
+    def _build_layer_table(self) -> None:
+        """amqb_mega_layer[n_block] in device memory: per-layer weight pointers / bit widths (the searched arch),
+        norm weights and KV cache pointers."""
+        lin = np.dtype([("w", "<u8"), ("bias", "<u8"), ("bits", "<i4"), ("pad", "<i4")])
+        rec = np.dtype([("lin", lin, (7,)), ("norm1", "<u8"), ("norm2", "<u8"), ("kc", "<u8"), ("vc", "<u8"), ("pad", "<i8")])
+        assert rec.itemsize == 208
+        tab = np.zeros(self.n_block, dtype=rec)
+        for li, L in enumerate(self.layers):
+            bias = L.get("qkv_bias")
+            boff = [0, self.q_dim, self.q_dim + self.kv_dim]
+            for j, name in enumerate(LINEARS):
+                bits, w, N, K = L[name]
+                tab[li]["lin"][j]["w"] = w.data_ptr()
+                tab[li]["lin"][j]["bits"] = bits
+                tab[li]["lin"][j]["bias"] = (bias.data_ptr() + 2 * boff[j]) if (bias is not None and j < 3) else 0
+            tab[li]["norm1"], tab[li]["norm2"] = L["norm1"].data_ptr(), L["norm2"].data_ptr()
+            tab[li]["kc"], tab[li]["vc"] = L["k_cache"].data_ptr(), L["v_cache"].data_ptr()
+        self._layer_table = torch.from_numpy(tab.view(np.uint8).copy()).to(self.dev)
+        nbar = int(lib().amqb_decode_layers_barrier_bytes(self.n_block))
+        self._mega_bar = torch.zeros(nbar, dtype=torch.uint8, device=self.dev)
+        self.mega_err = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        S = self.shape
+        self._mega_shape = MegaShape(S.hidden, S.inter, self.Hq, self.Hkv, self.D, self.max_seq, self.n_block,
+                                     float(S.rms_eps), float(S.rope_theta))
+
     # ---------------------------------------------------------------- one decode step (all launches)
     def _gemv(self, arr, n) -> None:
         check(lib().amqb_gemv_grouped(arr, n, ptr(self.ws), ctypes.c_size_t(self.ws.numel()), int(self.pdl), cur_stream()),
@@ -177,7 +219,12 @@ class QuantDecoder:
         self.launches_per_step = 0
         check(Lb.amqb_embed(ptr(self.tokens), ptr(self.embed), ptr(self.h), self.B, self.H, st), "embed")
         self.launches_per_step += 1
-        for P in self._plan:
+        if self.persistent:
+            check(Lb.amqb_decode_layers(ctypes.byref(self._mega_shape), ptr(self._layer_table), ptr(self.h), ptr(self.qkv),
+                                        ptr(self.attn), ptr(self.gu), ptr(self.pos), ptr(self.rope), ptr(self._mega_bar),
+                                        ptr(self.mega_err), int(self.pdl), st), "decode_layers")
+            self.launches_per_step += 1
+        for P in (() if self.persistent else self._plan):
             L = P["L"]
             self._gemv(P["qkv"], 3)
             check(Lb.amqb_attn_decode(ptr(self.qkv), ptr(L["k_cache"]), ptr(L["v_cache"]), ptr(self.attn), ptr(self.pos),

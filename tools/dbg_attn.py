@@ -19,4 +19,4 @@ for mode in ("eager", "graph_nopdl", "graph"):
         else: m.step()
         torch.cuda.synchronize()
         rel = (m.logits - ref).abs().max() / ref.abs().max()
-        print(mode, pos, float(rel), flush=True)
+        print(mode, pos, float(rel), "persistent", m.persistent, "err", int(m.mega_err.item()) if m.persistent else None, flush=True)
