@@ -56,6 +56,7 @@ struct MegaArgs {
   int n_layers, Hq, Hkv, D, max_seq, hidden, inter, qkv_ld;
   MegaSlot slot[kMegaLin];
   int n_stages, stage_bytes, xprime_bytes, xs_floats, copy_recs, lv_bytes, xp_region;
+  long long* dbg;                 // AMQB_TIMELINE builds: [CTA][5 phases][8] clock stamps of layer 1
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
@@ -64,20 +65,31 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   return v;
 }
 
-// every consumer warp waits on its own (lane 0 polls); a time-out (~2 s) raises *err instead of hanging the GPU
-__device__ __forceinline__ void grid_wait(const unsigned int* ctr, unsigned int target, int* err, volatile int* s_err, int lane) {
-  if (lane == 0 && !*s_err) {
-    const long long t0 = clock64();
-    while (ld_acquire_gpu(ctr) < target) {
-      __nanosleep(20);
-      if (clock64() - t0 > 4000000000LL) { *s_err = 1; *err = 1; break; }
+__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// ONE thread per CTA polls (relaxed loads: 148 pollers on the counter's L2 line, not 2368), fences once, then releases
+// the other consumer warps through a named barrier.  A time-out (~2 s) raises *err instead of hanging the GPU.
+__device__ __forceinline__ void grid_wait(const unsigned int* ctr, unsigned int target, int* err, volatile int* s_err,
+                                          int warp, int lane) {
+  if (warp == 0) {
+    if (lane == 0 && !*s_err) {
+      const long long t0 = clock64();
+      while (ld_relaxed_gpu(ctr) < target) {
+        if (clock64() - t0 > 4000000000LL) { *s_err = 1; *err = 1; break; }
+      }
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
+    __syncwarp();
   }
-  __syncwarp();
+  named_bar_sync(2, kCThreads);
 }
 __device__ __forceinline__ void grid_arrive(unsigned int* ctr, int lane) {
   __syncwarp();                               // the warp's stores of this phase are ordered before lane 0's fence
-  if (lane == 0) { __threadfence(); atomicAdd(ctr, 1u); }
+  if (lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(ctr), "r"(1u) : "memory");
 }
 
 __device__ __forceinline__ void phase_slots(int t, int& s0, int& cnt) {
@@ -105,7 +117,7 @@ __device__ __forceinline__ float ld_cg_half(const __half* p) {
 template <int D>
 __device__ __forceinline__ void mega_attention(const MegaArgs& A, const MegaLayerVar& lv, int pos, float* scratch,
                                                const unsigned int* wait_ctr, volatile int* s_err, int warp, int lane) {
-  constexpr int EPL = D / 32, UNR = 8;
+  constexpr int EPL = D / 32, UNR = 4;      // 4 cached rows in flight per warp: the kernel's 96-register budget
   const int h = blockIdx.x, Hq = A.Hq, Hkv = A.Hkv;
   const int rep = Hq / Hkv, hk = h / rep;
   const __half* qp = A.qkv + h * D;
@@ -137,7 +149,7 @@ __device__ __forceinline__ void mega_attention(const MegaArgs& A, const MegaLaye
       }
     }
   }
-  grid_wait(wait_ctr, gridDim.x, A.err, s_err, lane);          // q|k|v of this step complete
+  grid_wait(wait_ctr, gridDim.x, A.err, s_err, warp, lane);          // q|k|v of this step complete
   float q[EPL], kn[EPL], vn[EPL];
 #pragma unroll
   for (int e = 0; e < EPL; ++e) {
@@ -333,6 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
           }
         }
         grid_arrive(A.bar + phase, lane);
+        AMQB_DBG(if (A.dbg && layer == 1 && lane == 0) A.dbg[((size_t)cid * kPhPerLayer + t) * 8 + 5] = clock64();)
       }
     }
     return;
@@ -355,15 +368,19 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
   for (int layer = 0; layer < A.n_layers; ++layer) {
     const MegaLayerVar& lv = lvs[layer];
     for (int t = 0; t < kPhPerLayer; ++t, ++phase) {
+      AMQB_DBG(const bool dbg_on = A.dbg && layer == 1 && tid == 0; long long* dbg = A.dbg + ((size_t)cid * kPhPerLayer + t) * 8;)
+      AMQB_DBG(if (dbg_on) dbg[0] = clock64();)
       if (t == kPhAttn) {
         if (cid < A.Hq) {
           if (A.D == 128) mega_attention<128>(A, lv, pos, reinterpret_cast<float*>(xp), A.bar + phase - 1, s_err, warp, lane);
           else mega_attention<64>(A, lv, pos, reinterpret_cast<float*>(xp), A.bar + phase - 1, s_err, warp, lane);
         }
         if (warp == 0) grid_arrive(A.bar + phase, lane);
+        AMQB_DBG(if (dbg_on) dbg[4] = clock64();)
         continue;
       }
-      if (phase > 0) grid_wait(A.bar + phase - 1, ncl, A.err, s_err, lane);
+      if (phase > 0) grid_wait(A.bar + phase - 1, ncl, A.err, s_err, warp, lane);
+      AMQB_DBG(if (dbg_on) dbg[1] = clock64();)
       int s0, cnt;
       phase_slots(t, s0, cnt);
       const int variants = cnt > 1 ? 3 : 1;
@@ -381,6 +398,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
           else
             build_xprime<AMQB_PRO_RMSNORM>(P, 1, 0, P.n_g, xp, xsd, sred, warp, lane, built_mask != 0, rs1, want, variants, A.xprime_bytes, xl);
           built_mask |= want;
+          AMQB_DBG(if (dbg_on) dbg[2] = clock64();)
         }
         const uint32_t rbytes = rec_bytes(P.bits);
         const int gbytes = xp_group_bytes(P.bits, 1);
@@ -421,6 +439,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bars[28 + buf]));
+          AMQB_DBG(if (dbg_on) dbg[4] = clock64();)
         }
       }
     }
@@ -428,6 +447,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
 }
 
 static int g_mega_sms = 0;
+extern long long* g_dbg;
 
 }  // namespace amqb
 
@@ -457,6 +477,7 @@ int amqb_decode_layers(const amqb_mega_shape* shp, const amqb_mega_layer* layers
   MegaArgs A{};
   A.layers = reinterpret_cast<const MegaLayerVar*>(layers_dev);
   A.h = (__half*)h; A.qkv = (__half*)qkv; A.attn = (__half*)attn; A.gu = (__half*)gu;
+  A.dbg = g_dbg;
   A.pos = pos_dev; A.rope = rope_cos_sin; A.bar = (unsigned int*)barrier_dev; A.err = err_dev;
   A.eps = shp->eps; A.rope_theta = shp->rope_theta;
   A.n_layers = nl; A.Hq = Hq; A.Hkv = Hkv; A.D = D; A.max_seq = shp->max_seq; A.hidden = H; A.inter = I;

@@ -7,7 +7,7 @@
 namespace amqb {
 
 static int g_sm_count = 0;
-static long long* g_dbg = nullptr;
+long long* g_dbg = nullptr;       // debug timeline buffer (amqb_debug_set_timeline), shared with decode_mega.cu
 
 static int sm_count() {
   if (g_sm_count == 0) {

@@ -110,10 +110,11 @@ class QuantDecoder:
         self.allreduce = None          # set by amq_b200.tp for tensor-parallel runs
         self.launches_per_step = 0
         self._build_problems()
-        # batch 1 on one GPU: all decoder layers run as ONE persistent launch (csrc/decode_mega.cu); anything else
-        # (batches, tensor-parallel shards, shapes its shared-memory plan does not take) uses the per-linear launches
+        # batch 1 on one GPU can run all decoder layers as ONE persistent launch (csrc/decode_mega.cu).  Opt-in
+        # (persistent=True or AMQB_PERSISTENT=1): as measured in round 1 its grid-wide phase barriers cost more than the
+        # programmatic-dependent-launch boundaries of the per-linear chain, so the chain stays default
         if persistent is None:
-            persistent = os.environ.get("AMQB_PERSISTENT", "1") != "0"
+            persistent = os.environ.get("AMQB_PERSISTENT", "0") == "1"
         self.persistent = bool(persistent) and batch == 1 and tp_world == 1 and self._persistent_supported()
         if self.persistent:
             self._build_layer_table()

@@ -7,7 +7,7 @@ shape = ModelShape("tiny-llama", 256, 512, 4, 4, 2, 512, head_dim=64)
 rs = np.random.RandomState(0)
 arch = {n: rs.choice([2, 3, 4], size=2).tolist() for n in LINEARS}
 for mode in ("eager", "graph_nopdl", "graph"):
-    m = QuantDecoder(shape, arch, batch=1, max_seq=32, seed=1, pdl=(mode == "graph"))
+    m = QuantDecoder(shape, arch, batch=1, max_seq=32, seed=1, pdl=(mode == "graph"), persistent=os.environ.get("AMQB_PERSISTENT") == "1")
     kc = [torch.zeros(1, m.Hkv, 32, m.D, device=m.dev) for _ in m.layers]
     vc = [torch.zeros(1, m.Hkv, 32, m.D, device=m.dev) for _ in m.layers]
     tok = torch.randint(0, shape.vocab, (1,), device=m.dev)
