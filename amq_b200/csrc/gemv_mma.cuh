@@ -131,6 +131,14 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
       "DONEC_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
 
+// first MMA of a group: D = A*B + magic (the accumulators start at the bit pattern of 1.5 * 2^23 without being
+// initialised register by register: the C operand is a loop-invariant register)
+__device__ __forceinline__ void imma_16832_first(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, int magic) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+      : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(magic));
+}
 __device__ __forceinline__ void imma_16832(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -470,16 +478,13 @@ __device__ __forceinline__ void process_record(const uint8_t* rec, const uint8_t
     const float4 xd = *reinterpret_cast<const float4*>(xsd + 2 * t);     // (xsum, delta) of columns 2t, 2t+1
     int c[2][4];
 #pragma unroll
-    for (int tile = 0; tile < 2; ++tile)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) c[tile][i] = (int)kMagicI;
-#pragma unroll
     for (int m = 0; m < NM; ++m)
 #pragma unroll
       for (int tile = 0; tile < 2; ++tile) {
         uint32_t a[4];
         afrag(tile, m, a);
-        imma_16832(c[tile], a, bf[m][0], bf[m][1]);
+        if (m == 0) imma_16832_first(c[tile], a, bf[m][0], bf[m][1], (int)kMagicI);
+        else imma_16832(c[tile], a, bf[m][0], bf[m][1]);
       }
 #pragma unroll
     for (int tile = 0; tile < 2; ++tile) {
@@ -501,27 +506,32 @@ __device__ __forceinline__ void process_record(const uint8_t* rec, const uint8_t
       if (mm > M - 1) mm = M - 1;
       bofs[hb] = (mm * 4 + t) * 8;
     }
+    // MMA-outer, tile-inner: one B fragment load feeds both tiles, six independent accumulator chains per block
+    int c[2][3][MB][4];
 #pragma unroll
-    for (int tile = 0; tile < 2; ++tile) {
-      int c[3][MB][4];
+    for (int tile = 0; tile < 2; ++tile)
 #pragma unroll
       for (int d = 0; d < 3; ++d)
 #pragma unroll
         for (int hb = 0; hb < MB; ++hb)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) c[d][hb][i] = (int)kMagicI;
+          for (int i = 0; i < 4; ++i) c[tile][d][hb][i] = (int)kMagicI;
 #pragma unroll
-      for (int m = 0; m < NM; ++m) {
-        uint32_t a[4];
-        afrag(tile, m, a);
+    for (int m = 0; m < NM; ++m) {
+      uint32_t a0[4], a1[4];
+      afrag(0, m, a0);
+      afrag(1, m, a1);
 #pragma unroll
-        for (int d = 0; d < 3; ++d)
+      for (int d = 0; d < 3; ++d)
 #pragma unroll
-          for (int hb = 0; hb < MB; ++hb) {
-            const uint2 b = *reinterpret_cast<const uint2*>(xpg + (size_t)(m * C + d * M) * 32 + bofs[hb]);
-            imma_16832(c[d][hb], a, b.x, b.y);
-          }
-      }
+        for (int hb = 0; hb < MB; ++hb) {
+          const uint2 b = *reinterpret_cast<const uint2*>(xpg + (size_t)(m * C + d * M) * 32 + bofs[hb]);
+          imma_16832(c[0][d][hb], a0, b.x, b.y);
+          imma_16832(c[1][d][hb], a1, b.x, b.y);
+        }
+    }
+#pragma unroll
+    for (int tile = 0; tile < 2; ++tile) {
       const float2 m0 = __half22float2(meta[tile * 16 + g]);
       const float2 m1 = __half22float2(meta[tile * 16 + g + 8]);
 #pragma unroll
@@ -531,8 +541,8 @@ __device__ __forceinline__ void process_record(const uint8_t* rec, const uint8_t
         for (int i = 0; i < 4; ++i) {
           const float dk = (i & 1) ? xd.w : xd.y, xs = (i & 1) ? xd.z : xd.x;
           const float2 sc = i < 2 ? m0 : m1;
-          const float fh = __int_as_float(c[0][hb][i]) - kMagicF, fm = __int_as_float(c[1][hb][i]) - kMagicF,
-                      fl = __int_as_float(c[2][hb][i]) - kMagicF;
+          const float fh = __int_as_float(c[tile][0][hb][i]) - kMagicF, fm = __int_as_float(c[tile][1][hb][i]) - kMagicF,
+                      fl = __int_as_float(c[tile][2][hb][i]) - kMagicF;
           const float v = fmaf(fh, 65536.f * dk, fmaf(fm, 256.f * dk, fl * dk));
           acc[tile][hb][i] = fmaf(-sc.y, xs, fmaf(sc.x, v, acc[tile][hb][i]));
         }

@@ -3,9 +3,13 @@ usage: python tools/ncu_regions.py rep.ncu-rep file.cuh name:lo-hi [name:lo-hi .
 import csv, subprocess, sys, collections
 rep, fname = sys.argv[1], sys.argv[2]
 regions = []
-for a in sys.argv[3:]:
+extra = []
+args = sys.argv[3:]
+if args and args[0].startswith("--skip="):
+    extra = ["--launch-skip", args[0].split("=")[1], "--launch-count", "1"]; args = args[1:]
+for a in args:
     n, r = a.split(":"); lo, hi = r.split("-"); regions.append((n, int(lo), int(hi)))
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] + extra, capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
 hi_ = [i for i, r in enumerate(rows) if r and r[0] == "Line No" and len(r) > 5]
 hdr = rows[hi_[0]]
