@@ -267,7 +267,7 @@ def run_ours(args, shape, arch):
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "algorithmic_bytes_per_launch": g_bytes / g_launch, "peak_source": peak_src,
-                         "kernel": "gemv_mma_kernel<bits,..> (decode GEMV family, %d launches per step)" % g_launch,
+                         "kernel": "gemv_mma_kernel<MB,kind,prologue> (IMMA decode GEMV family, %d launches per step)" % g_launch,
                          "algorithmic_bytes_per_step": g_bytes, "avg_launch_us": g_ms * 1e3 / g_launch,
                          "step_frac_of_weight_roofline": (bytes_tok["total"] / (peak * 1e9)) / (ms_dev / args.steps * 1e-3)},
             "cpu_baseline": {"value": cpu_tok_s, "unit": "tok/s", "cores": os.cpu_count(), "kind": "port", "sample": cpu_desc},
