@@ -21,6 +21,11 @@
 
 namespace amqb {
 
+#ifdef AMQB_TIMELINE
+#define AMQB_DBG_PTR (dbg_on ? dbg : nullptr)
+#else
+#define AMQB_DBG_PTR nullptr
+#endif
 constexpr int kMegaLin = 7;     // q, k, v, o, gate, up, down
 constexpr int kSmemHeader = 384; // mbarriers + error flag
 enum { kPhQkv = 0, kPhAttn = 1, kPhO = 2, kPhGu = 3, kPhDown = 4, kPhPerLayer = 5 };
@@ -116,7 +121,7 @@ __device__ __forceinline__ float ld_cg_half(const __half* p) {
 // ---- attention phase: head h = blockIdx.x, the 16 consumer warps (same math as attn_decode_kernel, glue.cu) ----------
 template <int D>
 __device__ __forceinline__ void mega_attention(const MegaArgs& A, const MegaLayerVar& lv, int pos, float* scratch,
-                                               const unsigned int* wait_ctr, volatile int* s_err, int warp, int lane) {
+                                               const unsigned int* wait_ctr, volatile int* s_err, int warp, int lane, long long* dbg) {
   constexpr int EPL = D / 32, UNR = 4;      // 4 cached rows in flight per warp: the kernel's 96-register budget
   const int h = blockIdx.x, Hq = A.Hq, Hkv = A.Hkv;
   const int rep = Hq / Hkv, hk = h / rep;
@@ -150,6 +155,7 @@ __device__ __forceinline__ void mega_attention(const MegaArgs& A, const MegaLaye
     }
   }
   grid_wait(wait_ctr, gridDim.x, A.err, s_err, warp, lane);          // q|k|v of this step complete
+  AMQB_DBG(if (dbg) dbg[1] = clock64();)
   float q[EPL], kn[EPL], vn[EPL];
 #pragma unroll
   for (int e = 0; e < EPL; ++e) {
@@ -169,6 +175,7 @@ __device__ __forceinline__ void mega_attention(const MegaArgs& A, const MegaLaye
       vcb[(size_t)pos * D + EPL * lane + e] = __float2half_rn(vn[e]);
     }
   }
+  AMQB_DBG(if (dbg) dbg[2] = clock64() + (q[0] == 1234.5f);)
   const float scale = rsqrtf((float)D);
   float mx = -INFINITY, den = 0.f, acc[EPL];
 #pragma unroll
@@ -223,6 +230,7 @@ __device__ __forceinline__ void mega_attention(const MegaArgs& A, const MegaLaye
       }
     }
   }
+  AMQB_DBG(if (dbg) dbg[3] = clock64() + (den == 1234.5f);)
   float* s_m = scratch;                      // [kCW]
   float* s_d = scratch + kCW;                // [kCW]
   float* s_acc = scratch + 2 * kCW;          // [kCW][D]
@@ -230,6 +238,7 @@ __device__ __forceinline__ void mega_attention(const MegaArgs& A, const MegaLaye
 #pragma unroll
   for (int e = 0; e < EPL; ++e) s_acc[warp * D + EPL * lane + e] = acc[e];
   named_bar_sync(1, kCThreads);
+  AMQB_DBG(if (dbg) dbg[6] = clock64();)
   if (warp == 0) {
     float gm = -INFINITY;
 #pragma unroll
@@ -372,8 +381,8 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
       AMQB_DBG(if (dbg_on) dbg[0] = clock64();)
       if (t == kPhAttn) {
         if (cid < A.Hq) {
-          if (A.D == 128) mega_attention<128>(A, lv, pos, reinterpret_cast<float*>(xp), A.bar + phase - 1, s_err, warp, lane);
-          else mega_attention<64>(A, lv, pos, reinterpret_cast<float*>(xp), A.bar + phase - 1, s_err, warp, lane);
+          if (A.D == 128) mega_attention<128>(A, lv, pos, reinterpret_cast<float*>(xp), A.bar + phase - 1, s_err, warp, lane, AMQB_DBG_PTR);
+          else mega_attention<64>(A, lv, pos, reinterpret_cast<float*>(xp), A.bar + phase - 1, s_err, warp, lane, AMQB_DBG_PTR);
         }
         if (warp == 0) grid_arrive(A.bar + phase, lane);
         AMQB_DBG(if (dbg_on) dbg[4] = clock64();)

@@ -299,9 +299,27 @@ __device__ __forceinline__ void build_xprime(const DevProblem& P, int S, int g_l
                                              long long* dbgp = nullptr) {
   const int koff = 16 * (lane >> 2) + 2 * (lane & 3);     // this lane's first k inside a group (second pair at + 8)
   AMQB_DBG(if (dbgp) dbgp[3] = clock64();)
+  const int items = len > cw ? (len - cw + kCW - 1) / kCW : 0;      // gl = cw, cw + kCW, ...
+  uint2 a0, b0, a1, b1;
+  bool preloaded = false;
   if (PRO == AMQB_PRO_RMSNORM && !have_stats) {
     float ss = 0.f;
-    if (S == 1) {
+    if (S == 1 && items <= 2) {
+      // one pass (K <= 4096): the warp's items are loaded once; the squares are summed from the registers that are
+      // normalised afterwards, so the statistic costs no second trip to L2
+      if (items > 0) {
+        const bool v1 = items > 1;
+        load_item<PRO>(P, 0, g_lo + cw, koff, a0, b0);
+        load_item<PRO>(P, 0, g_lo + (v1 ? cw + kCW : cw), koff, a1, b1);
+        const float2 p0 = __half22float2(*reinterpret_cast<const __half2*>(&a0.x)), p1 = __half22float2(*reinterpret_cast<const __half2*>(&a0.y));
+        ss = p0.x * p0.x + p0.y * p0.y + p1.x * p1.x + p1.y * p1.y;
+        if (v1) {
+          const float2 r0 = __half22float2(*reinterpret_cast<const __half2*>(&a1.x)), r1 = __half22float2(*reinterpret_cast<const __half2*>(&a1.y));
+          ss += r0.x * r0.x + r0.y * r0.y + r1.x * r1.x + r1.y * r1.y;
+        }
+        preloaded = true;
+      }
+    } else if (S == 1) {
       // every warp sums the squares of the groups it owns; together the warps cover the whole row
       for (int gl = cw; gl < len; gl += kCW) {
         const uint2 v = __ldcg(reinterpret_cast<const uint2*>(P.x + (g_lo + gl) * kGroup + 4 * lane));
@@ -334,13 +352,13 @@ __device__ __forceinline__ void build_xprime(const DevProblem& P, int S, int g_l
     vbase[v] = xp + (size_t)(variants == 3 ? v : 0) * var_stride;
     gbytes[v] = xp_group_bytes(v + 2, 1);
   }
-  const int items = len > cw ? (len - cw + kCW - 1) / kCW : 0;      // gl = cw, cw + kCW, ...
   for (int it = 0; it < items; it += 2) {
     const bool v1 = it + 1 < items;
     const int gl0 = cw + it * kCW, gl1 = v1 ? gl0 + kCW : gl0;
-    uint2 a0, b0, a1, b1;
-    load_item<PRO>(P, 0, g_lo + gl0, koff, a0, b0);
-    load_item<PRO>(P, 0, g_lo + gl1, koff, a1, b1);
+    if (!(preloaded && it == 0)) {
+      load_item<PRO>(P, 0, g_lo + gl0, koff, a0, b0);
+      load_item<PRO>(P, 0, g_lo + gl1, koff, a1, b1);
+    }
     __half2 lo0, hi0, lo1, hi1;
     finish_item<PRO>(a0, b0, rs1, lo0, hi0);
     finish_item<PRO>(a1, b1, rs1, lo1, hi1);

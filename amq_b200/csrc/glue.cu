@@ -52,10 +52,21 @@ __global__ void embed_kernel(const int64_t* __restrict__ ids, const __half* __re
 // grid (Hq, B), 16 warps.  Lane l of a warp owns head-dim elements [EPL*l, EPL*l+EPL); warp w owns
 // positions w, w+16, ...  (8 in flight per warp: one pass covers 128 cached positions).
 constexpr int kAttnWarps = 16;
-__device__ __forceinline__ float ld_dep(const __half* p) {
-  unsigned short v;
-  asm volatile("ld.global.u16 %0, [%1];" : "=h"(v) : "l"(p) : "memory");
-  return __half2float(__ushort_as_half(v));
+// EPL consecutive fp16 values that depend on the previous kernel: ONE vector load, volatile asm so that it stays below
+// griddepcontrol.wait (qkv is const __restrict__, which would otherwise let the compiler hoist it above the wait)
+template <int EPL>
+__device__ __forceinline__ void ld_dep(const __half* p, float (&out)[EPL]) {
+  if (EPL == 4) {
+    uint32_t a, b;
+    asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "l"(p) : "memory");
+    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&a)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&b));
+    out[0] = f0.x; out[1] = f0.y; out[EPL - 2] = f1.x; out[EPL - 1] = f1.y;
+  } else {
+    uint32_t a;
+    asm volatile("ld.global.u32 %0, [%1];" : "=r"(a) : "l"(p) : "memory");
+    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&a));
+    out[0] = f0.x; out[1] = f0.y;
+  }
 }
 template <int D>
 __global__ void __launch_bounds__(kAttnWarps * 32)
@@ -118,18 +129,19 @@ attn_decode_kernel(const __half* __restrict__ qkv, __half* __restrict__ kc, __ha
   pdl_wait();
   // RoPE, HF rotate_half convention: pair (i, i + D/2), angle pos * theta^(-2i/D)
   float q[EPL], kn[EPL], vn[EPL];
+  {
+    // the lane's EPL elements and their rotate_half partners (i +- D/2) are both contiguous: five vector loads in flight
+    const int i0 = EPL * lane, ip0 = i0 < D / 2 ? i0 + D / 2 : i0 - D / 2;
+    const float sgn = i0 < D / 2 ? -1.f : 1.f;
+    float qa[EPL], qb[EPL], ka[EPL], kb[EPL];
+    ld_dep<EPL>(qp + i0, qa); ld_dep<EPL>(qp + ip0, qb);
+    ld_dep<EPL>(kp + i0, ka); ld_dep<EPL>(kp + ip0, kb);
+    ld_dep<EPL>(vp + i0, vn);
 #pragma unroll
-  for (int e = 0; e < EPL; ++e) {
-    const int i = EPL * lane + e;
-    const int ip = i < D / 2 ? i + D / 2 : i - D / 2;
-    const float sgn = i < D / 2 ? -1.f : 1.f;
-    // ld_dep: these are the ONLY loads that depend on the previous kernel; volatile asm keeps them below the wait
-    // (qkv is const __restrict__, which would otherwise let the compiler hoist them above it)
-    q[e] = ld_dep(qp + i) * cs[e] + sgn * ld_dep(qp + ip) * sn[e];
-    kn[e] = ld_dep(kp + i) * cs[e] + sgn * ld_dep(kp + ip) * sn[e];
-    q[e] = __half2float(__float2half_rn(q[e]));
-    kn[e] = __half2float(__float2half_rn(kn[e]));
-    vn[e] = ld_dep(vp + i);
+    for (int e = 0; e < EPL; ++e) {
+      q[e] = __half2float(__float2half_rn(qa[e] * cs[e] + sgn * qb[e] * sn[e]));
+      kn[e] = __half2float(__float2half_rn(ka[e] * cs[e] + sgn * kb[e] * sn[e]));
+    }
   }
   if (h % rep == 0 && warp == 0) {
 #pragma unroll

@@ -127,3 +127,43 @@ def test_step_host_matches_device_loop():
     assert all(torch.equal(a, b) for a, b in zip(want, got))
     with pytest.raises(ValueError):
         m.step_host(start.clone(), host_out)    # not pinned
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("family", ["llama", "qwen2", "gqa128"])
+def test_persistent_decode_kernel_matches_chain(family):
+    """amqb_decode_layers (all layers in one cooperative launch, csrc/decode_mega.cu) against the torch fp32 reference
+    and against the chained per-linear launches: same logits within fp16 rounding, same greedy tokens, no barrier
+    time-out; eager and graph-replayed."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from amq_b200.arch import ModelShape, LINEARS
+    from amq_b200.model import QuantDecoder
+    if family == "llama":
+        shape = ModelShape("tiny-llama", 256, 512, 4, 4, 3, 512, head_dim=64)
+    elif family == "qwen2":
+        shape = ModelShape("tiny-qwen2", 256, 512, 4, 2, 2, 512, head_dim=64, rope_theta=1e6, rms_eps=1e-6, qkv_bias=True)
+    else:
+        shape = ModelShape("tiny-gqa", 512, 1408, 4, 2, 2, 512, head_dim=128)
+    rs = np.random.RandomState(1)
+    arch = {n: rs.choice([2, 3, 4], size=shape.n_block).tolist() for n in LINEARS}
+    mp = QuantDecoder(shape, arch, batch=1, max_seq=48, seed=2, persistent=True)
+    mc = QuantDecoder(shape, arch, batch=1, max_seq=48, seed=2, persistent=False)
+    assert mp.persistent and not mc.persistent
+    kc = [torch.zeros(1, mp.Hkv, 48, mp.D, device=mp.dev) for _ in mp.layers]
+    vc = [torch.zeros(1, mp.Hkv, 48, mp.D, device=mp.dev) for _ in mp.layers]
+    tok = torch.randint(0, shape.vocab, (1,), device=mp.dev)
+    for m in (mp, mc):
+        m.reset(); m.tokens.copy_(tok)
+    for pos in range(40):                      # crosses the 16-position and 32-position boundaries of the attention phase
+        cur = mp.tokens.clone()
+        ref = _ref_step(mp, cur, pos, kc, vc) if pos < 6 else None
+        mc.tokens.copy_(cur)                   # keep the two decoders on the same token stream
+        if pos % 2: mp.step(); mc.step()
+        else: mp.step_eager(); mc.step_eager()
+        torch.cuda.synchronize()
+        assert int(mp.mega_err.item()) == 0
+        rel = (mp.logits - mc.logits).abs().max() / mc.logits.abs().max()
+        assert rel < 5e-3, (family, pos, float(rel))
+        if ref is not None:
+            assert (mp.logits - ref).abs().max() / ref.abs().max() < 2e-2

@@ -20,8 +20,8 @@ d = dbg.cpu().view(148, 5, 8).double()
 t0 = d[:, 0, 1].clone().view(148, 1, 1)
 d = torch.where(d > 0, (d - t0) / 1.965e3, torch.full_like(d, float("nan")))
 names = ["qkv", "attn", "o", "gu", "down"]
-ev = {0: "phase entered", 1: "wait done", 2: "x' built", 4: "last deposit", 5: "reducer arrived"}
+ev = {0: "phase entered", 1: "wait done", 2: "x' built / qkv loaded", 3: "attn loop done", 6: "attn cta barrier", 4: "last deposit / attn arrived", 5: "reducer arrived"}
 for t in range(5):
     for e, nm in ev.items():
         c = d[:, t, e]; c = c[~torch.isnan(c)]
-        if c.numel(): print(f"{names[t]:5s} {nm:16s} n={c.numel():3d} min {c.min():7.2f} med {c.median():7.2f} max {c.max():7.2f} us")
+        if c.numel(): print(f"{names[t]:5s} {nm:28s} n={c.numel():3d} min {c.min():7.2f} med {c.median():7.2f} max {c.max():7.2f} us")
