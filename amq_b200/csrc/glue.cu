@@ -320,6 +320,80 @@ lm_head_kernel(const __half* __restrict__ W, const __half* __restrict__ x, const
   }
 }
 
+// M = 2..16: tensor-core lm_head.  One warp per 16 vocab rows, W streamed once with 16-byte loads.  The k order inside
+// an MMA is permuted identically on both operands, so the 8 consecutive weights a lane loads feed two m16n8k16 MMAs
+// directly from registers (no shared-memory staging of W, no ldmatrix); activations sit in shared memory (fp16,
+// normalised once per CTA, rows padded by 64 B against bank conflicts).
+constexpr int kHeadPad = 32;     // halves
+template <int NB>
+__global__ void __launch_bounds__(256)
+lm_head_mma_kernel(const __half* __restrict__ W, const __half* __restrict__ x, const __half* __restrict__ gamma,
+                   float eps, float* __restrict__ logits, int M, int V, int K) {
+  extern __shared__ __half xs[];   // [NB*8][K + kHeadPad]
+  __shared__ float ssq[8];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ldk = K + kHeadPad;
+  for (int m = 0; m < NB * 8; ++m) {
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < K; i += 256) {
+      const __half hv = m < M ? x[(size_t)m * K + i] : __float2half(0.f);
+      const float v = __half2float(hv);
+      xs[m * ldk + i] = hv;
+      ss += v * v;
+    }
+    if (gamma && m < M) {            // m < M is uniform across the CTA
+#pragma unroll
+      for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      if (lane == 0) ssq[warp] = ss;
+      __syncthreads();
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += ssq[w];
+      const float rs = rsqrtf(t / (float)K + eps);
+      for (int i = threadIdx.x; i < K; i += 256) {
+        const __half xn = __float2half_rn(__half2float(xs[m * ldk + i]) * rs);
+        xs[m * ldk + i] = __hmul(gamma[i], xn);
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  const int g = lane >> 2, t = lane & 3;
+  const int tiles = V / 16;
+  for (int tile = blockIdx.x * 8 + warp; tile < tiles; tile += gridDim.x * 8) {
+    const uint4* w0 = reinterpret_cast<const uint4*>(W + (size_t)(tile * 16 + g) * K) + t;
+    const uint4* w1 = reinterpret_cast<const uint4*>(W + (size_t)(tile * 16 + g + 8) * K) + t;
+    float c[NB][4];
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) c[nb][i] = 0.f;
+#pragma unroll 8
+    for (int kk = 0; kk < K / 32; ++kk) {
+      uint4 a, b;
+      asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(w0 + kk * 4));
+      asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(w1 + kk * 4));
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        const uint4 xv = *reinterpret_cast<const uint4*>(xs + (size_t)(nb * 8 + g) * ldk + 32 * kk + 8 * t);
+        const uint32_t a0[4] = {a.x, b.x, a.y, b.y}, a1[4] = {a.z, b.z, a.w, b.w};
+        mma_m16n8k16(c[nb], a0, xv.x, xv.y, c[nb]);
+        mma_m16n8k16(c[nb], a1, xv.z, xv.w, c[nb]);
+      }
+    }
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      const int m0 = nb * 8 + 2 * t, r0 = tile * 16 + g;
+      if (m0 < M) { logits[(size_t)m0 * V + r0] = c[nb][0]; logits[(size_t)m0 * V + r0 + 8] = c[nb][2]; }
+      if (m0 + 1 < M) { logits[(size_t)(m0 + 1) * V + r0] = c[nb][1]; logits[(size_t)(m0 + 1) * V + r0 + 8] = c[nb][3]; }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ argmax (lowest index among maxima)
 __global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ logits, int64_t* __restrict__ out, int V) {
   pdl_launch_dependents();
@@ -402,10 +476,31 @@ int amqb_lm_head(const void* W_f16, const void* x, const void* gamma, float eps,
     if (rc) return rc;
     return amqb_lm_head(W_f16, (const __half*)x + (size_t)h1 * K, gamma, eps, logits + (size_t)h1 * V, M - h1, V, K, stream);
   }
-  const size_t smem = (size_t)M * K * sizeof(__half);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (M >= 2 && V % 16 == 0 && K % 32 == 0) {
+    // batches: tensor-core kernel (the CUDA-core kernel below is FMA-bound beyond one activation row)
+    const int NB = M <= 8 ? 1 : 2;
+    const size_t smem_mma = (size_t)NB * 8 * (K + kHeadPad) * sizeof(__half);
+    if (smem_mma <= 200 * 1024) {
+      static bool attr_mma = false;
+      if (!attr_mma) {
+        cudaFuncSetAttribute(lm_head_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(lm_head_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_mma = true;
+      }
+      const int per_sm_mma = smem_mma > 100 * 1024 ? 1 : 2;
+      int grid_mma = sms * per_sm_mma;
+      if (grid_mma > (V / 16 + 7) / 8) grid_mma = (V / 16 + 7) / 8;
+      if (NB == 1)
+        return launch(lm_head_mma_kernel<1>, dim3(grid_mma), dim3(256), smem_mma, (cudaStream_t)stream, "lm_head", (const __half*)W_f16,
+                      (const __half*)x, (const __half*)gamma, eps, logits, M, V, K);
+      return launch(lm_head_mma_kernel<2>, dim3(grid_mma), dim3(256), smem_mma, (cudaStream_t)stream, "lm_head", (const __half*)W_f16,
+                    (const __half*)x, (const __half*)gamma, eps, logits, M, V, K);
+    }
+  }
+  const size_t smem = (size_t)M * K * sizeof(__half);
   const int per_sm = smem > 100 * 1024 ? 1 : 2;
   cudaStream_t st = (cudaStream_t)stream;
   static bool attr = false;

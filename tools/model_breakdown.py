@@ -9,7 +9,8 @@ import ctypes
 
 shape = MODELS["Llama-2-7b-hf"]
 arch = sample_arch(shape, 3.0, seed=0)
-m = QuantDecoder(shape, arch, batch=1, max_seq=256)
+B = int(os.environ.get("B", "1"))
+m = QuantDecoder(shape, arch, batch=B, max_seq=256)
 m.pos.fill_(100)
 L = lib()
 L.amqb_set_pdl(1)
