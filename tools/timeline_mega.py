@@ -8,6 +8,9 @@ from amq_b200.model import QuantDecoder
 from amq_b200 import _lib
 shape = MODELS["Llama-2-7b-hf"]
 arch = sample_arch(shape, 3.0, seed=0)
+if os.environ.get("UNIFORM"):
+    from amq_b200.arch import LINEARS
+    arch = {n: [int(os.environ["UNIFORM"])] * shape.n_block for n in LINEARS}
 m = QuantDecoder(shape, arch, batch=1, max_seq=256)
 m.pos.fill_(100)
 for _ in range(3): m.step_eager()
