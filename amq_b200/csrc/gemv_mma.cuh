@@ -52,7 +52,7 @@ constexpr int kThreads = kCThreads + 64;     // + producer warp + reducer warp =
 constexpr int kStageRecs = kCW;              // records per pipeline stage: one per consumer warp
 constexpr int kMaxProblems = 4;
 constexpr int kXprimeBudget = 72 * 1024;
-constexpr int kSmemTarget = 208 * 1024;
+constexpr int kSmemTarget = 222 * 1024;
 constexpr int kMaxCluster = 8;
 constexpr uint32_t kMagicI = 0x4B400000u;    // int32 accumulators start at the bit pattern of 1.5 * 2^23 ...
 constexpr float kMagicF = 12582912.f;        // ... so that (float&)acc - 1.5 * 2^23 == the integer sum (|sum| < 2^22)

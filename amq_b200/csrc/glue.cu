@@ -219,21 +219,19 @@ attn_decode_kernel(const __half* __restrict__ qkv, __half* __restrict__ kc, __ha
 #pragma unroll
   for (int e = 0; e < EPL; ++e) s_acc[warp][EPL * lane + e] = acc[e];
   __syncthreads();
-  if (warp == 0) {
+  if (threadIdx.x < D) {                     // one thread per head dim merges the 16 warps' partials
+    const int i = threadIdx.x;
     float gm = -INFINITY;
 #pragma unroll
     for (int w = 0; w < kAttnWarps; ++w) gm = fmaxf(gm, s_m[w]);
-    float gd = 0.f, wt[kAttnWarps];
+    float o = 0.f, gd = 0.f;
 #pragma unroll
-    for (int w = 0; w < kAttnWarps; ++w) { wt[w] = (s_m[w] == -INFINITY) ? 0.f : __expf(s_m[w] - gm); gd += s_d[w] * wt[w]; }
-#pragma unroll
-    for (int e = 0; e < EPL; ++e) {
-      const int i = EPL * lane + e;
-      float o = 0.f;
-#pragma unroll
-      for (int w = 0; w < kAttnWarps; ++w) o += s_acc[w][i] * wt[w];
-      out[(size_t)b * Hq * D + h * D + i] = __float2half_rn(o / gd);
+    for (int w = 0; w < kAttnWarps; ++w) {
+      const float wt = (s_m[w] == -INFINITY) ? 0.f : __expf(s_m[w] - gm);
+      o += s_acc[w][i] * wt;
+      gd += s_d[w] * wt;
     }
+    out[(size_t)b * Hq * D + h * D + i] = __float2half_rn(o / gd);
   }
 }
 
@@ -501,7 +499,7 @@ int amqb_lm_head(const void* W_f16, const void* x, const void* gamma, float eps,
     }
   }
   const size_t smem = (size_t)M * K * sizeof(__half);
-  const int per_sm = smem > 100 * 1024 ? 1 : 2;
+  const int per_sm = smem > 100 * 1024 ? 1 : (smem > 48 * 1024 ? 2 : 4);
   cudaStream_t st = (cudaStream_t)stream;
   static bool attr = false;
   if (!attr) {
