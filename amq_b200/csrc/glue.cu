@@ -287,22 +287,33 @@ lm_head_kernel(const __half* __restrict__ W, const __half* __restrict__ x, const
     float acc[MAXM];
 #pragma unroll
     for (int m = 0; m < MAXM; ++m) acc[m] = 0.f;
-#pragma unroll 16
-    for (int i = lane; i < K / 8; i += 32) {
-      uint4 wv;
-      asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                   : "=r"(wv.x), "=r"(wv.y), "=r"(wv.z), "=r"(wv.w) : "l"(wr + i));
-      const __half2* h2 = reinterpret_cast<const __half2*>(&wv);
-      float wf[8];
+    // eight 16-byte loads per lane issued before the first use (256 B in flight per lane), then the FMAs
+    for (int i0 = lane; i0 < K / 8; i0 += 32 * 8) {
+      uint4 wv[8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h2[j]); wf[2 * j] = f.x; wf[2 * j + 1] = f.y; }
+      for (int u = 0; u < 8; ++u) {
+        wv[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (i0 + 32 * u < K / 8)
+          asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(wv[u].x), "=r"(wv[u].y), "=r"(wv[u].z), "=r"(wv[u].w) : "l"(wr + i0 + 32 * u));
+      }
 #pragma unroll
-      for (int m = 0; m < MAXM; ++m) {
-        if (m < M) {
-          const uint4 xv = *reinterpret_cast<const uint4*>(&xs[m * K + 8 * i]);
-          const __half2* xh = reinterpret_cast<const __half2*>(&xv);
-          const float2 a0 = __half22float2(xh[0]), a1 = __half22float2(xh[1]), a2 = __half22float2(xh[2]), a3 = __half22float2(xh[3]);
-          acc[m] += wf[0] * a0.x + wf[1] * a0.y + wf[2] * a1.x + wf[3] * a1.y + wf[4] * a2.x + wf[5] * a2.y + wf[6] * a3.x + wf[7] * a3.y;
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + 32 * u;
+        if (i < K / 8) {
+          const __half2* h2 = reinterpret_cast<const __half2*>(&wv[u]);
+          float wf[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h2[j]); wf[2 * j] = f.x; wf[2 * j + 1] = f.y; }
+#pragma unroll
+          for (int m = 0; m < MAXM; ++m) {
+            if (m < M) {
+              const uint4 xv = *reinterpret_cast<const uint4*>(&xs[m * K + 8 * i]);
+              const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+              const float2 a0 = __half22float2(xh[0]), a1 = __half22float2(xh[1]), a2 = __half22float2(xh[2]), a3 = __half22float2(xh[3]);
+              acc[m] += wf[0] * a0.x + wf[1] * a0.y + wf[2] * a1.x + wf[3] * a1.y + wf[4] * a2.x + wf[5] * a2.y + wf[6] * a3.x + wf[7] * a3.y;
+            }
+          }
         }
       }
     }
