@@ -404,7 +404,8 @@ lm_head_mma_kernel(const __half* __restrict__ W, const __half* __restrict__ x, c
 }
 
 // ------------------------------------------------------------------ argmax (lowest index among maxima)
-__global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ logits, int64_t* __restrict__ out, int V) {
+__global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ logits, int64_t* __restrict__ out, int V,
+                                                      int64_t* __restrict__ feed, int* __restrict__ pos) {
   pdl_launch_dependents();
   pdl_wait();
   const int m = blockIdx.x;
@@ -433,7 +434,11 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ 
       const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
       if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
     }
-    if (threadIdx.x == 0) out[m] = bi;
+    if (threadIdx.x == 0) {
+      out[m] = bi;
+      if (feed) feed[m] = bi;              // the generated id is the next step's input
+      if (pos && m == 0) pos[0] += 1;      // nothing later in this step reads the position
+    }
   }
 }
 
@@ -532,7 +537,14 @@ int amqb_lm_head(const void* W_f16, const void* x, const void* gamma, float eps,
 
 int amqb_argmax(const float* logits, int64_t* out_ids, int M, int V, void* stream) {
   if (!logits || !out_ids || M < 1 || V < 1) return fail(AMQB_ERR_BAD_ARG, "argmax: bad argument");
-  return launch(argmax_kernel, dim3(M), dim3(1024), 0, (cudaStream_t)stream, "argmax", logits, out_ids, V);
+  return launch(argmax_kernel, dim3(M), dim3(1024), 0, (cudaStream_t)stream, "argmax", logits, out_ids, V, (int64_t*)nullptr,
+                (int*)nullptr);
+}
+
+int amqb_argmax_advance(const float* logits, int64_t* out_ids, int64_t* next_input_ids, int* pos_dev, int M, int V,
+                        void* stream) {
+  if (!logits || !out_ids || M < 1 || V < 1) return fail(AMQB_ERR_BAD_ARG, "argmax_advance: bad argument");
+  return launch(argmax_kernel, dim3(M), dim3(1024), 0, (cudaStream_t)stream, "argmax", logits, out_ids, V, next_input_ids, pos_dev);
 }
 
 }  // extern "C"

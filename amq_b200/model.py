@@ -243,7 +243,9 @@ class QuantDecoder:
                 self.launches_per_step += 1
         check(Lb.amqb_lm_head(ptr(self.lm_head), ptr(self.h), ptr(self.final_norm), ctypes.c_float(S.rms_eps),
                               ptr(self.logits), self.B, S.vocab, self.H, st), "lm_head")
-        check(Lb.amqb_argmax(ptr(self.logits), ptr(self.next_tokens), self.B, S.vocab, st), "argmax")
+        # greedy token, fed back as the next input, position advanced: all in the step's last launch
+        check(Lb.amqb_argmax_advance(ptr(self.logits), ptr(self.next_tokens), ptr(self.tokens), ptr(self.pos), self.B, S.vocab, st),
+              "argmax_advance")
         self.launches_per_step += 2
 
     def _capture(self, host_in: Optional[torch.Tensor] = None, host_out: Optional[torch.Tensor] = None):
@@ -251,23 +253,21 @@ class QuantDecoder:
         s = torch.cuda.Stream(device=self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(s):
-            saved_pos = self.pos.clone()
+            saved_pos, saved_tok = self.pos.clone(), self.tokens.clone()
             for _ in range(2):                      # warm-up outside capture (lazy module loads, attributes)
                 self._step_launches()
-            self.pos.copy_(saved_pos)
+            self.pos.copy_(saved_pos)               # the step advances position and input ids itself: undo the warm-up's
+            self.tokens.copy_(saved_tok)
             s.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=s):
                 if host_in is not None:
                     self.tokens.copy_(host_in, non_blocking=True)      # memcpy node: pinned host -> device
                 self._step_launches()
-                self.tokens.copy_(self.next_tokens)
-                self.pos.add_(1)
                 if host_out is not None:
                     host_out.copy_(self.tokens, non_blocking=True)     # memcpy node: device -> pinned host
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
-        self.pos.copy_(saved_pos)
         return g
 
     def capture(self) -> None:
@@ -303,8 +303,6 @@ class QuantDecoder:
         self.pdl = False
         self._step_launches()
         self.pdl = saved
-        self.tokens.copy_(self.next_tokens)
-        self.pos.add_(1)
 
     def reset(self) -> None:
         self.pos.zero_()

@@ -169,6 +169,10 @@ int amqb_attn_decode(const void* qkv, void* k_cache, void* v_cache, void* out,
 int amqb_lm_head(const void* W_f16, const void* x, const void* gamma, float eps,
                  float* logits, int M, int V, int K, void* stream);
 int amqb_argmax(const float* logits, int64_t* out_ids, int M, int V, void* stream);
+/* Same, and closes the decode step in the same launch: the generated ids are also written to next_input_ids
+ * (may be NULL) and *pos_dev (may be NULL) is incremented, so a captured step needs no extra copy / add nodes. */
+int amqb_argmax_advance(const float* logits, int64_t* out_ids, int64_t* next_input_ids, int* pos_dev,
+                        int M, int V, void* stream);
 
 /* ---- persistent decode kernel: every decoder layer of one batch-1 token in ONE launch --------
  * Replaces the chain of ~5 dependent launches per layer that amq_speed_benchmark.py times
