@@ -372,6 +372,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
   pdl_wait();                        // h comes from the embedding kernel
   float acc[2][1][4];
   int s = 0, ph = 0, nblk = 0;
+  bool waited = true;                // griddepcontrol.wait taken above
   unsigned int phase = 0;
   float rs1 = 1.f;
   for (int layer = 0; layer < A.n_layers; ++layer) {
@@ -401,11 +402,11 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
         const int want = variants == 3 ? (mask & ~built_mask) : (1 << P.bits);
         if (want) {
           if (t == kPhO)
-            build_xprime<AMQB_PRO_NONE>(P, 1, 0, P.n_g, xp, xsd, sred, warp, lane, false, rs1, want, variants, A.xprime_bytes, xl);
+            build_xprime<AMQB_PRO_NONE>(P, 1, 0, P.n_g, xp, xsd, sred, warp, lane, false, rs1, want, variants, A.xprime_bytes, xl, waited);
           else if (t == kPhDown)
-            build_xprime<AMQB_PRO_SILU_MUL>(P, 1, 0, P.n_g, xp, xsd, sred, warp, lane, false, rs1, want, variants, A.xprime_bytes, xl);
+            build_xprime<AMQB_PRO_SILU_MUL>(P, 1, 0, P.n_g, xp, xsd, sred, warp, lane, false, rs1, want, variants, A.xprime_bytes, xl, waited);
           else
-            build_xprime<AMQB_PRO_RMSNORM>(P, 1, 0, P.n_g, xp, xsd, sred, warp, lane, built_mask != 0, rs1, want, variants, A.xprime_bytes, xl);
+            build_xprime<AMQB_PRO_RMSNORM>(P, 1, 0, P.n_g, xp, xsd, sred, warp, lane, built_mask != 0, rs1, want, variants, A.xprime_bytes, xl, waited);
           built_mask |= want;
           AMQB_DBG(if (dbg_on) dbg[2] = clock64();)
         }

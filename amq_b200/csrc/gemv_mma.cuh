@@ -296,12 +296,20 @@ template <int PRO>
 __device__ __forceinline__ void build_xprime(const DevProblem& P, int S, int g_lo, int len, uint8_t* xp,
                                              float2* xsd, float* sred, int cw, int lane, bool have_stats, float& rs1,
                                              int mask, int variants, int var_stride, const XLane (&xl)[3],
-                                             long long* dbgp = nullptr) {
+                                             bool& waited, long long* dbgp = nullptr) {
   const int koff = 16 * (lane >> 2) + 2 * (lane & 3);     // this lane's first k inside a group (second pair at + 8)
   AMQB_DBG(if (dbgp) dbgp[3] = clock64();)
   const int items = len > cw ? (len - cw + kCW - 1) / kCW : 0;      // gl = cw, cw + kCW, ...
   uint2 a0, b0, a1, b1;
   bool preloaded = false;
+  uint8_t* vbase[3];
+  int gbytes[3];
+#pragma unroll
+  for (int v = 0; v < 3; ++v) {
+    vbase[v] = xp + (size_t)(variants == 3 ? v : 0) * var_stride;
+    gbytes[v] = xp_group_bytes(v + 2, 1);
+  }
+  if (!waited) { pdl_wait(); waited = true; }      // first read of x below: everything above overlapped the previous kernel
   if (PRO == AMQB_PRO_RMSNORM && !have_stats) {
     float ss = 0.f;
     if (S == 1 && items <= 2) {
@@ -344,13 +352,6 @@ __device__ __forceinline__ void build_xprime(const DevProblem& P, int S, int g_l
 #pragma unroll
     for (int w = 0; w < kCW; ++w) tt += sred[w];
     rs1 = rsqrtf(tt / (float)P.K + P.eps);
-  }
-  uint8_t* vbase[3];
-  int gbytes[3];
-#pragma unroll
-  for (int v = 0; v < 3; ++v) {
-    vbase[v] = xp + (size_t)(variants == 3 ? v : 0) * var_stride;
-    gbytes[v] = xp_group_bytes(v + 2, 1);
   }
   for (int it = 0; it < items; it += 2) {
     const bool v1 = it + 1 < items;
@@ -746,7 +747,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
     xl[v] = make_xlane(v + 2, lane, 3, 0);
     asm volatile("" :: "r"(xl[v].off0), "r"(xl[v].fexp0), "r"(xl[v].off1), "r"(xl[v].fexp1));
   }
-  pdl_wait();                        // x / residual come from the previous kernel
+  // griddepcontrol.wait is taken as late as possible: right before the first read of x (inside the x' builder, or
+  // before the bulk fetch of the pre-built x' at M > 1), so that the per-problem bookkeeping below also overlaps the
+  // previous kernel's drain
+  bool waited = false;
   AMQB_STAMP(1);
   float acc[2][MB][4];
   int s = 0, ph = 0, nblk = 0;
@@ -773,6 +777,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
       // whatever the host scheduled at this problem (all bit widths of the problems sharing this x)
       if (!M1 && P.xg) {
         // M > 1: x' of this chunk was built once for the whole grid; fetch it like the weights (TMA bulk copy)
+        if (!waited) { pdl_wait(); waited = true; }   // the pre-pass kernel wrote x'
         named_bar_sync(1, kCThreads);              // every warp is done with the previous chunk's x'
         const uint32_t xb = smem_u32(&bars[32]);
         if (tid == 0) {
@@ -787,7 +792,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
         const int want = (chunked || L.xp_variants != 3) ? (1 << P.bits) : ((run_mask | (1 << P.bits)) & ~built_mask);
         if (want && M1)
           build_xprime<PRO>(P, S, c_lo, c_hi - c_lo, xp, xsd, sred + (stat_par ? kCW : 0), warp, lane,
-                            same_x && built_mask != 0, rs1, want, L.xp_variants, L.xprime_bytes, xl
+                            same_x && built_mask != 0, rs1, want, L.xp_variants, L.xprime_bytes, xl, waited
                             AMQB_DBG(, (L.dbg && tid == 0) ? L.dbg + blockIdx.x * 16 : nullptr));
         built_mask |= want | (1 << P.bits);
       }
