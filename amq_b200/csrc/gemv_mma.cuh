@@ -570,6 +570,17 @@ __device__ __forceinline__ void process_record(const uint8_t* rec, const uint8_t
   }
 }
 
+// problem p of the launch descriptor, read with STATIC indices: constant-bank operands with immediate offsets instead of
+// register-indexed constant loads on the dependent path between two problems of a grouped launch
+__device__ __forceinline__ DevProblem load_problem(const GemvLaunch& L, int p) {
+  switch (p) {
+    case 0: return L.prob[0];
+    case 1: return L.prob[1];
+    case 2: return L.prob[2];
+    default: return L.prob[3];
+  }
+}
+
 __device__ __forceinline__ int first_rb(int cid, int rot, int ncl) {
   const int r = cid - rot;
   return r < 0 ? r + ncl : r;
@@ -628,7 +639,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
       int s = 0, ph = 0;
       bool wrapped = false;
       for (int p = 0; p < L.count; ++p) {
-        const DevProblem& P = L.prob[p];
+        const DevProblem P = load_problem(L, p);
         const uint32_t rbytes = rec_bytes(P.bits);
         const int g_lo = (P.n_g * rank) >> L.log2S, g_hi = (P.n_g * (rank + 1)) >> L.log2S;
         for (int c_lo = g_lo; c_lo < g_hi; c_lo += P.kc) {
@@ -661,7 +672,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
     pdl_wait();                      // bias / residual / y belong to the dependency chain
     int nblk = 0;
     for (int p = 0; p < L.count; ++p) {
-      const DevProblem& P = L.prob[p];
+      const DevProblem P = load_problem(L, p);
       if (first_rb(cid, P.rot, ncl) >= P.n_rb) continue;
       const int g_lo = (P.n_g * rank) >> L.log2S, g_hi = (P.n_g * (rank + 1)) >> L.log2S;
       const bool chunked = (g_hi - g_lo) > P.kc;
@@ -760,7 +771,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
   uint32_t xphase = 0;
   float rs1 = 1.f;
   for (int p = 0; p < L.count; ++p) {
-    const DevProblem& P = L.prob[p];
+    const DevProblem P = load_problem(L, p);
     const uint32_t rbytes = rec_bytes(P.bits);
     const int gbytes = xp_group_bytes(P.bits, M);
     const int g_lo = (P.n_g * rank) >> L.log2S, g_hi = (P.n_g * (rank + 1)) >> L.log2S;
