@@ -682,6 +682,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
         int j = 0;
         for (int rb = first_rb(cid, P.rot, ncl); rb < P.n_rb; rb += ncl, ++nblk, ++j) {
           const int buf = nblk & 1, use = nblk >> 1;
+            // batch 1, unsplit K: bias and residual of this row block are fetched BEFORE waiting for the consumers'
+            // partial sums, so the store follows the last deposit without an L2 round trip
+            float addend = 0.f;
+            const bool pre = M1 && S == 1 && !chunked;
+            if (pre) {
+              const int n = rb * 32 + lane;
+              if (P.bias) addend += __half2float(P.bias[n]);
+              if (P.residual) addend += __half2float(__ushort_as_half(__ldcg(reinterpret_cast<const unsigned short*>(P.residual) + n)));
+            }
             mbar_wait(smem_u32(&bars[28 + buf]), use & 1);
             const float* rbase = red + (size_t)buf * kCW * 2 * MB * 128;
             constexpr int EPT = M1 ? 1 : 8 * MB;                 // output elements per lane
@@ -706,7 +715,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
               }
               if (last_chunk) {
                 if (S == 1) {
-                  if (col < M) store_out(P, rb * 32 + row, col, v);
+                  if (pre) P.y[rb * 32 + row] = __float2half_rn(v + addend);
+                  else if (col < M) store_out(P, rb * 32 + row, col, v);
                 } else {
                   // K was split across the cluster: partial sums meet in rank 0's shared memory (DSMEM)
                   float* pslot = part + (size_t)(p * S + rank) * 2 * MB * 128 + e;
