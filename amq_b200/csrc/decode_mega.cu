@@ -515,7 +515,7 @@ int amqb_decode_layers(const amqb_mega_shape* shp, const amqb_mega_layer* layers
   A.stage_bytes = kStageRecs * rec_bytes(4);
   {
     const char* e = getenv("AMQB_COPY_RECS");
-    A.copy_recs = e ? atoi(e) : 4;
+    A.copy_recs = e ? atoi(e) : 8;
     if (A.copy_recs < 1) A.copy_recs = 1;
   }
   const size_t smem_max = 227 * 1024;

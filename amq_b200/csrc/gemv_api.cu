@@ -130,7 +130,7 @@ static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, 
   }
   {
     const char* e = getenv("AMQB_COPY_RECS");
-    L.copy_recs = e ? atoi(e) : 4;
+    L.copy_recs = e ? atoi(e) : 8;
     if (L.copy_recs < 1) L.copy_recs = 1;
     const char* d = getenv("AMQB_DBG_DELAY_NS");
     L.dbg_delay_ns = d ? atoi(d) : 0;
