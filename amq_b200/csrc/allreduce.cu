@@ -40,9 +40,15 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 
 __global__ void __launch_bounds__(1024) allreduce_push_kernel(const ArArgs A) {
   __shared__ uint32_t s_epoch;
+  __shared__ uint8_t* s_peer[kArMaxWorld];
   pdl_launch_dependents();
-  pdl_wait();
+  // Before griddepcontrol.wait (overlaps the GEMV that produces `partial`): the peer pointers go to shared memory
+  // (no register-indexed constant loads on the dependent path) and the epoch is advanced.  The epoch word is
+  // private to this rank's all-reduce launches, and the previous one has completed by the time this grid can start
+  // (the GEMV between them waited for it before any of its CTAs could finish and free an SM for us... and this
+  // kernel's single CTA only starts once that GEMV's grid is resident).
   uint8_t* mine = A.peer[A.rank];
+  if (threadIdx.x < kArMaxWorld) s_peer[threadIdx.x] = A.peer[threadIdx.x];
   if (threadIdx.x == 0) {
     uint32_t* ep = reinterpret_cast<uint32_t*>(mine);
     s_epoch = *ep + 1;
@@ -54,35 +60,44 @@ __global__ void __launch_bounds__(1024) allreduce_push_kernel(const ArArgs A) {
   const size_t data_off = kArHeader + 128 * (size_t)A.world + (size_t)(epoch & 1) * A.world * slot_bytes;
   const int nvec = A.n_elems / 8;                         // 16-byte vectors
   const uint4* src = reinterpret_cast<const uint4*>(A.partial);
-  // 1. push my partial sums into slot [rank] of every peer (and my own buffer)
-  for (int i = threadIdx.x; i < nvec * A.world; i += blockDim.x) {
-    const int p = i / nvec, v = i - p * nvec;
-    reinterpret_cast<uint4*>(A.peer[p] + data_off + (size_t)A.rank * slot_bytes)[v] = src[v];
+  pdl_wait();
+  // 1. push my partial sums into slot [rank] of every peer (and my own buffer): each thread loads its vectors once
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    const uint4 q = __ldcg(src + v);
+    for (int p = 0; p < A.world; ++p)
+      reinterpret_cast<uint4*>(s_peer[p] + data_off + (size_t)A.rank * slot_bytes)[v] = q;
   }
-  __threadfence_system();
   __syncthreads();
-  // 2. raise my flag in every peer's buffer, 3. wait for every peer's flag in mine
-  if (threadIdx.x < A.world)
-    st_release_sys(reinterpret_cast<uint32_t*>(A.peer[threadIdx.x] + kArHeader + 128 * A.rank), epoch);
+  // 2. raise my flag in every peer's buffer (st.release.sys after the barrier is cumulative over the block's stores),
+  // 3. wait for every peer's flag in mine
   if (threadIdx.x < A.world) {
+    st_release_sys(reinterpret_cast<uint32_t*>(s_peer[threadIdx.x] + kArHeader + 128 * A.rank), epoch);
     const uint32_t* f = reinterpret_cast<const uint32_t*>(mine + kArHeader + 128 * threadIdx.x);
     while (ld_acquire_sys(f) != epoch) {}
   }
   __syncthreads();
-  // 4. reduce in rank order (+ residual)
+  // 4. reduce in rank order (+ residual); all loads of a vector are issued before the first add
   for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    uint4 q[kArMaxWorld / 2];
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    for (int r = 0; r < A.world; ++r) {
-      const uint4 q = reinterpret_cast<const uint4*>(mine + data_off + (size_t)r * slot_bytes)[v];
-      const __half2* h = reinterpret_cast<const __half2*>(&q);
+    uint4 res = make_uint4(0u, 0u, 0u, 0u);
+    if (A.residual) res = __ldcg(reinterpret_cast<const uint4*>(A.residual) + v);
+    for (int r0 = 0; r0 < A.world; r0 += kArMaxWorld / 2) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); acc[2 * i] += f.x; acc[2 * i + 1] += f.y; }
+      for (int u = 0; u < kArMaxWorld / 2; ++u)
+        if (r0 + u < A.world) q[u] = __ldcg(reinterpret_cast<const uint4*>(mine + data_off + (size_t)(r0 + u) * slot_bytes) + v);
+#pragma unroll
+      for (int u = 0; u < kArMaxWorld / 2; ++u)
+        if (r0 + u < A.world) {
+          const __half2* h = reinterpret_cast<const __half2*>(&q[u]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); acc[2 * i] += f.x; acc[2 * i + 1] += f.y; }
+        }
     }
     if (A.residual) {
-      const uint4 q = reinterpret_cast<const uint4*>(A.residual)[v];
-      const __half2* h = reinterpret_cast<const __half2*>(&q);
+      const __half2* h = reinterpret_cast<const __half2*>(&res);
 #pragma unroll
       for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); acc[2 * i] += f.x; acc[2 * i + 1] += f.y; }
     }
