@@ -389,10 +389,20 @@ template <int PRO>
 __global__ void __launch_bounds__(kXgWarps * 32) xprime_global_kernel(const XgArgs A) {
   __shared__ float sred[kXgWarps];
   pdl_launch_dependents();
-  pdl_wait();
   const int col = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_g = A.K / kGroup, M = A.M;
   const int koff = 16 * (lane >> 2) + 2 * (lane & 3);
+  // per-lane constants before griddepcontrol.wait (they overlap the previous kernel's drain)
+  const bool wide = M > 2;
+  const int C = 3 * M, col0 = wide ? col : 3 * col, cstride = wide ? M : 1;
+  XLane xl[3];
+  int gbytes[3];
+#pragma unroll
+  for (int v = 0; v < 3; ++v) {
+    xl[v] = make_xlane(v + 2, lane, C, col0); gbytes[v] = xp_group_bytes(v + 2, M);
+    asm volatile("" :: "r"(xl[v].off0), "r"(xl[v].fexp0), "r"(xl[v].off1), "r"(xl[v].fexp1));
+  }
+  pdl_wait();
   float rs = 1.f;
   if (PRO == AMQB_PRO_RMSNORM) {
     float ss = 0.f;
@@ -412,12 +422,6 @@ __global__ void __launch_bounds__(kXgWarps * 32) xprime_global_kernel(const XgAr
     for (int w = 0; w < kXgWarps; ++w) tt += sred[w];
     rs = rsqrtf(tt / (float)A.K + A.eps);
   }
-  const bool wide = M > 2;
-  const int C = 3 * M, col0 = wide ? col : 3 * col, cstride = wide ? M : 1;
-  XLane xl[3];
-  int gbytes[3];
-#pragma unroll
-  for (int v = 0; v < 3; ++v) { xl[v] = make_xlane(v + 2, lane, C, col0); gbytes[v] = xp_group_bytes(v + 2, M); }
   uint8_t* const vbase[3] = {A.xg[0], A.xg[1], A.xg[2]};
   for (int gl = blockIdx.y * kXgWarps + warp; gl < n_g; gl += gridDim.y * kXgWarps) {
     const __half* xr = A.x + (size_t)col * A.ldx + gl * kGroup + koff;
