@@ -1,3 +1,5 @@
+"""Decode step of a tiny model in three modes (eager, graph without PDL, graph with PDL) against the torch fp32
+reference; AMQB_PERSISTENT=1 runs the persistent kernel.  Catches ordering bugs that only show under PDL."""
 import sys, os, numpy as np, torch
 sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
 from test_gpu_model import _ref_step
