@@ -38,7 +38,9 @@ static int launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cu
 }
 
 // ------------------------------------------------------------------ embedding
-__global__ void embed_kernel(const int64_t* __restrict__ ids, const __half* __restrict__ table,
+// inputs written by the previous kernel are NOT __restrict__: nothing may let the compiler move their loads above
+// griddepcontrol.wait (see attn_decode_kernel)
+__global__ void embed_kernel(const int64_t* ids, const __half* __restrict__ table,
                              __half* __restrict__ out, int hidden) {
   pdl_launch_dependents();
   pdl_wait();
@@ -249,7 +251,7 @@ __global__ void rope_table_kernel(float2* __restrict__ tab, int max_seq, int D, 
 // One warp per vocab row (grid-stride); x normalised once per CTA into shared memory (fp32).
 template <int MAXM>
 __global__ void __launch_bounds__(256)
-lm_head_kernel(const __half* __restrict__ W, const __half* __restrict__ x, const __half* __restrict__ gamma,
+lm_head_kernel(const __half* __restrict__ W, const __half* x, const __half* __restrict__ gamma,
                float eps, float* __restrict__ logits, int M, int V, int K) {
   extern __shared__ __half xs[];   // [M][K] normalised activations (fp16, as the HF model feeds lm_head)
   __shared__ float ssq[8];
@@ -336,7 +338,7 @@ lm_head_kernel(const __half* __restrict__ W, const __half* __restrict__ x, const
 constexpr int kHeadPad = 32;     // halves
 template <int NB>
 __global__ void __launch_bounds__(256)
-lm_head_mma_kernel(const __half* __restrict__ W, const __half* __restrict__ x, const __half* __restrict__ gamma,
+lm_head_mma_kernel(const __half* __restrict__ W, const __half* x, const __half* __restrict__ gamma,
                    float eps, float* __restrict__ logits, int M, int V, int K) {
   extern __shared__ __half xs[];   // [NB*8][K + kHeadPad]
   __shared__ float ssq[8];
@@ -404,7 +406,7 @@ lm_head_mma_kernel(const __half* __restrict__ W, const __half* __restrict__ x, c
 }
 
 // ------------------------------------------------------------------ argmax (lowest index among maxima)
-__global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ logits, int64_t* __restrict__ out, int V,
+__global__ void __launch_bounds__(1024) argmax_kernel(const float* logits, int64_t* __restrict__ out, int V,
                                                       int64_t* __restrict__ feed, int* __restrict__ pos) {
   pdl_launch_dependents();
   pdl_wait();
