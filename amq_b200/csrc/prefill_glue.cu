@@ -1,0 +1,248 @@
+// Prompt-prefill glue around the tensor-core quantized linears (the M > 1 side): row-wise
+// RMSNorm, RoPE + KV-cache append for a block of prompt positions, causal attention over the cache, SiLU*up and the
+// residual add.  The decode path fuses all of these into the GEMV prologue / epilogue (gemv_mma.cuh) or the
+// single-query attention kernel (glue.cu); the prefill linears run through amqb_gemm_tc (tcgen05) whose operands
+// are whole [M, K] matrices, so here they are separate HBM-bound row kernels.
+//
+// Reference counterparts (HF modules the reference benchmark drives with the prompt, speed.py:23-46, and the FT
+// kernels it can swap in):
+//   RMSNorm                   /root/reference/amq/kernel/ft/layernorm/layernorm.cu:25-51
+//   RoPE + attention + cache  /root/reference/amq/kernel/ft/attention/ft_attention.cpp:110-181
+//   static KV cache layout    /root/reference/amq/kernel/monkeypatch/ftllama_modeling.py:61-68
+// Numerics follow the decode kernels op for op (fp16-rounded cos / sin, q and k rounded to fp16 after the rotation,
+// gamma * fp16(x * rsqrt(mean x^2 + eps)), fp16 silu(gate) * up) so that a prompt consumed here leaves the same
+// cache contents (to fp16 rounding of the linears) as the same prompt consumed token by token.
+#include "common.cuh"
+
+namespace amqb {
+
+// ------------------------------------------------------------------ RMSNorm over rows
+// grid = rows, 256 threads; one pass over the row for the statistic (L1 / L2 serve the second)
+__global__ void __launch_bounds__(256)
+rmsnorm_rows_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma, float eps,
+                    __half* __restrict__ out, int H) {
+  __shared__ float part[8];
+  const __half2* xr = reinterpret_cast<const __half2*>(x + (size_t)blockIdx.x * H);
+  const __half2* gr = reinterpret_cast<const __half2*>(gamma);
+  __half2* orow = reinterpret_cast<__half2*>(out + (size_t)blockIdx.x * H);
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < H / 2; i += blockDim.x) {
+    const float2 v = __half22float2(xr[i]);
+    ss += v.x * v.x + v.y * v.y;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tot += part[w];
+  const float rs = rsqrtf(tot / (float)H + eps);
+  for (int i = threadIdx.x; i < H / 2; i += blockDim.x) {
+    float2 v = __half22float2(xr[i]);
+    v.x *= rs; v.y *= rs;
+    orow[i] = __hmul2(gr[i], __float22half2_rn(v));
+  }
+}
+
+// ------------------------------------------------------------------ silu(gate) * up, h += y
+__global__ void __launch_bounds__(256)
+silu_mul_kernel(const __half2* __restrict__ gate, const __half2* __restrict__ up, __half2* __restrict__ out, size_t n2) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+    float2 g = __half22float2(gate[i]);
+    g.x = __fdividef(g.x, 1.f + __expf(-g.x));
+    g.y = __fdividef(g.y, 1.f + __expf(-g.y));
+    out[i] = __hmul2(__float22half2_rn(g), up[i]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+add_rows_kernel(__half2* __restrict__ h, const __half2* __restrict__ y, size_t n2) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+    const float2 a = __half22float2(h[i]), b = __half22float2(y[i]);
+    h[i] = __float22half2_rn(make_float2(a.x + b.x, a.y + b.y));
+  }
+}
+
+// ------------------------------------------------------------------ RoPE + KV append for T prompt positions
+// grid (T, B), 256 threads.  q is rotated in place; rotated k and plain v go to the cache rows pos0 + t.
+__global__ void __launch_bounds__(256)
+rope_append_kernel(__half* __restrict__ q, const __half* __restrict__ k, const __half* __restrict__ v,
+                   __half* __restrict__ kc, __half* __restrict__ vc, const float2* __restrict__ rope_tab,
+                   int pos0, int T, int Hq, int Hkv, int D, int max_seq) {
+  const int t = blockIdx.x, b = blockIdx.y;
+  const size_t row = (size_t)b * T + t;
+  const int pos = pos0 + t;
+  const int half_d = D / 2;
+  __half* qr = q + row * (size_t)Hq * D;
+  const __half* kr = k + row * (size_t)Hkv * D;
+  const __half* vr = v + row * (size_t)Hkv * D;
+  const float2* tab = rope_tab + (size_t)pos * half_d;
+  // HF rotate_half convention: pair (i, i + D/2), angle pos * theta^(-2i/D); cos / sin rounded to fp16 as
+  // LlamaRotaryEmbedding casts them to the activation dtype
+  for (int idx = threadIdx.x; idx < (Hq + Hkv) * half_d; idx += blockDim.x) {
+    const int head = idx / half_d, i = idx - head * half_d;
+    const float2 cs2 = tab[i];
+    const float cs = __half2float(__float2half_rn(cs2.x)), sn = __half2float(__float2half_rn(cs2.y));
+    if (head < Hq) {
+      __half* p = qr + head * D;
+      const float a = __half2float(p[i]), c = __half2float(p[i + half_d]);
+      p[i] = __float2half_rn(a * cs - c * sn);
+      p[i + half_d] = __float2half_rn(c * cs + a * sn);
+    } else {
+      const int hk = head - Hq;
+      const __half* p = kr + hk * D;
+      __half* dst = kc + (((size_t)b * Hkv + hk) * max_seq + pos) * D;
+      const float a = __half2float(p[i]), c = __half2float(p[i + half_d]);
+      dst[i] = __float2half_rn(a * cs - c * sn);
+      dst[i + half_d] = __float2half_rn(c * cs + a * sn);
+    }
+  }
+  for (int idx = threadIdx.x; idx < Hkv * D; idx += blockDim.x) {
+    const int hk = idx / D, i = idx - hk * D;
+    vc[(((size_t)b * Hkv + hk) * max_seq + pos) * D + i] = vr[idx];
+  }
+}
+
+// ------------------------------------------------------------------ causal attention over the cache
+// grid (ceil(T / 8), Hq, B), 8 warps: warp w owns query t0 + w (cache position pos0 + t0 + w) of head h.  The cached
+// K / V rows are staged 32 positions at a time in shared memory (each row is read from L2 once per 8 queries); inside
+// a warp lane l owns head-dim elements [EPL*l, EPL*l + EPL) like the decode kernel: eight positions in flight per
+// butterfly reduction, online softmax in fp32.
+constexpr int kPfWarps = 8;
+constexpr int kPfTile = 32;
+template <int D>
+__global__ void __launch_bounds__(kPfWarps * 32)
+attn_prefill_kernel(const __half* __restrict__ q, const __half* __restrict__ kc, const __half* __restrict__ vc,
+                    __half* __restrict__ out, int pos0, int T, int Hq, int Hkv, int max_seq) {
+  constexpr int EPL = D / 32;
+  constexpr int UNR = 8;
+  __shared__ __align__(16) __half sk[kPfTile][D];
+  __shared__ __align__(16) __half sv[kPfTile][D];
+  const int t0 = blockIdx.x * kPfWarps, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hk = h / (Hq / Hkv);
+  const int t = t0 + warp;
+  const bool active = t < T;
+  const int p = pos0 + (active ? t : T - 1);               // this warp's last visible cache position
+  const int t_last = min(t0 + kPfWarps, T) - 1;
+  const int p_max = pos0 + t_last;                          // the CTA's last visible position
+  const __half* kcb = kc + ((size_t)b * Hkv + hk) * max_seq * D;
+  const __half* vcb = vc + ((size_t)b * Hkv + hk) * max_seq * D;
+  float qf[EPL];
+  {
+    const __half* qp = q + ((size_t)b * T + (active ? t : T - 1)) * (size_t)Hq * D + h * D + EPL * lane;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) qf[e] = __half2float(qp[e]);
+  }
+  const float scale = rsqrtf((float)D);
+  float mx = -INFINITY, den = 0.f, acc[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
+  for (int j0 = 0; j0 <= p_max; j0 += kPfTile) {
+    __syncthreads();                                        // the previous tile has been consumed
+    constexpr int V8 = D / 8;                               // uint4 per row
+    for (int i = threadIdx.x; i < kPfTile * V8; i += kPfWarps * 32) {
+      const int r = i / V8, c = i - r * V8;
+      if (j0 + r <= p_max) {
+        reinterpret_cast<uint4*>(&sk[r][0])[c] = reinterpret_cast<const uint4*>(kcb + (size_t)(j0 + r) * D)[c];
+        reinterpret_cast<uint4*>(&sv[r][0])[c] = reinterpret_cast<const uint4*>(vcb + (size_t)(j0 + r) * D)[c];
+      }
+    }
+    __syncthreads();
+    if (j0 > p) continue;                                   // warp-uniform: nothing visible to this query in the tile
+#pragma unroll 1
+    for (int jj = 0; jj < kPfTile; jj += UNR) {
+      if (j0 + jj > p) break;                               // warp-uniform
+      float sc[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        float s = 0.f;
+        if (j0 + jj + u <= p) {                             // rows beyond p_max were never staged: do not touch them
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) s += qf[e] * __half2float(sk[jj + u][EPL * lane + e]);
+        }
+        sc[u] = s;
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1)
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], o);
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if (j0 + jj + u <= p) {
+          const float s = sc[u] * scale;
+          const float nm = fmaxf(mx, s);
+          const float corr = __expf(mx - nm), pr = __expf(s - nm);
+          den = den * corr + pr;
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) acc[e] = acc[e] * corr + pr * __half2float(sv[jj + u][EPL * lane + e]);
+          mx = nm;
+        }
+      }
+    }
+  }
+  if (active) {
+    __half* op = out + ((size_t)b * T + t) * (size_t)Hq * D + h * D + EPL * lane;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) op[e] = __float2half_rn(acc[e] / den);
+  }
+}
+
+static int ew_grid(size_t n2) {
+  size_t g = (n2 + 255) / 256;
+  return (int)(g < 148 * 8 ? (g ? g : 1) : 148 * 8);
+}
+
+}  // namespace amqb
+
+using namespace amqb;
+
+extern "C" {
+
+int amqb_rmsnorm_rows(const void* x_f16, const void* gamma_f16, float eps, void* out_f16, int M, int H, void* stream) {
+  if (!x_f16 || !gamma_f16 || !out_f16 || M < 1 || H < 2 || H % 2) return fail(AMQB_ERR_BAD_ARG, "rmsnorm_rows: bad argument");
+  rmsnorm_rows_kernel<<<M, 256, 0, (cudaStream_t)stream>>>((const __half*)x_f16, (const __half*)gamma_f16, eps,
+                                                            (__half*)out_f16, H);
+  return check_launch("rmsnorm_rows");
+}
+
+int amqb_silu_mul_rows(const void* gate_f16, const void* up_f16, void* out_f16, int M, int I, void* stream) {
+  if (!gate_f16 || !up_f16 || !out_f16 || M < 1 || I < 2 || I % 2) return fail(AMQB_ERR_BAD_ARG, "silu_mul_rows: bad argument");
+  const size_t n2 = (size_t)M * I / 2;
+  silu_mul_kernel<<<ew_grid(n2), 256, 0, (cudaStream_t)stream>>>((const __half2*)gate_f16, (const __half2*)up_f16,
+                                                                  (__half2*)out_f16, n2);
+  return check_launch("silu_mul_rows");
+}
+
+int amqb_add_rows(void* h_f16, const void* y_f16, int M, int H, void* stream) {
+  if (!h_f16 || !y_f16 || M < 1 || H < 2 || H % 2) return fail(AMQB_ERR_BAD_ARG, "add_rows: bad argument");
+  const size_t n2 = (size_t)M * H / 2;
+  add_rows_kernel<<<ew_grid(n2), 256, 0, (cudaStream_t)stream>>>((__half2*)h_f16, (const __half2*)y_f16, n2);
+  return check_launch("add_rows");
+}
+
+int amqb_attn_prefill(void* q_f16, const void* k_f16, const void* v_f16, void* k_cache, void* v_cache, void* out_f16,
+                      int pos0, int T, int B, int Hq, int Hkv, int D, int max_seq, const float* rope_cos_sin,
+                      void* stream) {
+  if (!q_f16 || !k_f16 || !v_f16 || !k_cache || !v_cache || !out_f16 || !rope_cos_sin || T < 1 || B < 1 || Hq < 1 ||
+      Hkv < 1 || Hq % Hkv || pos0 < 0 || pos0 + T > max_seq || B > 65535 || Hq > 65535)
+    return fail(AMQB_ERR_BAD_ARG, "attn_prefill: bad argument (pos0 + T <= max_seq, Hq % Hkv == 0, rope table required)");
+  if (D != 64 && D != 128) return fail(AMQB_ERR_UNSUPPORTED_SHAPE, "attn_prefill: head_dim must be 64 or 128");
+  cudaStream_t st = (cudaStream_t)stream;
+  rope_append_kernel<<<dim3(T, B), 256, 0, st>>>((__half*)q_f16, (const __half*)k_f16, (const __half*)v_f16,
+                                                 (__half*)k_cache, (__half*)v_cache, (const float2*)rope_cos_sin, pos0, T,
+                                                 Hq, Hkv, D, max_seq);
+  int rc = check_launch("attn_prefill (rope + append)");
+  if (rc) return rc;
+  const dim3 grid((T + kPfWarps - 1) / kPfWarps, Hq, B);
+  if (D == 128)
+    attn_prefill_kernel<128><<<grid, kPfWarps * 32, 0, st>>>((const __half*)q_f16, (const __half*)k_cache,
+                                                             (const __half*)v_cache, (__half*)out_f16, pos0, T, Hq, Hkv, max_seq);
+  else
+    attn_prefill_kernel<64><<<grid, kPfWarps * 32, 0, st>>>((const __half*)q_f16, (const __half*)k_cache,
+                                                            (const __half*)v_cache, (__half*)out_f16, pos0, T, Hq, Hkv, max_seq);
+  return check_launch("attn_prefill");
+}
+
+}  // extern "C"

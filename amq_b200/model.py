@@ -307,11 +307,67 @@ class QuantDecoder:
     def reset(self) -> None:
         self.pos.zero_()
 
+    # ---------------------------------------------------------------- prompt prefill (all prompt rows at once)
     @torch.inference_mode()
-    def generate(self, input_ids: torch.Tensor, max_new_tokens: int, use_graph: bool = True) -> torch.Tensor:
+    def prefill(self, ids: torch.Tensor) -> None:
+        """Consume ids [B, T] at cache positions pos .. pos+T-1 in ONE pass over the weights: every linear runs once
+        on the [B*T, K] activation matrix (tcgen05 GEMM for more than 16 rows, the skinny decode kernel below,
+        ops.linear_forward — the reference modules' own row-count dispatch, autogptq.py:163, ft.py:129-142), with the
+        row kernels of csrc/prefill_glue.cu in between.  Leaves the K/V cache filled and the position advanced; the
+        hidden state of the prompt rows is not kept (the last layer stops after the cache append), so the caller feeds
+        the LAST prompt token through step() to obtain the first logits.  What HF generate() does with the prompt in
+        the reference's benchmark_tps (speed.py:23-46)."""
+        if self.tp_world != 1:
+            raise RuntimeError("prefill: single-GPU decoders only (tensor-parallel runs consume the prompt through step())")
+        Lb, st = lib(), cur_stream()
+        S = self.shape
+        ids = ids.to(self.dev).to(torch.int64).contiguous()
+        B, T = ids.shape
+        assert B == self.B and T >= 1
+        pos0 = int(self.pos.item())
+        assert pos0 + T <= self.max_seq
+        M, H = B * T, self.H
+        f16 = dict(dtype=torch.float16, device=self.dev)
+        h = torch.empty(M, H, **f16)
+        x = torch.empty(M, H, **f16)
+        attn = torch.empty(M, self.q_dim, **f16)
+        act = torch.empty(M, self.I_loc, **f16)
+        check(Lb.amqb_embed(ptr(ids.reshape(-1)), ptr(self.embed), ptr(h), M, H, st), "embed")
+
+        def linear(L, name, inp, bias=None):
+            bits, w, N, K = L[name]
+            return ops.linear_forward(bits, w, inp, N, K, bias)
+
+        for li, L in enumerate(self.layers):
+            check(Lb.amqb_rmsnorm_rows(ptr(h), ptr(L["norm1"]), ctypes.c_float(S.rms_eps), ptr(x), M, H, st), "rmsnorm_rows")
+            bias = L.get("qkv_bias")
+            bq = bk = bv = None
+            if bias is not None:
+                bq, bk, bv = bias[: self.q_dim], bias[self.q_dim: self.q_dim + self.kv_dim], bias[self.q_dim + self.kv_dim:]
+            q = linear(L, "self_attn.q_proj", x, bq)
+            k = linear(L, "self_attn.k_proj", x, bk)
+            v = linear(L, "self_attn.v_proj", x, bv)
+            check(Lb.amqb_attn_prefill(ptr(q), ptr(k), ptr(v), ptr(L["k_cache"]), ptr(L["v_cache"]), ptr(attn), pos0, T, B,
+                                       self.Hq, self.Hkv, self.D, self.max_seq, ptr(self.rope), st), "attn_prefill")
+            if li == len(self.layers) - 1:
+                break                                   # only the cache rows of the last layer are needed
+            o = linear(L, "self_attn.o_proj", attn)
+            check(Lb.amqb_add_rows(ptr(h), ptr(o), M, H, st), "add_rows")
+            check(Lb.amqb_rmsnorm_rows(ptr(h), ptr(L["norm2"]), ctypes.c_float(S.rms_eps), ptr(x), M, H, st), "rmsnorm_rows")
+            g = linear(L, "mlp.gate_proj", x)
+            u = linear(L, "mlp.up_proj", x)
+            check(Lb.amqb_silu_mul_rows(ptr(g), ptr(u), ptr(act), M, self.I_loc, st), "silu_mul_rows")
+            d = linear(L, "mlp.down_proj", act)
+            check(Lb.amqb_add_rows(ptr(h), ptr(d), M, H, st), "add_rows")
+        self.pos.add_(T)
+
+    @torch.inference_mode()
+    def generate(self, input_ids: torch.Tensor, max_new_tokens: int, use_graph: bool = True,
+                 prefill: Optional[bool] = None) -> torch.Tensor:
         """Greedy generation like model.generate(do_sample=False, min=max_new_tokens) in the reference's
-        benchmark_tps (speed.py:23-46).  input_ids: [B, prompt] (host or device).  The prompt is consumed
-        token by token through the decode path (prefill through the tensor-core GEMM: amq_b200.prefill)."""
+        benchmark_tps (speed.py:23-46).  input_ids: [B, prompt] (host or device).  prefill=True (default on one
+        GPU): prompt tokens 0..P-2 go through prefill() in one pass, the last prompt token through the decode
+        step; prefill=False: the whole prompt is consumed token by token through the decode path."""
         assert input_ids.shape[0] == self.B
         prompt = input_ids.shape[1]
         assert prompt + max_new_tokens <= self.max_seq
@@ -321,7 +377,13 @@ class QuantDecoder:
         if use_graph and self.graph is None:
             self.capture()
         out = torch.empty(self.B, max_new_tokens, dtype=torch.int64, device=self.dev)
-        for t in range(prompt):
+        if prefill is None:
+            prefill = self.tp_world == 1
+        first = 0
+        if prefill and prompt > 1:
+            self.prefill(ids[:, : prompt - 1])
+            first = prompt - 1
+        for t in range(first, prompt):
             self.tokens.copy_(ids[:, t])
             fn()
         out[:, 0] = self.tokens

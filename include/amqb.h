@@ -174,6 +174,24 @@ int amqb_argmax(const float* logits, int64_t* out_ids, int M, int V, void* strea
 int amqb_argmax_advance(const float* logits, int64_t* out_ids, int64_t* next_input_ids, int* pos_dev,
                         int M, int V, void* stream);
 
+/* ---- prompt-prefill glue (csrc/prefill_glue.cu) --------------------------
+ * The row kernels between the tensor-core linears (amqb_gemm_tc) when a whole prompt is consumed at once, as the
+ * reference's benchmark does through HF generate (amq/utils/speed.py:23-46); FT counterparts:
+ * amq/kernel/ft/layernorm/layernorm.cu:25-51, amq/kernel/ft/attention/ft_attention.cpp:110-181.
+ * Rows are (sequence b, prompt position t) -> b*T + t; all matrices contiguous fp16. */
+/* out[m, :] = gamma * fp16(x[m, :] * rsqrt(mean(x[m, :]^2) + eps)) */
+int amqb_rmsnorm_rows(const void* x_f16, const void* gamma_f16, float eps, void* out_f16, int M, int H, void* stream);
+/* out = fp16(silu(gate)) * up, [M, I] each */
+int amqb_silu_mul_rows(const void* gate_f16, const void* up_f16, void* out_f16, int M, int I, void* stream);
+/* h += y (fp32 add, one rounding), [M, H] */
+int amqb_add_rows(void* h_f16, const void* y_f16, int M, int H, void* stream);
+/* RoPE on q [B*T, Hq*D] (in place) and k [B*T, Hkv*D] for cache positions pos0 .. pos0+T-1, append k, v to the
+ * static cache ([B, Hkv, max_seq, D], as amqb_attn_decode), causal attention of every prompt row over cache
+ * positions [0, pos0 + t].  out: fp16 [B*T, Hq*D].  rope_cos_sin: table from amqb_rope_table (required). */
+int amqb_attn_prefill(void* q_f16, const void* k_f16, const void* v_f16, void* k_cache, void* v_cache, void* out_f16,
+                      int pos0, int T, int B, int Hq, int Hkv, int D, int max_seq, const float* rope_cos_sin,
+                      void* stream);
+
 /* ---- persistent decode kernel: every decoder layer of one batch-1 token in ONE launch --------
  * Replaces the chain of ~5 dependent launches per layer that amq_speed_benchmark.py times
  * (amq/utils/speed.py:23-46 over the modules of hqq/backends/{autogptq,ft}.py): one CTA per SM stays

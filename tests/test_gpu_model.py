@@ -167,3 +167,67 @@ def test_persistent_decode_kernel_matches_chain(family):
         assert rel < 5e-3, (family, pos, float(rel))
         if ref is not None:
             assert (mp.logits - ref).abs().max() / ref.abs().max() < 2e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("family,batch,prompt", [("llama", 2, 9), ("llama", 1, 42), ("qwen2", 2, 26), ("gqa128", 1, 70)])
+def test_prefill_matches_token_by_token(family, batch, prompt):
+    """QuantDecoder.prefill (one pass over the weights for all prompt rows: tcgen05 GEMM above 16 rows, skinny decode
+    kernel below, row kernels of csrc/prefill_glue.cu in between) leaves the same K/V cache as the same prompt
+    consumed token by token through the decode step, and the next decode step gives the same logits, to the fp16
+    rounding of the linears.  Also in two chunks (pos0 > 0)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from amq_b200.arch import ModelShape, LINEARS
+    from amq_b200.model import QuantDecoder
+    if family == "llama":
+        shape = ModelShape("tiny-llama", 256, 512, 4, 4, 3, 512, head_dim=64)
+    elif family == "qwen2":
+        shape = ModelShape("tiny-qwen2", 256, 512, 4, 2, 2, 512, head_dim=64, rope_theta=1e6, rms_eps=1e-6, qkv_bias=True)
+    else:
+        shape = ModelShape("tiny-gqa", 512, 1408, 4, 2, 2, 512, head_dim=128)
+    rs = np.random.RandomState(2)
+    arch = {n: rs.choice([2, 3, 4], size=shape.n_block).tolist() for n in LINEARS}
+    S = 96
+    m = QuantDecoder(shape, arch, batch=batch, max_seq=S, seed=4)
+    ids = torch.randint(0, shape.vocab, (batch, prompt), device=m.dev)
+    P = prompt - 1
+
+    def last_step():
+        m.tokens.copy_(ids[:, P]); m.step(); torch.cuda.synchronize()
+        return m.logits.clone()
+
+    def caches():
+        return [(L["k_cache"][:, :, :P].float().clone(), L["v_cache"][:, :, :P].float().clone()) for L in m.layers]
+
+    def wipe():
+        for L in m.layers:
+            L["k_cache"].zero_(); L["v_cache"].zero_()
+        m.reset()
+
+    wipe()
+    for t in range(P):
+        m.tokens.copy_(ids[:, t]); m.step()
+    want_c, want_l = caches(), last_step()
+
+    def compare(tag):
+        assert int(m.pos.item()) == P, tag
+        for li, ((k0, v0), (k1, v1)) in enumerate(zip(want_c, caches())):
+            assert (k0 - k1).abs().max() / k0.abs().max() < 1e-2, (tag, family, li, "k")
+            assert (v0 - v1).abs().max() / v0.abs().max() < 1e-2, (tag, family, li, "v")
+        got_l = last_step()
+        assert (got_l - want_l).abs().max() / want_l.abs().max() < 2e-2, (tag, family)
+
+    wipe()
+    m.prefill(ids[:, :P])
+    compare("one pass")
+    wipe()
+    cut = P // 3 + 1                                  # second chunk attends to cache rows written by the first
+    m.prefill(ids[:, :cut]); m.prefill(ids[:, cut:P])
+    compare("two chunks")
+    # generate(): prefill and token-by-token prompts give the same first token when its margin is clear
+    a = m.generate(ids, 3, prefill=True)
+    b = m.generate(ids, 3, prefill=False)
+    top2 = want_l.topk(2, dim=-1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 4e-2 * want_l.abs().max()
+    assert torch.equal(a[clear, 0], b[clear, 0])
