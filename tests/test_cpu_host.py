@@ -175,3 +175,30 @@ def test_gloo_world2_row_parallel(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+def test_speed_benchmark_cli_mirrors_reference_flags():
+    """amq_speed_benchmark.py keeps the reference's command line (amq/amq_speed_benchmark.py:103-125: names, types,
+    defaults) and refuses to run without a GPU; benchmark_speed keeps the reference's signature (speed.py:130)."""
+    import inspect
+    sys.path.insert(0, ROOT)
+    import amq_speed_benchmark as cli
+    from amq_b200.utils import speed
+    p = cli.build_parser()
+    a = p.parse_args([])
+    ref_defaults = {"model_path": "meta-llama", "model_name": "Llama-2-7b-hf", "save_path": "/SSD/hqq", "use_ft": False,
+                    "batch_size": 1, "seq_length": 64, "gen_length": 128, "tps": False, "gemm": False, "gemv": False,
+                    "ttft": False, "memory": False, "peak_memory": False, "target_bits": 4, "arch_path": None,
+                    "file_name": None}
+    for k, v in ref_defaults.items():
+        assert getattr(a, k) == v, k
+    a = p.parse_args(["--tps", "--gemv", "--target_bits", "3", "--arch_path", "x.stats", "--batch_size", "4"])
+    assert a.tps and a.gemv and a.target_bits == 3.0 and a.arch_path == "x.stats" and a.batch_size == 4
+    sig = inspect.signature(speed.benchmark_speed)
+    assert list(sig.parameters) == ["model", "tokenizer", "use_ft", "iteration", "sizes", "mode", "get_peak_memory"]
+    assert sig.parameters["sizes"].default == (1, 128, 128) and sig.parameters["mode"].default == "TPS"
+    with pytest.raises(AssertionError):
+        speed.benchmark_speed(None, mode="latency")
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            cli.main(["--tps"])

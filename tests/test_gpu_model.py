@@ -231,3 +231,39 @@ def test_prefill_matches_token_by_token(family, batch, prompt):
     top2 = want_l.topk(2, dim=-1).values
     clear = (top2[:, 0] - top2[:, 1]) > 4e-2 * want_l.abs().max()
     assert torch.equal(a[clear, 0], b[clear, 0])
+
+
+@pytest.mark.gpu
+def test_speed_benchmark_protocol(tmp_path, monkeypatch):
+    """benchmark_speed (the reference's protocol, amq/utils/speed.py:130-255) in all four modes on a tiny decoder, and
+    the amq_speed_benchmark.py command line on one block of Llama-2-7B with a searched-arch file."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import json
+    import os
+    import sys
+    from amq_b200.arch import MODELS, ModelShape, LINEARS, make_stats_file
+    from amq_b200.model import QuantDecoder
+    from amq_b200.utils.speed import benchmark_speed
+    shape = ModelShape("tiny-llama", 256, 512, 4, 4, 2, 512, head_dim=64)
+    arch = {n: [2, 4] for n in LINEARS}
+    m = QuantDecoder(shape, arch, batch=2, max_seq=64, seed=5)
+    for mode, it in (("TPS", 2), ("GeMV", 1), ("GeMM", 3), ("TTFT", 3)):
+        d = benchmark_speed(m, None, iteration=it, sizes=(2, 20, 8), mode=mode, get_peak_memory=(mode == "TPS"))
+        assert set(d) == ({mode.lower(), "peak_memory"} if mode == "TPS" else {mode.lower()})
+        assert d[mode.lower()]["2.20.8"] > 0
+    with pytest.raises(ValueError):
+        benchmark_speed(m, None, sizes=(1, 20, 8), mode="TPS")          # batch mismatch
+    with pytest.raises(ValueError):
+        benchmark_speed(m, None, sizes=(2, 60, 8), mode="TPS")          # beyond the static KV cache
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import amq_speed_benchmark as cli
+    stats = str(tmp_path / "iter_1.stats")
+    make_stats_file(stats, MODELS["Llama-2-7b-hf"], 3.0, n=4)
+    monkeypatch.chdir(tmp_path)
+    res = cli.main(["--model_name", "Llama-2-7b-hf", "--n_block", "1", "--target_bits", "3", "--arch_path", stats, "--tps",
+                    "--gemv", "--memory", "--seq_length", "24", "--gen_length", "8", "--file_name", "out.json"])
+    assert res["3.0bit"]["tps"]["1.24.8"] > 0 and res["3.0bit"]["gemv"]["1.24.8"] > 0 and res["3.0bit"]["memory"] > 0.5
+    saved = json.load(open(tmp_path / "benchmark" / "outputs" / "out.json"))
+    assert saved["args"]["target_bits"] == 3.0 and "3.0bit" in saved
