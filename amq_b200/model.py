@@ -309,23 +309,53 @@ class QuantDecoder:
 
     # ---------------------------------------------------------------- prompt prefill (all prompt rows at once)
     @torch.inference_mode()
-    def prefill(self, ids: torch.Tensor) -> None:
+    def prefill(self, ids: torch.Tensor, use_graph: bool = True) -> None:
         """Consume ids [B, T] at cache positions pos .. pos+T-1 in ONE pass over the weights: every linear runs once
         on the [B*T, K] activation matrix (tcgen05 GEMM for more than 16 rows, the skinny decode kernel below,
         ops.linear_forward — the reference modules' own row-count dispatch, autogptq.py:163, ft.py:129-142), with the
         row kernels of csrc/prefill_glue.cu in between.  Leaves the K/V cache filled and the position advanced; the
         hidden state of the prompt rows is not kept (the last layer stops after the cache append), so the caller feeds
         the LAST prompt token through step() to obtain the first logits.  What HF generate() does with the prompt in
-        the reference's benchmark_tps (speed.py:23-46)."""
+        the reference's benchmark_tps (speed.py:23-46).  The ~16 launches per layer are captured in a CUDA graph per
+        (T, start position) and replayed (a 64-token prompt is otherwise bound by the host's launch rate)."""
         if self.tp_world != 1:
             raise RuntimeError("prefill: single-GPU decoders only (tensor-parallel runs consume the prompt through step())")
-        Lb, st = lib(), cur_stream()
-        S = self.shape
         ids = ids.to(self.dev).to(torch.int64).contiguous()
         B, T = ids.shape
         assert B == self.B and T >= 1
         pos0 = int(self.pos.item())
         assert pos0 + T <= self.max_seq
+        if not use_graph:
+            self._prefill_launches(ids, pos0)
+            self.pos.add_(T)
+            return
+        if not hasattr(self, "_pf_graphs"):
+            self._pf_graphs = {}
+        key = (T, pos0)
+        if key not in self._pf_graphs:
+            if len(self._pf_graphs) >= 4:                     # each graph pins its activation pool: keep a few shapes
+                self._pf_graphs.pop(next(iter(self._pf_graphs)))
+            static_ids = ids.clone()
+            cur = torch.cuda.current_stream(self.dev)
+            s = torch.cuda.Stream(device=self.dev)
+            s.wait_stream(cur)
+            with torch.cuda.stream(s):
+                self._prefill_launches(static_ids, pos0)       # warm-up outside capture (workspaces, attributes)
+                s.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=s):
+                    self._prefill_launches(static_ids, pos0)
+            cur.wait_stream(s)
+            self._pf_graphs[key] = (g, static_ids)
+        g, static_ids = self._pf_graphs[key]
+        static_ids.copy_(ids)
+        g.replay()
+        self.pos.add_(T)
+
+    def _prefill_launches(self, ids: torch.Tensor, pos0: int) -> None:
+        Lb, st = lib(), cur_stream()
+        S = self.shape
+        B, T = ids.shape
         M, H = B * T, self.H
         f16 = dict(dtype=torch.float16, device=self.dev)
         h = torch.empty(M, H, **f16)
@@ -359,7 +389,6 @@ class QuantDecoder:
             check(Lb.amqb_silu_mul_rows(ptr(g), ptr(u), ptr(act), M, self.I_loc, st), "silu_mul_rows")
             d = linear(L, "mlp.down_proj", act)
             check(Lb.amqb_add_rows(ptr(h), ptr(d), M, H, st), "add_rows")
-        self.pos.add_(T)
 
     @torch.inference_mode()
     def generate(self, input_ids: torch.Tensor, max_new_tokens: int, use_graph: bool = True,

@@ -225,6 +225,12 @@ def test_prefill_matches_token_by_token(family, batch, prompt):
     cut = P // 3 + 1                                  # second chunk attends to cache rows written by the first
     m.prefill(ids[:, :cut]); m.prefill(ids[:, cut:P])
     compare("two chunks")
+    wipe()
+    m.prefill(ids[:, :P], use_graph=False)            # plain launches (the default replays a captured graph)
+    compare("eager")
+    wipe()
+    m.prefill(ids[:, :P])                             # replay of the graph captured above, after the cache was wiped
+    compare("graph replay")
     # generate(): prefill and token-by-token prompts give the same first token when its margin is clear
     a = m.generate(ids, 3, prefill=True)
     b = m.generate(ids, 3, prefill=False)
@@ -267,3 +273,74 @@ def test_speed_benchmark_protocol(tmp_path, monkeypatch):
     assert res["3.0bit"]["tps"]["1.24.8"] > 0 and res["3.0bit"]["gemv"]["1.24.8"] > 0 and res["3.0bit"]["memory"] > 0.5
     saved = json.load(open(tmp_path / "benchmark" / "outputs" / "out.json"))
     assert saved["args"]["target_bits"] == 3.0 and "3.0bit" in saved
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("D,Hq,Hkv,B,T,pos0", [(64, 4, 2, 2, 19, 0), (128, 8, 2, 1, 45, 7), (128, 4, 4, 3, 8, 33)])
+def test_prefill_row_kernels_against_torch(D, Hq, Hkv, B, T, pos0):
+    """Each kernel of csrc/prefill_glue.cu against a plain PyTorch fp32 statement of the same op: row RMSNorm, SiLU*up,
+    residual add, RoPE (q in place, k into the cache), V append, causal attention over [earlier context | this block]."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import ctypes
+    from amq_b200._lib import check, cur_stream, lib, ptr
+    dev, S, theta = "cuda:0", 64, 10000.0
+    torch.cuda.set_device(0)
+    g = torch.Generator(device=dev).manual_seed(D + T)
+    M, H = B * T, Hq * D
+    L, st = lib(), cur_stream()
+
+    def rnd(*shape):
+        return torch.randn(*shape, device=dev, generator=g).half()
+
+    def close(got, ref, tol):
+        return float((got.float() - ref).abs().max()) <= tol * float(ref.abs().max())
+
+    x, gamma = rnd(M, H), (1 + 0.1 * torch.randn(H, device=dev, generator=g)).half()
+    out = torch.empty_like(x)
+    check(L.amqb_rmsnorm_rows(ptr(x), ptr(gamma), ctypes.c_float(1e-5), ptr(out), M, H, st), "rmsnorm_rows")
+    xf = x.float()
+    ref = gamma.float() * (xf * torch.rsqrt((xf * xf).mean(-1, keepdim=True) + 1e-5)).half().float()
+    assert close(out, ref, 1e-3)
+    gate, up = rnd(M, H), rnd(M, H)
+    check(L.amqb_silu_mul_rows(ptr(gate), ptr(up), ptr(out), M, H, st), "silu_mul_rows")
+    assert close(out, torch.nn.functional.silu(gate.float()).half().float() * up.float(), 1e-3)
+    h0, y = rnd(M, H), rnd(M, H)
+    h = h0.clone()
+    check(L.amqb_add_rows(ptr(h), ptr(y), M, H, st), "add_rows")
+    assert torch.equal(h, (h0.float() + y.float()).half())
+
+    rope = torch.empty(S, D // 2, 2, dtype=torch.float32, device=dev)
+    check(L.amqb_rope_table(ptr(rope), S, D, ctypes.c_float(theta), st), "rope_table")
+    q, k, v = rnd(M, Hq * D), rnd(M, Hkv * D), rnd(M, Hkv * D)
+    kc = torch.zeros(B, Hkv, S, D, device=dev, dtype=torch.float16)
+    vc = torch.zeros(B, Hkv, S, D, device=dev, dtype=torch.float16)
+    kc[:, :, :pos0], vc[:, :, :pos0] = rnd(B, Hkv, pos0, D), rnd(B, Hkv, pos0, D)        # earlier context
+    q0, kc0, vc0 = q.clone(), kc.clone(), vc.clone()
+    att = torch.empty(M, Hq * D, device=dev, dtype=torch.float16)
+    check(L.amqb_attn_prefill(ptr(q), ptr(k), ptr(v), ptr(kc), ptr(vc), ptr(att), pos0, T, B, Hq, Hkv, D, S, ptr(rope), st),
+          "attn_prefill")
+    inv = theta ** (-torch.arange(0, D // 2, device=dev).float() * 2 / D)
+    ang = torch.arange(pos0, pos0 + T, device=dev).float()[:, None] * inv[None]
+    cos = torch.cat([ang.cos(), ang.cos()], -1).half().float()[None, :, None, :]
+    sin = torch.cat([ang.sin(), ang.sin()], -1).half().float()[None, :, None, :]
+
+    def rot(t):                   # [B, T, heads, D], HF rotate_half
+        t1, t2 = t[..., : D // 2], t[..., D // 2:]
+        return (t * cos + torch.cat([-t2, t1], -1) * sin).half().float()
+
+    qr, kr = rot(q0.float().view(B, T, Hq, D)), rot(k.float().view(B, T, Hkv, D))
+    assert close(q.view(B, T, Hq, D), qr, 2e-3)
+    Kf, Vf = kc0.float(), vc0.float()
+    Kf[:, :, pos0:pos0 + T] = kr.permute(0, 2, 1, 3)
+    Vf[:, :, pos0:pos0 + T] = v.float().view(B, T, Hkv, D).permute(0, 2, 1, 3)
+    assert close(kc, Kf, 2e-3) and torch.equal(vc.float(), Vf)
+    assert torch.equal(kc[:, :, pos0 + T:], kc0[:, :, pos0 + T:])                          # nothing written past the block
+    # attention reference from the kernel's own (fp16) rotated q / cache contents: isolates the softmax . V part
+    Kr = kc.float()[:, :, : pos0 + T].repeat_interleave(Hq // Hkv, dim=1)
+    Vr = vc.float()[:, :, : pos0 + T].repeat_interleave(Hq // Hkv, dim=1)
+    sc = torch.einsum("bthd,bhsd->bhts", q.float().view(B, T, Hq, D), Kr) / D ** 0.5
+    vis = torch.arange(pos0 + T, device=dev)[None, :] <= (pos0 + torch.arange(T, device=dev))[:, None]
+    sc = sc.masked_fill(~vis[None, None], float("-inf"))
+    o = torch.einsum("bhts,bhsd->bthd", torch.softmax(sc, -1), Vr).reshape(M, Hq * D)
+    assert close(att, o, 2e-3)
