@@ -237,6 +237,223 @@ attn_decode_kernel(const __half* __restrict__ qkv, __half* __restrict__ kc, __ha
   }
 }
 
+// Long-context variant of attn_decode_kernel above (which stays byte for byte what the short-context graph launches: folding
+// both into one kernel cost the batch-1 step 0.65 us per layer, measured on the same box).
+// SPLIT = false: one CTA per (head, sequence), compile-time position stride.
+// SPLIT = true (long contexts, pos >= split_min_pos): the gridDim.z CTAs of a head share its cached positions (CTA sp
+// takes the "virtual warps" 16 sp .. 16 sp + 15 of 16 ns), leave (max, denominator, unnormalised sum) in split_ws and
+// the last one to arrive merges.
+template <int D, bool SPLIT>
+__device__ __forceinline__ void attn_decode_body(const __half* __restrict__ qkv, __half* __restrict__ kc,
+                                                 __half* __restrict__ vc, __half* __restrict__ out,
+                                                 const int* __restrict__ pos_dev, int Hq, int Hkv, int max_seq, float theta,
+                                                 const float* __restrict__ rope_tab, float* split_ws, const int ns) {
+  constexpr int EPL = D / 32;     // elements per lane
+  constexpr int UNR = 8;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int rep = Hq / Hkv, hk = h / rep;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sp = SPLIT ? (int)blockIdx.z : 0;
+  const int vw = SPLIT ? sp * kAttnWarps + warp : warp;
+  const int vstride = SPLIT ? ns * kAttnWarps : kAttnWarps;
+  // Everything below up to griddepcontrol.wait reads only data that no kernel of this decode step writes before this
+  // one (the position counter, the RoPE table, the cache rows of EARLIER positions), so it overlaps the q|k|v GEMV's
+  // drain: after the wait only q, k, v of this step are loaded.
+  const int pos = pos_dev[0];
+  const int ld = (Hq + 2 * Hkv) * D;
+  const __half* qp = qkv + (size_t)b * ld + h * D;
+  const __half* kp = qkv + (size_t)b * ld + (Hq + hk) * D;
+  const __half* vp = qkv + (size_t)b * ld + (Hq + Hkv + hk) * D;
+  __half* kcb = kc + ((size_t)b * Hkv + hk) * max_seq * D;
+  __half* vcb = vc + ((size_t)b * Hkv + hk) * max_seq * D;
+  float cs[EPL], sn[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) {
+    const int ih = (EPL * lane + e) % (D / 2);
+    if (rope_tab) {                       // [max_seq][D/2] float2(cos, sin), built once by amqb_rope_table
+      const float2 t2 = reinterpret_cast<const float2*>(rope_tab)[(size_t)pos * (D / 2) + ih];
+      cs[e] = t2.x; sn[e] = t2.y;
+    } else {
+      const float inv = __powf(theta, -2.f * (float)ih / (float)D);
+      sincosf((float)pos * inv, &sn[e], &cs[e]);
+    }
+    // fp16-rounded cos / sin as HF (LlamaRotaryEmbedding casts to the activation dtype)
+    cs[e] = __half2float(__float2half_rn(cs[e]));
+    sn[e] = __half2float(__float2half_rn(sn[e]));
+  }
+  // first pass of cached rows (positions vw, vw + vstride, ... < pos), raw fp16 bits: 8 rows in flight per warp
+  uint2 kraw[UNR][EPL == 4 ? 1 : EPL], vraw[UNR][EPL == 4 ? 1 : EPL];
+#pragma unroll
+  for (int u = 0; u < UNR; ++u) {
+    const int j = vw + vstride * u;
+    if (EPL == 4) {
+      kraw[u][0] = make_uint2(0u, 0u); vraw[u][0] = make_uint2(0u, 0u);
+      if (j < pos) {
+        kraw[u][0] = *reinterpret_cast<const uint2*>(kcb + (size_t)j * D + 4 * lane);
+        vraw[u][0] = *reinterpret_cast<const uint2*>(vcb + (size_t)j * D + 4 * lane);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        kraw[u][e].x = 0u; vraw[u][e].x = 0u;
+        if (j < pos) {
+          kraw[u][e].x = __half_as_ushort(kcb[(size_t)j * D + EPL * lane + e]);
+          vraw[u][e].x = __half_as_ushort(vcb[(size_t)j * D + EPL * lane + e]);
+        }
+      }
+    }
+  }
+  pdl_wait();
+  // RoPE, HF rotate_half convention: pair (i, i + D/2), angle pos * theta^(-2i/D)
+  float q[EPL], kn[EPL], vn[EPL];
+  {
+    // the lane's EPL elements and their rotate_half partners (i +- D/2) are both contiguous: five vector loads in flight
+    const int i0 = EPL * lane, ip0 = i0 < D / 2 ? i0 + D / 2 : i0 - D / 2;
+    const float sgn = i0 < D / 2 ? -1.f : 1.f;
+    float qa[EPL], qb[EPL], ka[EPL], kb[EPL];
+    ld_dep<EPL>(qp + i0, qa); ld_dep<EPL>(qp + ip0, qb);
+    ld_dep<EPL>(kp + i0, ka); ld_dep<EPL>(kp + ip0, kb);
+    ld_dep<EPL>(vp + i0, vn);
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      q[e] = __half2float(__float2half_rn(qa[e] * cs[e] + sgn * qb[e] * sn[e]));
+      kn[e] = __half2float(__float2half_rn(ka[e] * cs[e] + sgn * kb[e] * sn[e]));
+    }
+  }
+  if (h % rep == 0 && warp == 0 && sp == 0) {
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      kcb[(size_t)pos * D + EPL * lane + e] = __float2half_rn(kn[e]);
+      vcb[(size_t)pos * D + EPL * lane + e] = __float2half_rn(vn[e]);
+    }
+  }
+  const float scale = rsqrtf((float)D);
+  float mx = -INFINITY, den = 0.f, acc[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
+  // positions j = vw, vw + vstride, ... ; eight at a time so the loads and the butterfly reductions of
+  // independent positions overlap (the loop is latency-bound, not bandwidth-bound)
+  for (int j0 = vw; j0 <= pos; j0 += vstride * UNR) {
+    float kj[UNR][EPL], vj[UNR][EPL], sc[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int j = j0 + vstride * u;
+      if (j < pos) {
+        if (EPL == 4) {
+          uint2 kk, vv;
+          if (j0 == vw) { kk = kraw[u][0]; vv = vraw[u][0]; }       // prefetched before the wait
+          else {
+            kk = *reinterpret_cast<const uint2*>(kcb + (size_t)j * D + 4 * lane);
+            vv = *reinterpret_cast<const uint2*>(vcb + (size_t)j * D + 4 * lane);
+          }
+          const float2 k0 = __half22float2(*reinterpret_cast<const __half2*>(&kk.x)), k1 = __half22float2(*reinterpret_cast<const __half2*>(&kk.y));
+          const float2 v0 = __half22float2(*reinterpret_cast<const __half2*>(&vv.x)), v1 = __half22float2(*reinterpret_cast<const __half2*>(&vv.y));
+          kj[u][0] = k0.x; kj[u][1] = k0.y; kj[u][EPL - 2] = k1.x; kj[u][EPL - 1] = k1.y;
+          vj[u][0] = v0.x; vj[u][1] = v0.y; vj[u][EPL - 2] = v1.x; vj[u][EPL - 1] = v1.y;
+        } else {
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) {
+            if (j0 == vw) {
+              kj[u][e] = __half2float(__ushort_as_half((unsigned short)kraw[u][e].x));
+              vj[u][e] = __half2float(__ushort_as_half((unsigned short)vraw[u][e].x));
+            } else {
+              kj[u][e] = __half2float(kcb[(size_t)j * D + EPL * lane + e]);
+              vj[u][e] = __half2float(vcb[(size_t)j * D + EPL * lane + e]);
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) { kj[u][e] = kn[e]; vj[u][e] = vn[e]; }   // j == pos: this step's k / v
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      float s = 0.f;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) s += q[e] * kj[u][e];
+      sc[u] = s;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], o);
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (j0 + vstride * u <= pos) {
+        const float s = sc[u] * scale;
+        const float nm = fmaxf(mx, s);
+        const float corr = __expf(mx - nm), p = __expf(s - nm);
+        den = den * corr + p;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) acc[e] = acc[e] * corr + p * vj[u][e];
+        mx = nm;
+      }
+    }
+  }
+  __shared__ float s_m[kAttnWarps], s_d[kAttnWarps], s_acc[kAttnWarps][D];
+  if (lane == 0) { s_m[warp] = mx; s_d[warp] = den; }
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) s_acc[warp][EPL * lane + e] = acc[e];
+  __syncthreads();
+  float o = 0.f, gd = 0.f, gm = -INFINITY;
+  if (threadIdx.x < D) {                     // one thread per head dim merges the 16 warps' partials
+    const int i = threadIdx.x;
+#pragma unroll
+    for (int w = 0; w < kAttnWarps; ++w) gm = fmaxf(gm, s_m[w]);
+#pragma unroll
+    for (int w = 0; w < kAttnWarps; ++w) {
+      const float wt = (s_m[w] == -INFINITY) ? 0.f : __expf(s_m[w] - gm);
+      o += s_acc[w][i] * wt;
+      gd += s_d[w] * wt;
+    }
+    if (!SPLIT) out[(size_t)b * Hq * D + h * D + i] = __float2half_rn(o / gd);
+  }
+  if (!SPLIT) return;
+  // split_ws: [B * Hq] arrival counters (zero between launches), then per (b, h, sp) D + 2 floats: sum[D], max, denominator
+  __shared__ int s_last;
+  int* counter = reinterpret_cast<int*>(split_ws) + (b * Hq + h);
+  float* part = split_ws + (((size_t)gridDim.y * Hq + 63) & ~size_t(63)) + ((size_t)(b * Hq + h) * gridDim.z) * (D + 2);
+  if (threadIdx.x < D) {
+    float* mine = part + (size_t)sp * (D + 2);
+    mine[threadIdx.x] = o;
+    if (threadIdx.x == 0) { mine[D] = gm; mine[D + 1] = gd; }
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(counter, 1) == ns - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < D) {
+    const int i = threadIdx.x;
+    float m_all = -INFINITY;
+    for (int c = 0; c < ns; ++c) m_all = fmaxf(m_all, __ldcg(part + (size_t)c * (D + 2) + D));
+    float oo = 0.f, dd = 0.f;
+    for (int c = 0; c < ns; ++c) {
+      const float mc = __ldcg(part + (size_t)c * (D + 2) + D);
+      const float wt = (mc == -INFINITY) ? 0.f : __expf(mc - m_all);
+      oo += __ldcg(part + (size_t)c * (D + 2) + i) * wt;
+      dd += __ldcg(part + (size_t)c * (D + 2) + D + 1) * wt;
+    }
+    out[(size_t)b * Hq * D + h * D + i] = __float2half_rn(oo / dd);
+    if (i == 0) *counter = 0;                // ready for the next launch (graph replay)
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kAttnWarps * 32)
+attn_decode_split_kernel(const __half* __restrict__ qkv, __half* __restrict__ kc, __half* __restrict__ vc,
+                   __half* __restrict__ out, const int* __restrict__ pos_dev, int Hq, int Hkv, int max_seq,
+                   float theta, const float* __restrict__ rope_tab, float* split_ws, int split_min_pos) {
+  pdl_launch_dependents();
+  // short contexts: CTAs z > 0 leave at once and CTA 0 runs the single-CTA body unchanged
+  const int ns = (gridDim.z > 1 && pos_dev[0] >= split_min_pos) ? (int)gridDim.z : 1;
+  if ((int)blockIdx.z >= ns) return;
+  if (ns == 1) attn_decode_body<D, false>(qkv, kc, vc, out, pos_dev, Hq, Hkv, max_seq, theta, rope_tab, split_ws, 1);
+  else attn_decode_body<D, true>(qkv, kc, vc, out, pos_dev, Hq, Hkv, max_seq, theta, rope_tab, split_ws, ns);
+}
+
 __global__ void rope_table_kernel(float2* __restrict__ tab, int max_seq, int D, float theta) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= max_seq * (D / 2)) return;
@@ -480,6 +697,33 @@ int amqb_attn_decode(const void* qkv, void* k_cache, void* v_cache, void* out, c
     return launch(attn_decode_kernel<64>, dim3(Hq, B), dim3(kAttnWarps * 32), 0, st, "attn_decode", (const __half*)qkv,
                   (__half*)k_cache, (__half*)v_cache, (__half*)out, pos_dev, Hq, Hkv, max_seq, rope_theta, rope_cos_sin);
   return fail(AMQB_ERR_UNSUPPORTED_SHAPE, "attn_decode: head_dim must be 64 or 128");
+}
+
+size_t amqb_attn_split_workspace_bytes(int B, int Hq, int D, int splits) {
+  if (B < 1 || Hq < 1 || D < 1 || splits < 1) return 0;
+  return ((((size_t)B * Hq + 63) & ~size_t(63)) + (size_t)B * Hq * splits * (D + 2)) * sizeof(float);
+}
+
+int amqb_attn_decode_split(const void* qkv, void* k_cache, void* v_cache, void* out, const int* pos_dev, int B, int Hq,
+                           int Hkv, int D, int max_seq, float rope_theta, const float* rope_cos_sin, int splits,
+                           int split_min_pos, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!qkv || !k_cache || !v_cache || !out || !pos_dev || B < 1 || Hq < 1 || Hkv < 1 || Hq % Hkv || splits < 1 ||
+      splits > 16 || split_min_pos < 1)
+    return fail(AMQB_ERR_BAD_ARG, "attn_decode_split: bad argument");
+  if (splits > 1 && (!workspace || ((uintptr_t)workspace & 15) || workspace_bytes < amqb_attn_split_workspace_bytes(B, Hq, D, splits)))
+    return fail(AMQB_ERR_WORKSPACE, "attn_decode_split: needs a zeroed workspace of amqb_attn_split_workspace_bytes()");
+  if (splits == 1)          // the single-CTA kernel itself
+    return amqb_attn_decode(qkv, k_cache, v_cache, out, pos_dev, B, Hq, Hkv, D, max_seq, rope_theta, rope_cos_sin, stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (D == 128)
+    return launch(attn_decode_split_kernel<128>, dim3(Hq, B, splits), dim3(kAttnWarps * 32), 0, st, "attn_decode_split",
+                  (const __half*)qkv, (__half*)k_cache, (__half*)v_cache, (__half*)out, pos_dev, Hq, Hkv, max_seq, rope_theta,
+                  rope_cos_sin, (float*)workspace, split_min_pos);
+  if (D == 64)
+    return launch(attn_decode_split_kernel<64>, dim3(Hq, B, splits), dim3(kAttnWarps * 32), 0, st, "attn_decode_split",
+                  (const __half*)qkv, (__half*)k_cache, (__half*)v_cache, (__half*)out, pos_dev, Hq, Hkv, max_seq, rope_theta,
+                  rope_cos_sin, (float*)workspace, split_min_pos);
+  return fail(AMQB_ERR_UNSUPPORTED_SHAPE, "attn_decode_split: head_dim must be 64 or 128");
 }
 
 int amqb_lm_head(const void* W_f16, const void* x, const void* gamma, float eps, float* logits, int M, int V, int K,

@@ -106,6 +106,19 @@ class QuantDecoder:
         self.rope = torch.empty(max_seq, self.D // 2, 2, dtype=torch.float32, device=self.dev)
         check(lib().amqb_rope_table(ptr(self.rope), max_seq, self.D, ctypes.c_float(shape.rope_theta), cur_stream()), "rope_table")
         self.ws = ops.workspace(self.dev, 4 * shape.inter, max(shape.inter, shape.hidden), batch)
+        # long contexts: the cached positions of a head are shared by several CTAs (amqb_attn_decode_split) when one CTA
+        # per (head, sequence) would leave most of the chip idle; below ATTN_SPLIT_MIN_POS it is the single-CTA kernel
+        sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
+        self.attn_splits = max(1, min(4, sms // max(1, self.Hq * batch))) if tp_world == 1 else 1   # TP: validated path only
+        self.attn_split_min_pos = int(os.environ.get("AMQB_ATTN_SPLIT_MIN_POS", "256"))
+        self.attn_ws = torch.zeros(max(256, int(lib().amqb_attn_split_workspace_bytes(batch, self.Hq, self.D, self.attn_splits))),
+                                   dtype=torch.uint8, device=self.dev)
+        # Two captured steps: the short-context one launches one CTA per head (the extra CTAs of the split grid, although
+        # they leave at once below the threshold, were measured to cost ~0.75 us per layer); step() picks by a host-side
+        # mirror of the position.  Either graph is correct at any position — the mirror only selects the faster one.
+        self._cur_splits = 1
+        self._pos_h = 0
+        self.graph_long: Optional[torch.cuda.CUDAGraph] = None
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.allreduce = None          # set by amq_b200.tp for tensor-parallel runs
         self.launches_per_step = 0
@@ -228,9 +241,10 @@ class QuantDecoder:
         for P in (() if self.persistent else self._plan):
             L = P["L"]
             self._gemv(P["qkv"], 3)
-            check(Lb.amqb_attn_decode(ptr(self.qkv), ptr(L["k_cache"]), ptr(L["v_cache"]), ptr(self.attn), ptr(self.pos),
-                                      self.B, self.Hq, self.Hkv, self.D, self.max_seq, ctypes.c_float(S.rope_theta), ptr(self.rope), st),
-                  "attn_decode")
+            check(Lb.amqb_attn_decode_split(ptr(self.qkv), ptr(L["k_cache"]), ptr(L["v_cache"]), ptr(self.attn), ptr(self.pos),
+                                            self.B, self.Hq, self.Hkv, self.D, self.max_seq, ctypes.c_float(S.rope_theta),
+                                            ptr(self.rope), self._cur_splits, self.attn_split_min_pos, ptr(self.attn_ws),
+                                            ctypes.c_size_t(self.attn_ws.numel()), st), "attn_decode_split")
             self.launches_per_step += 1
             self._gemv(P["o"], 1)
             if self.allreduce is not None:
@@ -248,8 +262,12 @@ class QuantDecoder:
               "argmax_advance")
         self.launches_per_step += 2
 
-    def _capture(self, host_in: Optional[torch.Tensor] = None, host_out: Optional[torch.Tensor] = None):
+    def _long_context(self) -> bool:
+        return self.attn_splits > 1 and not self.persistent and self._pos_h >= self.attn_split_min_pos
+
+    def _capture(self, host_in: Optional[torch.Tensor] = None, host_out: Optional[torch.Tensor] = None, splits: int = 1):
         lib().amqb_set_pdl(int(self.pdl))
+        self._cur_splits = splits
         s = torch.cuda.Stream(device=self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(s):
@@ -268,18 +286,22 @@ class QuantDecoder:
                     host_out.copy_(self.tokens, non_blocking=True)     # memcpy node: device -> pinned host
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
+        self._cur_splits = 1
         return g
 
     def capture(self) -> None:
         """Capture one decode step (+ feeding the argmax back as the next input, + position advance)
-        into a CUDA graph."""
+        into a CUDA graph; when the cache can grow past the split threshold, a second one with the split attention grid."""
         self.graph = self._capture()
+        if self.attn_splits > 1 and not self.persistent and self.max_seq > self.attn_split_min_pos:
+            self.graph_long = self._capture(splits=self.attn_splits)
 
     def step(self) -> None:
         """One token for every sequence of the batch: replay the captured graph."""
         if self.graph is None:
             self.capture()
-        self.graph.replay()
+        (self.graph_long if (self.graph_long is not None and self._long_context()) else self.graph).replay()
+        self._pos_h += 1
 
     def step_host(self, host_in: torch.Tensor, host_out: torch.Tensor) -> None:
         """Host-facing step: this step's input ids are read from the pinned host tensor `host_in` [B] and the
@@ -292,20 +314,27 @@ class QuantDecoder:
             raise ValueError("step_host: host tensors must match the token buffer [B] int64")
         key = (host_in.data_ptr(), host_out.data_ptr())
         if getattr(self, "_io_key", None) != key:
-            self._io_graph, self._io_key = self._capture(host_in, host_out), key
+            self._io_graphs, self._io_key = {False: self._capture(host_in, host_out)}, key
+            if self.attn_splits > 1 and not self.persistent and self.max_seq > self.attn_split_min_pos:
+                self._io_graphs[True] = self._capture(host_in, host_out, splits=self.attn_splits)
             self._io_bufs = (host_in, host_out)                         # keep the captured addresses alive
-        self._io_graph.replay()
+        self._io_graphs[self._long_context() and True in self._io_graphs].replay()
+        self._pos_h += 1
         torch.cuda.current_stream(self.dev).synchronize()
 
     def step_eager(self) -> None:
         lib().amqb_set_pdl(0)
         saved = self.pdl
         self.pdl = False
+        self._cur_splits = self.attn_splits if self._long_context() else 1
         self._step_launches()
+        self._cur_splits = 1
+        self._pos_h += 1
         self.pdl = saved
 
     def reset(self) -> None:
         self.pos.zero_()
+        self._pos_h = 0
 
     # ---------------------------------------------------------------- prompt prefill (all prompt rows at once)
     @torch.inference_mode()
@@ -325,6 +354,7 @@ class QuantDecoder:
         assert B == self.B and T >= 1
         pos0 = int(self.pos.item())
         assert pos0 + T <= self.max_seq
+        self._pos_h = pos0 + T
         if not use_graph:
             self._prefill_launches(ids, pos0)
             self.pos.add_(T)

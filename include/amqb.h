@@ -164,6 +164,16 @@ int amqb_rope_table(float* cos_sin, int max_seq, int D, float rope_theta, void* 
 int amqb_attn_decode(const void* qkv, void* k_cache, void* v_cache, void* out,
                      const int* pos_dev, int B, int Hq, int Hkv, int D, int max_seq,
                      float rope_theta, const float* rope_cos_sin, void* stream);
+/* Same kernel with the cached positions of every head shared by `splits` CTAs once *pos_dev >= split_min_pos
+ * (flash-decoding style: partial (max, denominator, sum) per CTA in `workspace`, the last CTA to arrive merges; below
+ * split_min_pos the extra CTAs exit at once and the result is bit-identical to amqb_attn_decode).  At long contexts a
+ * single CTA per head leaves most SMs idle (Hq = 32 heads on 148 SMs).  workspace: amqb_attn_split_workspace_bytes()
+ * bytes, zeroed once by the caller (the kernel leaves its arrival counters at zero). */
+size_t amqb_attn_split_workspace_bytes(int B, int Hq, int D, int splits);
+int amqb_attn_decode_split(const void* qkv, void* k_cache, void* v_cache, void* out,
+                           const int* pos_dev, int B, int Hq, int Hkv, int D, int max_seq,
+                           float rope_theta, const float* rope_cos_sin, int splits, int split_min_pos,
+                           void* workspace, size_t workspace_bytes, void* stream);
 /* fp16 GEMV for the unquantised lm_head with fused final RMSNorm prologue:
  * logits fp32 [M, V] = rmsnorm(x) @ W^T. */
 int amqb_lm_head(const void* W_f16, const void* x, const void* gamma, float eps,

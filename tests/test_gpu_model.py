@@ -344,3 +344,85 @@ def test_prefill_row_kernels_against_torch(D, Hq, Hkv, B, T, pos0):
     sc = sc.masked_fill(~vis[None, None], float("-inf"))
     o = torch.einsum("bhts,bhsd->bthd", torch.softmax(sc, -1), Vr).reshape(M, Hq * D)
     assert close(att, o, 2e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("D,Hq,Hkv,B,pos,splits", [(128, 8, 2, 1, 300, 4), (64, 4, 4, 2, 517, 3), (128, 4, 2, 1, 40, 4),
+                                                    (128, 32, 32, 1, 256, 4)])
+def test_attn_decode_split_matches_single_cta(D, Hq, Hkv, B, pos, splits):
+    """amqb_attn_decode_split (cached positions of a head shared by several CTAs beyond split_min_pos, last CTA merges)
+    against the single-CTA kernel and a PyTorch fp32 attention over the same cache; below the threshold it is
+    bit-identical; replays leave the arrival counters clean."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import ctypes
+    from amq_b200._lib import check, cur_stream, lib, ptr
+    dev, S, theta, min_pos = "cuda:0", 640, 10000.0, 256
+    torch.cuda.set_device(0)
+    g = torch.Generator(device=dev).manual_seed(pos)
+    L, st = lib(), cur_stream()
+
+    def rnd(*shape):
+        return torch.randn(*shape, device=dev, generator=g).half()
+
+    rope = torch.empty(S, D // 2, 2, dtype=torch.float32, device=dev)
+    check(L.amqb_rope_table(ptr(rope), S, D, ctypes.c_float(theta), st), "rope_table")
+    qkv = rnd(B, (Hq + 2 * Hkv) * D)
+    kc0 = torch.zeros(B, Hkv, S, D, device=dev, dtype=torch.float16)
+    vc0 = torch.zeros(B, Hkv, S, D, device=dev, dtype=torch.float16)
+    kc0[:, :, :pos], vc0[:, :, :pos] = rnd(B, Hkv, pos, D), rnd(B, Hkv, pos, D)
+    pos_dev = torch.tensor([pos], dtype=torch.int32, device=dev)
+    kc1, vc1, out1 = kc0.clone(), vc0.clone(), torch.empty(B, Hq * D, device=dev, dtype=torch.float16)
+    check(L.amqb_attn_decode(ptr(qkv), ptr(kc1), ptr(vc1), ptr(out1), ptr(pos_dev), B, Hq, Hkv, D, S, ctypes.c_float(theta),
+                             ptr(rope), st), "attn_decode")
+    L.amqb_attn_split_workspace_bytes.restype = ctypes.c_size_t
+    ws = torch.zeros(int(L.amqb_attn_split_workspace_bytes(B, Hq, D, splits)), dtype=torch.uint8, device=dev)
+    outs = []
+    for _ in range(3):                                   # same workspace: the counters must come back to zero
+        kc2, vc2, out2 = kc0.clone(), vc0.clone(), torch.empty(B, Hq * D, device=dev, dtype=torch.float16)
+        check(L.amqb_attn_decode_split(ptr(qkv), ptr(kc2), ptr(vc2), ptr(out2), ptr(pos_dev), B, Hq, Hkv, D, S,
+                                       ctypes.c_float(theta), ptr(rope), splits, min_pos, ptr(ws), ctypes.c_size_t(ws.numel()), st),
+              "attn_decode_split")
+        outs.append(out2)
+        assert torch.equal(kc1, kc2) and torch.equal(vc1, vc2)
+    torch.cuda.synchronize()
+    assert int(ws[: 4 * B * Hq].view(torch.int32).abs().sum()) == 0
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    if pos < min_pos:
+        assert torch.equal(out1, outs[0])
+    # fp32 reference from the cache the kernel left (rotated k of this step at row pos) and the rotated q
+    inv = theta ** (-torch.arange(0, D // 2, device=dev).float() * 2 / D)
+    ang = pos * inv
+    cos = torch.cat([ang.cos(), ang.cos()]).half().float()
+    sin = torch.cat([ang.sin(), ang.sin()]).half().float()
+    q = qkv[:, : Hq * D].float().view(B, Hq, D)
+    q = (q * cos + torch.cat([-q[..., D // 2:], q[..., : D // 2]], -1) * sin).half().float()
+    K = kc1.float()[:, :, : pos + 1].repeat_interleave(Hq // Hkv, dim=1)
+    V = vc1.float()[:, :, : pos + 1].repeat_interleave(Hq // Hkv, dim=1)
+    att = torch.softmax(torch.einsum("bhd,bhsd->bhs", q, K) / D ** 0.5, -1)
+    ref = torch.einsum("bhs,bhsd->bhd", att, V).reshape(B, Hq * D)
+    for o in (out1, outs[0]):
+        assert float((o.float() - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
+
+
+@pytest.mark.gpu
+def test_decode_step_with_split_attention_in_graph(monkeypatch):
+    """The captured decode step with the split attention path forced on from position 8: logits against the PyTorch
+    fp32 decoder across the threshold (graph replays reuse one workspace for every layer)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from amq_b200.arch import ModelShape, LINEARS
+    from amq_b200.model import QuantDecoder
+    monkeypatch.setenv("AMQB_ATTN_SPLIT_MIN_POS", "8")
+    shape = ModelShape("tiny-gqa", 512, 1408, 4, 2, 2, 512, head_dim=128)
+    arch = {n: [3, 4] for n in LINEARS}
+    m = QuantDecoder(shape, arch, batch=2, max_seq=32, seed=7)
+    assert m.attn_splits == 4 and m.attn_split_min_pos == 8
+    kc = [torch.zeros(2, m.Hkv, 32, m.D, device=m.dev) for _ in m.layers]
+    vc = [torch.zeros(2, m.Hkv, 32, m.D, device=m.dev) for _ in m.layers]
+    m.reset(); m.tokens.copy_(torch.tensor([3, 11], device=m.dev))
+    for pos in range(14):
+        ref = _ref_step(m, m.tokens.clone(), pos, kc, vc)
+        m.step()
+        torch.cuda.synchronize()
+        assert (m.logits - ref).abs().max() / ref.abs().max() < 2e-2, pos

@@ -27,13 +27,15 @@ def main():
     ap.add_argument("--prompt", type=int, default=64)
     ap.add_argument("--gen", type=int, default=128)
     ap.add_argument("--out", default="gpurun_out/ref_protocol.json")
+    ap.add_argument("--model", default="Llama-2-7b-hf")
+    ap.add_argument("--bits", type=float, default=3.0)
     a = ap.parse_args()
-    shape = MODELS["Llama-2-7b-hf"]
-    arch = sample_arch(shape, 3.0, seed=0)
-    m = QuantDecoder(shape, arch, batch=1, max_seq=768, seed=0)
+    shape = MODELS[a.model]
+    arch = sample_arch(shape, a.bits, seed=0)
+    m = QuantDecoder(shape, arch, batch=1, max_seq=max(768, a.prompt + a.gen + 8), seed=0)
     m.capture()
     ids = torch.randint(0, shape.vocab - 1, (1, a.prompt))        # speed.py:93 input_ids = randint(0, vocab-1, (b, seq))
-    res = {"workload": f"{shape.name} AMQ avg 3.0, batch 1, prompt {a.prompt}, gen {a.gen} (speed.py:23-46 protocol)"}
+    res = {"workload": f"{shape.name} AMQ avg {a.bits}, batch 1, prompt {a.prompt}, gen {a.gen} (speed.py:23-46 protocol)"}
     for mode in (True, False):
         m.generate(ids, 4, prefill=mode)                           # warm-up (lazy module loads)
         ts = []
