@@ -5,9 +5,8 @@ bits the way the search space does (amq/search/space.py:34-84)."""
 from __future__ import annotations
 
 import json
-import math
 import os
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, List, Optional
 
 import numpy as np

@@ -3,7 +3,7 @@ and pass raw device pointers + the current CUDA stream; the library allocates no
 from __future__ import annotations
 
 import ctypes
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, Optional, Sequence, Tuple
 
 import torch
 

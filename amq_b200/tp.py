@@ -8,12 +8,11 @@ from __future__ import annotations
 import ctypes
 import json
 import os
-import time
 from typing import Dict, List, Optional
 
 import torch
 
-from .arch import LINEARS, MODELS, ModelShape, sample_arch
+from .arch import MODELS, ModelShape, sample_arch
 
 GROUP = 128
 

@@ -18,7 +18,7 @@ from __future__ import annotations
 
 import gc
 import time
-from typing import Dict, Optional, Sequence
+from typing import Dict, Sequence
 
 import numpy as np
 import torch

@@ -139,7 +139,6 @@ def gemv_roofline(model, iters: int = 5):
     """Time one step's worth of decode-GEMV launches alone (same problems, same order, PDL on, CUDA
     graph, events on the launching stream).  The 2.4 GB of packed weights exceed L2 (126 MB)."""
     import torch
-    from amq_b200 import ops
     s = torch.cuda.Stream(device=model.dev)
     n_launch = 0
     with torch.cuda.stream(s):

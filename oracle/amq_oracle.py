@@ -19,7 +19,6 @@ HQQ = amq/kernel/hqq/hqq.
 """
 from __future__ import annotations
 
-import json
 import math
 from typing import Dict, List, Optional, Sequence, Tuple
 
