@@ -63,3 +63,55 @@ def test_arch_selection(golden_dir):
     with open(os.path.join(golden_dir, "arch_stats.json")) as f:
         d = json.load(f)
     assert O.select_arch(d["stats"], d["target_bits"]) == d["expected"]
+
+
+@pytest.mark.parametrize("bits", [2, 3, 4])
+def test_oracle_roundtrip_properties(bits):
+    """Size-independent properties of the restated layouts on seeded random codes (beyond the committed fixtures):
+    every packer is inverted exactly by its unpacker, including ragged 3-bit row counts (padding to a multiple of 10,
+    bitpack.py:69-91), the smallest legal shapes, and the two 3-bit codes of every 32 that straddle a word boundary
+    (autogptq.py:133-151)."""
+    rs = np.random.RandomState(100 + bits)
+    for R in ([1, 9, 10, 13, 130, 257] if bits == 3 else [4, 8, 64, 256]):
+        codes = rs.randint(0, 2 ** bits, size=(R, 128)).astype(np.uint8)
+        packed = O.hqq_pack(codes, bits)
+        assert packed.shape[0] == ((R + 9) // 10 if bits == 3 else R // (8 // bits))
+        assert np.array_equal(O.hqq_unpack(packed, bits, rows=R), codes)
+    for N, K in [(2, 32), (6, 96), (64, 256)]:
+        codes = rs.randint(0, 2 ** bits, size=(N, K)).astype(np.uint8)
+        qw = O.gptq_pack_codes(codes, bits)
+        assert qw.shape == (K * bits // 32, N) and qw.dtype == np.int32
+        assert np.array_equal(O.gptq_unpack(qw, bits), codes.T)
+        assert np.array_equal(O.gptq_unpack_fast(qw, bits), codes.T)
+    # extreme codes: all-ones fields must not bleed into their neighbours
+    full = np.full((4, 64), 2 ** bits - 1, dtype=np.uint8)
+    full[:, ::2] = 0
+    assert np.array_equal(O.gptq_unpack(O.gptq_pack_codes(full, bits), bits), full.T)
+    if bits == 4:
+        for N, K in [(4, 64), (8, 192), (64, 256)]:
+            codes = rs.randint(0, 16, size=(N, K)).astype(np.uint8)
+            q = O.ft_pack_intweight(codes)
+            assert q.shape == (N // 4, K) and q.dtype == np.int16
+            assert np.array_equal(O.ft_unpack(q), codes)
+
+
+def test_oracle_forward_linearity_and_bits_accounting():
+    """The restated torch forward is linear in x (fp32 form) and agrees with a dense matmul of the dequantised weight;
+    get_bits_usage reproduces func.py:101-114 on a hand-computed case."""
+    rs = np.random.RandomState(7)
+    bits, N, K, G = 3, 32, 256, 128
+    codes = rs.randint(0, 8, size=(N, K)).astype(np.uint8)
+    qw = O.gptq_pack_codes(codes, bits)
+    scales = torch.from_numpy(rs.uniform(0.01, 0.02, size=(K // G, N)).astype(np.float32)).half().float()
+    zeros = torch.from_numpy(rs.uniform(0.02, 0.1, size=(K // G, N)).astype(np.float32)).half().float()
+    x1, x2 = torch.randn(1, K).half(), torch.randn(1, K).half()
+    y1 = O.gptq_forward_fp32(x1, qw, scales, zeros, bits, G)
+    y2 = O.gptq_forward_fp32(x2, qw, scales, zeros, bits, G)
+    y12 = O.gptq_forward_fp32((x1.float() + x2.float()), qw, scales, zeros, bits, G)
+    assert torch.allclose(y1 + y2, y12, rtol=1e-5, atol=1e-5)
+    W = (torch.from_numpy(codes.T.astype(np.float32)).reshape(K // G, G, N) * scales[:, None, :] - zeros[:, None, :]).reshape(K, N)
+    assert torch.allclose(y1, x1.float() @ W, rtol=1e-5, atol=1e-5)
+    cfg = {"linear_shape": {"a": [4, 256], "b": [8, 128]}, "model_numel": 4 * 256 + 8 * 128}
+    arch = {"linear": {"a": [2, 4], "b": [3, 3]}}
+    want = (4 * 256 * (2.25 + 4.25) + 8 * 128 * (3.25 + 3.25)) / (4 * 256 + 8 * 128)
+    assert abs(O.get_bits_usage(arch, cfg) - want) < 1e-12
