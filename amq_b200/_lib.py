@@ -27,13 +27,6 @@ class GemvProblem(ctypes.Structure):
     ]
 
 
-class MegaShape(ctypes.Structure):
-    """amqb_mega_shape (include/amqb.h)."""
-    _fields_ = [("hidden", ctypes.c_int), ("inter", ctypes.c_int), ("Hq", ctypes.c_int), ("Hkv", ctypes.c_int),
-                ("D", ctypes.c_int), ("max_seq", ctypes.c_int), ("n_layers", ctypes.c_int),
-                ("eps", ctypes.c_float), ("rope_theta", ctypes.c_float)]
-
-
 def lib() -> ctypes.CDLL:
     global _lib
     if _lib is None:
@@ -44,7 +37,7 @@ def lib() -> ctypes.CDLL:
         L = ctypes.CDLL(LIB_PATH)
         L.amqb_last_error_string.restype = ctypes.c_char_p
         for name in ("amqb_native_bytes", "amqb_workspace_bytes", "amqb_gemm_workspace_bytes",
-                     "amqb_hqq_quantize_workspace_bytes", "amqb_ar_buffer_bytes", "amqb_decode_layers_barrier_bytes",
+                     "amqb_hqq_quantize_workspace_bytes", "amqb_ar_buffer_bytes",
                      "amqb_attn_split_workspace_bytes"):
             if hasattr(L, name):
                 getattr(L, name).restype = ctypes.c_size_t

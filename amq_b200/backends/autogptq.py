@@ -27,9 +27,6 @@ class GPTQLinear(nn.Module):
         super().__init__()
         if bits not in [2, 3, 4, 8]:
             raise NotImplementedError("Only 2,3,4,8 bits are supported.")
-        if bits == 8:
-            # autogptq.py:203 — the reference's fp16 kernel path also rejects 8 bits at forward time
-            raise NotImplementedError("Only 2,3,4 bits are supported.")
         if trainable:
             raise NotImplementedError("amq_b200.GPTQLinear is inference-only")
         self.infeatures = infeatures
@@ -47,7 +44,7 @@ class GPTQLinear(nn.Module):
         else:
             self.bias = None
         self.half_indim = self.infeatures // 2
-        self.use_cuda_fp16 = use_cuda_fp16
+        self.use_cuda_fp16 = use_cuda_fp16 if bits != 8 else False      # autogptq.py:86
         self.kernel_switch_threshold = kernel_switch_threshold   # kept for API parity; unused
         self.trainable = trainable
         # kernel-native repack (amq_b200/csrc/layout.cuh); rebuilt lazily after pack()/load_state_dict()
@@ -61,7 +58,7 @@ class GPTQLinear(nn.Module):
         if not self.qweight.is_cuda:
             raise RuntimeError("amq_b200.GPTQLinear: move the module to a CUDA device first (no CPU path)")
         N, K, G = self.outfeatures, self.infeatures, self.group_size
-        ok = ops.native_supported(self.bits, N, K, G)
+        ok = self.bits != 8 and ops.native_supported(self.bits, N, K, G)
         if ok:
             # scales / zeros hold fp16-exact values in the AMQ flow (they come from fp16 HQQ meta,
             # autogptq.py:112-114); the native layout stores them as fp16.  Otherwise keep fp32 meta
@@ -96,6 +93,10 @@ class GPTQLinear(nn.Module):
         x2 = x.reshape(-1, x.shape[-1])
         if x_dtype != torch.float16:
             x2 = x2.half()      # the reference kernels cast too (autogptq.py:165-169)
+        if self.bits == 8 and x2.shape[0] < self.kernel_switch_threshold:
+            # autogptq.py:86,204-205: 8-bit modules have use_cuda_fp16 = False and the reference's small-M branch
+            # raises exactly this; only the large-M branch (:245-283) serves them
+            raise NotImplementedError("Only use_cuda_fp16=True is supported.")
         if self._native_ok is None:
             self.post_init()
         N, K = self.outfeatures, self.infeatures

@@ -197,32 +197,40 @@ class HQQLinear(nn.Module):
         return ops.unpack_codes(self.W_q.data, int(self.meta["nbits"]), LAYOUT_HQQ, N, K, self.meta["group_size"])
 
     def matmul(self, x: Tensor, transpose: bool = True) -> Tensor:
-        weight = self.dequantize()
-        return torch.matmul(x, weight.t() if transpose else weight)
+        """quantize.py:880-882.  x @ W_r.T through the fused kernels; the untransposed product only serves the
+        reference's backprop variants, which are not part of AMQ's path."""
+        if not transpose:
+            raise NotImplementedError("amq_b200.HQQLinear.matmul: transpose=False (backprop) is not on AMQ's path")
+        bias, self.bias = self.bias, None
+        try:
+            return self.forward(x)
+        finally:
+            self.bias = bias
 
-    # ---- backends (quantize.py:393-418 `set_backend`): "pytorch" = dequantise + library GEMM (the reference's
-    # forward_pytorch); "fused" (default) = the search-stage fast path of SURVEY §8f-3: W_q is transcoded once,
-    # integer-exactly, HQQ layout -> kernel-native records, and every forward is the dequant-fused decode GEMV
-    # (M <= 16) or the tcgen05 prefill GEMM, so no [N, K] fp16 weight is materialised per call.
+    # ---- forward (quantize.py:880-898 `forward_pytorch`): x @ ((W_q - zero) * scale).T + bias.  ONE path: W_q is
+    # transcoded once, integer-exactly, HQQ layout -> kernel-native records (SURVEY §8f-3), and every forward is the
+    # dequant-fused decode GEMV (M <= 16) or the tcgen05 prefill GEMM — no [N, K] fp16 weight is materialised per
+    # call and there is no dequantise + library-GEMM branch.  `set_backend` is kept for call-site compatibility
+    # (quantize.py:393-418); every reference backend name maps onto the fused kernels.
     backend = "fused"
 
     @classmethod
     def set_backend(cls, backend):
         name = getattr(backend, "value", backend)
-        name = {"forward_pytorch": "pytorch", "forward_pytorch_backprop": "pytorch"}.get(name, name)
-        if name not in ("pytorch", "fused"):
-            raise ValueError(f"HQQLinear.set_backend: unknown backend {backend!r} (pytorch | fused)")
-        cls.backend = name
+        if name not in ("fused", "pytorch", "forward_pytorch", "forward_pytorch_backprop", "forward_pytorch_compile",
+                        "forward_pytorch_backprop_compile", "forward_aten", "forward_aten_backprop"):
+            raise ValueError(f"HQQLinear.set_backend: unknown backend {backend!r}")
+        cls.backend = "fused"
 
     def native_weight(self):
-        """Kernel-native copy of (W_q, scale, zero); None when the layer does not meet the kernel's preconditions
-        (axis 1, group 128, N % 32 == 0, K % 128 == 0, 2/3/4 bits).  Rebuilt when W_q / meta are replaced."""
+        """Kernel-native copy of (W_q, scale, zero); None when the layer does not meet the native layout's
+        preconditions (axis 1, group 128, N % 32 == 0, K % 128 == 0, 2/3/4 bits).  Rebuilt when W_q / meta are replaced."""
         key = (self.W_q.data_ptr(), self.meta["scale"].data_ptr(), self.meta["zero"].data_ptr())
         if getattr(self, "_native_key", None) == key:
             return self._w_native
         N, K = self.meta["shape"]
         bits, G = int(self.meta["nbits"]), self.meta["group_size"]
-        self._native_key, self._w_native = key, None
+        self._native_key, self._w_native, self._gptq = key, None, None
         if self.meta.get("axis", 1) == 1 and self.meta["nbits"] == bits and ops.native_supported(bits, N, K, G) \
                 and self.W_q.is_cuda:
             scale = self.meta["scale"].reshape(N, -1).to(torch.float16)
@@ -230,19 +238,35 @@ class HQQLinear(nn.Module):
             self._w_native = ops.pack_native(bits, self.unpack_codes(), scale, zero)
         return self._w_native
 
+    def drop_native(self):
+        """Free the kernel-native copy (rebuilt on the next forward).  The proxies keep W_q for state_dict() /
+        dequantize(), so a layer that has run holds its weights twice: (bits + 0.25) / 8 bytes per weight more."""
+        self._native_key, self._w_native, self._gptq = None, None, None
+
     def forward(self, x: Tensor) -> Tensor:
-        """quantize.py:880-898.  Both backends compute x @ ((W_q - zero) * scale).T + bias; "pytorch" rounds the
-        weight to fp16 twice like the reference, "fused" once (inside the 1e-3 parity bound either way)."""
-        nat = self.native_weight() if (self.backend == "fused" and x.is_cuda and x.dtype == torch.float16) else None
+        if not x.is_cuda:
+            raise RuntimeError("amq_b200.HQQLinear.forward: CUDA tensor required (no CPU fallback)")
+        N, K = self.meta["shape"]
+        bits = int(self.meta["nbits"])
+        x2 = x.reshape(-1, K)
+        if x2.dtype != torch.float16:
+            x2 = x2.half()
+        x2 = x2.contiguous()
+        nat = self.native_weight()
         if nat is not None:
-            N, K = self.meta["shape"]
-            x2 = x.reshape(-1, K)
-            out = ops.linear_forward(int(self.meta["nbits"]), nat, x2, N, K, self.bias)
-            return out.reshape(*x.shape[:-1], N)
-        out = torch.matmul(x, self.dequantize().t())
-        if self.bias is not None:
-            out += self.bias
-        return out
+            out = ops.linear_forward(bits, nat, x2, N, K, self.bias)
+        else:
+            # shapes outside the native record grid (never AMQ's): the reference's own conversion (dequantise ->
+            # GPTQLinear.pack, autogptq.py:318-325) once, then the any-shape GPTQ-layout kernel in 16-row slabs
+            if self._gptq is None:
+                G = self.meta["group_size"]
+                self._gptq = ops.gptq_pack(bits, self.dequantize(), self.meta["scale"].reshape(N, -1),
+                                           self.meta["zero"].reshape(N, -1), G)
+            q, s, z = self._gptq
+            outs = [ops.gemv_gptq_layout(bits, q, s, z, x2[i:i + 16].contiguous(), N, K, self.meta["group_size"], self.bias)
+                    for i in range(0, x2.shape[0], 16)]
+            out = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+        return out.to(x.dtype).reshape(*x.shape[:-1], N)
 
     # ---- HQQ-format (de)serialisation, quantize.py:643-787
     def state_dict_keys(self):
@@ -263,6 +287,20 @@ class HQQLinear(nn.Module):
             for key, value in state.items():
                 kwargs["destination"][kwargs["prefix"] + key] = value
         return state
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        """quantize.py:684-706: a parent model.load_state_dict() hands this layer the flat dict; gather the
+        prefix + state_dict_keys() entries (removing them from the parent's dict, so strict loading does not report
+        them as unexpected) and load them as a layer state dict."""
+        layer_sd = {}
+        for key in self.state_dict_keys():
+            full = prefix + key
+            if full in state_dict:
+                layer_sd[key] = state_dict.pop(full)
+            elif strict and key in ("W_q", "scale", "zero", "nbits", "group_size", "shape"):
+                missing_keys.append(full)
+        if "W_q" in layer_sd and layer_sd["W_q"] is not None:
+            self.load_state_dict(layer_sd, strict=strict)
 
     def load_state_dict(self, state_dict, strict=True, assign=False):
         sd = dict(state_dict)

@@ -43,12 +43,14 @@ __global__ void __launch_bounds__(1024) allreduce_push_kernel(const ArArgs A) {
   __shared__ uint8_t* s_peer[kArMaxWorld];
   pdl_launch_dependents();
   // Before griddepcontrol.wait (overlaps the GEMV that produces `partial`): the peer pointers go to shared memory
-  // (no register-indexed constant loads on the dependent path) and the epoch is advanced.  The epoch word is
-  // private to this rank's all-reduce launches, and the previous one has completed by the time this grid can start
-  // (the GEMV between them waited for it before any of its CTAs could finish and free an SM for us... and this
-  // kernel's single CTA only starts once that GEMV's grid is resident).
+  // (no register-indexed constant loads on the dependent path).  The epoch word is private to this rank's all-reduce
+  // launches; it is advanced AFTER the wait, i.e. ordered after the previous all-reduce launch by the stream itself.
   uint8_t* mine = A.peer[A.rank];
   if (threadIdx.x < kArMaxWorld) s_peer[threadIdx.x] = A.peer[threadIdx.x];
+  const size_t slot_bytes = (size_t)A.max_elems * 2;
+  const int nvec = A.n_elems / 8;                         // 16-byte vectors
+  const uint4* src = reinterpret_cast<const uint4*>(A.partial);
+  pdl_wait();
   if (threadIdx.x == 0) {
     uint32_t* ep = reinterpret_cast<uint32_t*>(mine);
     s_epoch = *ep + 1;
@@ -56,11 +58,7 @@ __global__ void __launch_bounds__(1024) allreduce_push_kernel(const ArArgs A) {
   }
   __syncthreads();
   const uint32_t epoch = s_epoch;
-  const size_t slot_bytes = (size_t)A.max_elems * 2;
   const size_t data_off = kArHeader + 128 * (size_t)A.world + (size_t)(epoch & 1) * A.world * slot_bytes;
-  const int nvec = A.n_elems / 8;                         // 16-byte vectors
-  const uint4* src = reinterpret_cast<const uint4*>(A.partial);
-  pdl_wait();
   // 1. push my partial sums into slot [rank] of every peer (and my own buffer): each thread loads its vectors once
   for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
     const uint4 q = __ldcg(src + v);
@@ -73,7 +71,7 @@ __global__ void __launch_bounds__(1024) allreduce_push_kernel(const ArArgs A) {
   if (threadIdx.x < A.world) {
     st_release_sys(reinterpret_cast<uint32_t*>(s_peer[threadIdx.x] + kArHeader + 128 * A.rank), epoch);
     const uint32_t* f = reinterpret_cast<const uint32_t*>(mine + kArHeader + 128 * threadIdx.x);
-    while (ld_acquire_sys(f) != epoch) {}
+    while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {}    // wrap-safe: a faster peer may already be one epoch ahead
   }
   __syncthreads();
   // 4. reduce in rank order (+ residual); all loads of a vector are issued before the first add

@@ -21,6 +21,33 @@ inline int check_launch(const char* what) {
   return AMQB_OK;
 }
 
+// Per-device one-time setup (func attributes, SM count): the library is used from one process on several devices
+// (HQQ proxies are dispatched across GPUs, amq/utils/dispatch.py), so nothing device-specific is cached process-wide.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d < 0 || d >= kMaxDevices) ? 0 : d;
+}
+struct PerDeviceOnce {
+  bool done[kMaxDevices] = {};
+  bool first() {
+    const int d = current_device();
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+inline int sm_count() {
+  static int cached[kMaxDevices] = {};
+  const int d = current_device();
+  if (cached[d] == 0) {
+    cudaDeviceGetAttribute(&cached[d], cudaDevAttrMultiProcessorCount, d);
+    if (cached[d] <= 0) cached[d] = 148;
+  }
+  return cached[d];
+}
+
 inline int fail(int code, const char* msg) {
   set_error("%s", msg);
   return code;

@@ -481,11 +481,10 @@ int amqb_gemm_tc(int bits, const void* w_native, const void* x, void* y, const v
   if (nws > (size_t)kWStagesMax) nws = kWStagesMax;
   A.nws = (int)nws;
   const size_t smem = kTcHeader + (size_t)kXStages * kXBytes + nws * w_stage;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.first()) {
     cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax);
     cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax);
-    attr = true;
   }
   const int n_tiles = N / kTileN;
   // cluster pair + X multicast halves the activations' L2 traffic but measured ~5% slower (the X ring is bound by the

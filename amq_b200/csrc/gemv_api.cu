@@ -6,18 +6,7 @@
 
 namespace amqb {
 
-static int g_sm_count = 0;
-long long* g_dbg = nullptr;       // debug timeline buffer (amqb_debug_set_timeline), shared with decode_mega.cu
-
-static int sm_count() {
-  if (g_sm_count == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sm_count <= 0) g_sm_count = 148;
-  }
-  return g_sm_count;
-}
+long long* g_dbg = nullptr;       // debug timeline buffer (amqb_debug_set_timeline)
 
 // One launch: problems sharing M and prologue kind (bit widths may differ).
 static size_t xg_xsd_bytes(int n_g, int MB) { return ((size_t)n_g * MB * 8 * sizeof(float2) + 255) & ~size_t(255); }

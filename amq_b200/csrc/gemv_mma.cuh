@@ -234,6 +234,9 @@ __device__ __forceinline__ float2 item_stats(__half2 lo, __half2 hi, float (&xf)
   float2 r;
   r.x = (float)tot * __int_as_float((127 + e - 32) << 23);         // sum of x-hat over the group
   r.y = __int_as_float((127 + e - 36) << 23);                      // delta' = 2^(e - 36): dot = delta' * (2^16 c0 + 2^8 c1 + c2)
+  // non-finite policy: an integer dot product cannot carry inf / NaN, so a group holding one poisons its activation
+  // row (delta' = NaN -> every output of the row is NaN) instead of contributing finite garbage
+  if (mx >= 0x7C00u) r.y = __int_as_float(0x7FC00000);
   return r;
 }
 
@@ -272,8 +275,7 @@ __device__ __forceinline__ void emit_item(__half2 lo, __half2 hi, const XLane (&
 
 template <int PRO>
 __device__ __forceinline__ void load_item(const DevProblem& P, int col, int group, int koff, uint2& a, uint2& b) {
-  // activations are read through L2 (ld.global.cg): inside the persistent decode kernel another CTA wrote them
-  // earlier in the same launch, and the SM's L1 may still hold the previous contents of the buffer
+  // activations are read through L2 (ld.global.cg): the previous launch wrote them and nothing here re-reads them
   const __half* xr = P.x + (size_t)col * P.ldx + group * kGroup + koff;
   a.x = __ldcg(reinterpret_cast<const uint32_t*>(xr));
   a.y = __ldcg(reinterpret_cast<const uint32_t*>(xr + 8));
@@ -896,11 +898,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
 template <int MB, int KIND, int PRO>
 static int launch_variant(const GemvLaunch& L, int grid, size_t smem, int pdl, cudaStream_t st) {
   auto kern = gemv_mma_kernel<MB, KIND, PRO>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-    attr_set = true;
-  }
+  static PerDeviceOnce attr;
+  if (attr.first()) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreads);

@@ -1,4 +1,5 @@
-// Direct replacement of vecquant{2,3,4}matmul_faster_old on the UNREPACKED GPTQLinear buffers
+// Direct replacement of vecquant{2,3,4}matmul_faster_old on the UNREPACKED GPTQLinear buffers (and the only path for the
+// 8-bit modules the reference constructor also accepts, autogptq.py:43-46, which AMQ never builds)
 // (/root/reference/amq/kernel/AutoGPTQ/auto_gptq_kernel.cu:160-225, 258-343, 376-440; call site
 // amq/kernel/hqq/hqq/backends/autogptq.py:159-203).  Same thread->column mapping idea as the
 // reference (coalesced along N), but: fp32 dot products, scale/zero applied once per group,
@@ -33,7 +34,7 @@ gemv_gptq_simt_kernel(const uint32_t* __restrict__ qw, const float* __restrict__
     for (int m = 0; m < 16; ++m) { dot[m] = 0.f; xsum[m] = 0.f; }
     for (int bi = 0; bi < blocks_per_group; ++bi) {
       const int kb = grp * blocks_per_group + bi;     // 32-code block index
-      uint32_t w[4] = {0u, 0u, 0u, 0u};
+      uint32_t w[BITS < 4 ? 4 : BITS + 1] = {};
       if (live) {
 #pragma unroll
         for (int i = 0; i < BITS; ++i) w[i] = qw[(size_t)(kb * BITS + i) * N + n];
@@ -81,7 +82,7 @@ using namespace amqb;
 extern "C" int amqb_gemv_gptq_layout(int bits, const int32_t* qweight, const float* scales, const float* zeros,
                                      const void* x, void* y, const void* bias, int M, int N, int K, int G, void* stream) {
   if (!qweight || !scales || !zeros || !x || !y) return fail(AMQB_ERR_BAD_ARG, "gemv_gptq_layout: null pointer");
-  if (!(bits == 2 || bits == 3 || bits == 4)) return fail(AMQB_ERR_BAD_ARG, "gemv_gptq_layout: bits must be 2, 3 or 4");
+  if (!(bits == 2 || bits == 3 || bits == 4 || bits == 8)) return fail(AMQB_ERR_BAD_ARG, "gemv_gptq_layout: bits must be 2, 3, 4 or 8");
   if (M < 1 || M > 16) return fail(AMQB_ERR_BAD_ARG, "gemv_gptq_layout: M must be 1..16");
   if (N <= 0 || K <= 0 || G <= 0 || K % G || G % 32) return fail(AMQB_ERR_UNSUPPORTED_SHAPE, "gemv_gptq_layout: K % G or G % 32");
   cudaStream_t st = (cudaStream_t)stream;
@@ -89,6 +90,7 @@ extern "C" int amqb_gemv_gptq_layout(int bits, const int32_t* qweight, const flo
   const uint32_t* q = (const uint32_t*)qweight;
   if (bits == 2) gemv_gptq_simt_kernel<2><<<grid, block, 0, st>>>(q, scales, zeros, (const __half*)x, (__half*)y, (const __half*)bias, M, N, K, G);
   else if (bits == 3) gemv_gptq_simt_kernel<3><<<grid, block, 0, st>>>(q, scales, zeros, (const __half*)x, (__half*)y, (const __half*)bias, M, N, K, G);
+  else if (bits == 8) gemv_gptq_simt_kernel<8><<<grid, block, 0, st>>>(q, scales, zeros, (const __half*)x, (__half*)y, (const __half*)bias, M, N, K, G);
   else gemv_gptq_simt_kernel<4><<<grid, block, 0, st>>>(q, scales, zeros, (const __half*)x, (__half*)y, (const __half*)bias, M, N, K, G);
   return check_launch("gemv_gptq_layout");
 }

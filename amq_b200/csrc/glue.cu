@@ -736,19 +736,16 @@ int amqb_lm_head(const void* W_f16, const void* x, const void* gamma, float eps,
     if (rc) return rc;
     return amqb_lm_head(W_f16, (const __half*)x + (size_t)h1 * K, gamma, eps, logits + (size_t)h1 * V, M - h1, V, K, stream);
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count();
   if (M >= 2 && V % 16 == 0 && K % 32 == 0) {
     // batches: tensor-core kernel (the CUDA-core kernel below is FMA-bound beyond one activation row)
     const int NB = M <= 8 ? 1 : 2;
     const size_t smem_mma = (size_t)NB * 8 * (K + kHeadPad) * sizeof(__half);
     if (smem_mma <= 200 * 1024) {
-      static bool attr_mma = false;
-      if (!attr_mma) {
+      static PerDeviceOnce attr_mma;
+      if (attr_mma.first()) {
         cudaFuncSetAttribute(lm_head_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(lm_head_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_mma = true;
       }
       const int per_sm_mma = smem_mma > 100 * 1024 ? 1 : 2;
       int grid_mma = sms * per_sm_mma;
@@ -763,12 +760,11 @@ int amqb_lm_head(const void* W_f16, const void* x, const void* gamma, float eps,
   const size_t smem = (size_t)M * K * sizeof(__half);
   const int per_sm = smem > 100 * 1024 ? 1 : (smem > 48 * 1024 ? 2 : 4);
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.first()) {
     cudaFuncSetAttribute(lm_head_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(lm_head_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(lm_head_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr = true;
   }
   const dim3 grid(sms * per_sm), block(256);
   if (M == 1)

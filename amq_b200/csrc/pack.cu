@@ -387,7 +387,7 @@ int amqb_repack_ft(const int16_t* qweight, const void* scales_f16, const void* s
 
 int amqb_gptq_pack(int bits, const void* W_f16, const void* scales_f16, const void* zeros_f16, int32_t* qweight,
                    float* scales_out, float* zeros_out, int N, int K, int G, void* stream) {
-  if (!bits_ok(bits) || !W_f16 || !scales_f16 || !zeros_f16 || !qweight || !scales_out || !zeros_out)
+  if (!(bits_ok(bits) || bits == 8) || !W_f16 || !scales_f16 || !zeros_f16 || !qweight || !scales_out || !zeros_out)
     return fail(AMQB_ERR_BAD_ARG, "gptq_pack: bad argument");
   if (G <= 0 || K % G || K % 32) return fail(AMQB_ERR_UNSUPPORTED_SHAPE, "gptq_pack: K % G or K % 32");
   cudaStream_t st = (cudaStream_t)stream;

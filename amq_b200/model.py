@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import ops
-from ._lib import PRO_NONE, PRO_RMSNORM, PRO_SILU_MUL, MegaShape, check, cur_stream, lib, ptr
+from ._lib import PRO_NONE, PRO_RMSNORM, PRO_SILU_MUL, check, cur_stream, lib, ptr
 from .arch import LINEARS, ModelShape
 
 GROUP = 128
@@ -50,7 +50,7 @@ class QuantDecoder:
 
     def __init__(self, shape: ModelShape, arch: Dict[str, List[int]], batch: int = 1, max_seq: int = 256,
                  device: str = "cuda:0", seed: int = 0, n_block: Optional[int] = None, pdl: bool = True,
-                 tp_rank: int = 0, tp_world: int = 1, persistent: Optional[bool] = None):
+                 tp_rank: int = 0, tp_world: int = 1):
         if not torch.cuda.is_available():
             raise RuntimeError("amq_b200.QuantDecoder needs a CUDA device (no CPU path)")
         self.shape = shape
@@ -123,14 +123,37 @@ class QuantDecoder:
         self.allreduce = None          # set by amq_b200.tp for tensor-parallel runs
         self.launches_per_step = 0
         self._build_problems()
-        # batch 1 on one GPU can run all decoder layers as ONE persistent launch (csrc/decode_mega.cu).  Opt-in
-        # (persistent=True or AMQB_PERSISTENT=1): as measured in round 1 its grid-wide phase barriers cost more than the
-        # programmatic-dependent-launch boundaries of the per-linear chain, so the chain stays default
-        if persistent is None:
-            persistent = os.environ.get("AMQB_PERSISTENT", "0") == "1"
-        self.persistent = bool(persistent) and batch == 1 and tp_world == 1 and self._persistent_supported()
-        if self.persistent:
-            self._build_layer_table()
+
+    # ---------------------------------------------------------------- tensor-parallel shard of another decoder
+    def adopt_shard_of(self, full: "QuantDecoder") -> None:
+        """Replace this rank's random weights by rank tp_rank's Megatron shard of `full` (a tp_world = 1 decoder of the
+        same shape / arch on the same device): column-parallel linears take a run of 32-row record blocks, row-parallel
+        ones a run of k groups of every row block.  Parity-test / emulation aid."""
+        assert full.tp_world == 1 and full.shape == self.shape and full.n_block == self.n_block and full.B == self.B
+        r, w = self.tp_rank, self.tp_world
+        self.embed, self.lm_head, self.final_norm = full.embed, full.lm_head, full.final_norm
+        for L, F in zip(self.layers, full.layers):
+            for name in LINEARS:
+                bits, buf, N, K = F[name]
+                rec = bits * 512 + 128
+                v = buf.view(N // 32, K // GROUP, rec)
+                _, _, n_loc, k_loc = L[name]
+                if name in ("self_attn.o_proj", "mlp.down_proj"):          # row-parallel: split K
+                    g0 = r * (k_loc // GROUP)
+                    shard = v[:, g0: g0 + k_loc // GROUP]
+                else:                                                        # column-parallel: split N
+                    b0 = r * (n_loc // 32)
+                    shard = v[b0: b0 + n_loc // 32]
+                L[name] = (bits, shard.contiguous().reshape(-1), n_loc, k_loc)
+            L["norm1"], L["norm2"] = F["norm1"], F["norm2"]
+            if "qkv_bias" in F:
+                fq, fk = full.q_dim, full.kv_dim
+                b = F["qkv_bias"]
+                L["qkv_bias"] = torch.cat([b[r * self.q_dim: (r + 1) * self.q_dim],
+                                           b[fq + r * self.kv_dim: fq + (r + 1) * self.kv_dim],
+                                           b[fq + fk + r * self.kv_dim: fq + fk + (r + 1) * self.kv_dim]]).contiguous()
+        self._build_problems()
+        self.graph = self.graph_long = None
 
     # ---------------------------------------------------------------- static launch descriptors
     def _build_problems(self) -> None:
@@ -186,40 +209,6 @@ class QuantDecoder:
             self._plan.append({"qkv": (ops.GemvProblem * 3)(*qkv), "o": (ops.GemvProblem * 1)(*o),
                                "gu": (ops.GemvProblem * 2)(*gu), "down": (ops.GemvProblem * 1)(*down), "L": L})
 
-    # ---------------------------------------------------------------- persistent decode kernel (batch 1)
-    def _persistent_supported(self) -> bool:
-        S = self.shape
-        x_single = (max(S.inter, S.hidden) // GROUP) * 480
-        x_multi = 3 * (((S.hidden // GROUP) * 480 + 127) // 128 * 128)
-        fixed = 384 + self.n_block * 208 + 2 * (max(S.inter, S.hidden) // GROUP) * 8 * 4 + max(x_single, x_multi) + 4096 + 512
-        return (S.head_dim in (64, 128) and S.hidden % GROUP == 0 and S.inter % GROUP == 0 and self.q_dim % GROUP == 0
-                and self.q_dim % 32 == 0 and self.kv_dim % 32 == 0 and fixed + 2 * 16 * 2176 <= 227 * 1024 and self.Hq <= 132)
-
-    def _build_layer_table(self) -> None:
-        """amqb_mega_layer[n_block] in device memory: per-layer weight pointers / bit widths (the searched arch),
-        norm weights and KV cache pointers."""
-        lin = np.dtype([("w", "<u8"), ("bias", "<u8"), ("bits", "<i4"), ("pad", "<i4")])
-        rec = np.dtype([("lin", lin, (7,)), ("norm1", "<u8"), ("norm2", "<u8"), ("kc", "<u8"), ("vc", "<u8"), ("pad", "<i8")])
-        assert rec.itemsize == 208
-        tab = np.zeros(self.n_block, dtype=rec)
-        for li, L in enumerate(self.layers):
-            bias = L.get("qkv_bias")
-            boff = [0, self.q_dim, self.q_dim + self.kv_dim]
-            for j, name in enumerate(LINEARS):
-                bits, w, N, K = L[name]
-                tab[li]["lin"][j]["w"] = w.data_ptr()
-                tab[li]["lin"][j]["bits"] = bits
-                tab[li]["lin"][j]["bias"] = (bias.data_ptr() + 2 * boff[j]) if (bias is not None and j < 3) else 0
-            tab[li]["norm1"], tab[li]["norm2"] = L["norm1"].data_ptr(), L["norm2"].data_ptr()
-            tab[li]["kc"], tab[li]["vc"] = L["k_cache"].data_ptr(), L["v_cache"].data_ptr()
-        self._layer_table = torch.from_numpy(tab.view(np.uint8).copy()).to(self.dev)
-        nbar = int(lib().amqb_decode_layers_barrier_bytes(self.n_block))
-        self._mega_bar = torch.zeros(nbar, dtype=torch.uint8, device=self.dev)
-        self.mega_err = torch.zeros(1, dtype=torch.int32, device=self.dev)
-        S = self.shape
-        self._mega_shape = MegaShape(S.hidden, S.inter, self.Hq, self.Hkv, self.D, self.max_seq, self.n_block,
-                                     float(S.rms_eps), float(S.rope_theta))
-
     # ---------------------------------------------------------------- one decode step (all launches)
     def _gemv(self, arr, n) -> None:
         check(lib().amqb_gemv_grouped(arr, n, ptr(self.ws), ctypes.c_size_t(self.ws.numel()), int(self.pdl), cur_stream()),
@@ -233,12 +222,7 @@ class QuantDecoder:
         self.launches_per_step = 0
         check(Lb.amqb_embed(ptr(self.tokens), ptr(self.embed), ptr(self.h), self.B, self.H, st), "embed")
         self.launches_per_step += 1
-        if self.persistent:
-            check(Lb.amqb_decode_layers(ctypes.byref(self._mega_shape), ptr(self._layer_table), ptr(self.h), ptr(self.qkv),
-                                        ptr(self.attn), ptr(self.gu), ptr(self.pos), ptr(self.rope), ptr(self._mega_bar),
-                                        ptr(self.mega_err), int(self.pdl), st), "decode_layers")
-            self.launches_per_step += 1
-        for P in (() if self.persistent else self._plan):
+        for P in self._plan:
             L = P["L"]
             self._gemv(P["qkv"], 3)
             check(Lb.amqb_attn_decode_split(ptr(self.qkv), ptr(L["k_cache"]), ptr(L["v_cache"]), ptr(self.attn), ptr(self.pos),
@@ -263,19 +247,30 @@ class QuantDecoder:
         self.launches_per_step += 2
 
     def _long_context(self) -> bool:
-        return self.attn_splits > 1 and not self.persistent and self._pos_h >= self.attn_split_min_pos
+        return self.attn_splits > 1 and self._pos_h >= self.attn_split_min_pos
 
-    def _capture(self, host_in: Optional[torch.Tensor] = None, host_out: Optional[torch.Tensor] = None, splits: int = 1):
+    def _check_room(self, steps: int = 1) -> None:
+        """The attention kernels index the K/V cache and the rope table straight from the device-side position: refuse a
+        step that would run past max_seq instead of writing past the cache."""
+        if self._pos_h + steps > self.max_seq:
+            raise RuntimeError(f"QuantDecoder: position {self._pos_h} + {steps} step(s) exceeds max_seq {self.max_seq}")
+
+    def _capture(self, host_in: Optional[torch.Tensor] = None, host_out: Optional[torch.Tensor] = None, splits: int = 1,
+                 stream: Optional[torch.cuda.Stream] = None, warm: bool = True):
+        """warm=False: the caller has already run the step eagerly (tp.LocalTPGroup warms all emulated ranks together:
+        a rank's step cannot finish before its peers' steps have been launched)."""
+        self._check_room(2)                         # the warm-up below runs two real steps from the current position
         lib().amqb_set_pdl(int(self.pdl))
         self._cur_splits = splits
-        s = torch.cuda.Stream(device=self.dev)
+        s = stream if stream is not None else torch.cuda.Stream(device=self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(s):
-            saved_pos, saved_tok = self.pos.clone(), self.tokens.clone()
-            for _ in range(2):                      # warm-up outside capture (lazy module loads, attributes)
-                self._step_launches()
-            self.pos.copy_(saved_pos)               # the step advances position and input ids itself: undo the warm-up's
-            self.tokens.copy_(saved_tok)
+            if warm:
+                saved_pos, saved_tok = self.pos.clone(), self.tokens.clone()
+                for _ in range(2):                  # warm-up outside capture (lazy module loads, attributes)
+                    self._step_launches()
+                self.pos.copy_(saved_pos)           # the step advances position and input ids itself: undo the warm-up's
+                self.tokens.copy_(saved_tok)
             s.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=s):
@@ -293,13 +288,14 @@ class QuantDecoder:
         """Capture one decode step (+ feeding the argmax back as the next input, + position advance)
         into a CUDA graph; when the cache can grow past the split threshold, a second one with the split attention grid."""
         self.graph = self._capture()
-        if self.attn_splits > 1 and not self.persistent and self.max_seq > self.attn_split_min_pos:
+        if self.attn_splits > 1 and self.max_seq > self.attn_split_min_pos:
             self.graph_long = self._capture(splits=self.attn_splits)
 
     def step(self) -> None:
         """One token for every sequence of the batch: replay the captured graph."""
         if self.graph is None:
             self.capture()
+        self._check_room()
         (self.graph_long if (self.graph_long is not None and self._long_context()) else self.graph).replay()
         self._pos_h += 1
 
@@ -315,14 +311,16 @@ class QuantDecoder:
         key = (host_in.data_ptr(), host_out.data_ptr())
         if getattr(self, "_io_key", None) != key:
             self._io_graphs, self._io_key = {False: self._capture(host_in, host_out)}, key
-            if self.attn_splits > 1 and not self.persistent and self.max_seq > self.attn_split_min_pos:
+            if self.attn_splits > 1 and self.max_seq > self.attn_split_min_pos:
                 self._io_graphs[True] = self._capture(host_in, host_out, splits=self.attn_splits)
             self._io_bufs = (host_in, host_out)                         # keep the captured addresses alive
+        self._check_room()
         self._io_graphs[self._long_context() and True in self._io_graphs].replay()
         self._pos_h += 1
         torch.cuda.current_stream(self.dev).synchronize()
 
     def step_eager(self) -> None:
+        self._check_room()
         lib().amqb_set_pdl(0)
         saved = self.pdl
         self.pdl = False

@@ -3,6 +3,7 @@ and pass raw device pointers + the current CUDA stream; the library allocates no
 from __future__ import annotations
 
 import ctypes
+import functools
 from typing import Dict, Optional, Sequence, Tuple
 
 import torch
@@ -12,6 +13,22 @@ from ._lib import GemvProblem, check, cur_stream, lib, ptr
 
 GROUP = 128
 _workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
+
+
+def _on_device(fn):
+    """Run the op with the device of its first CUDA tensor argument current: the launch stream, the workspace and
+    the library's per-device state all follow the TENSORS, not whatever device happens to be current (the reference
+    guards the same way, OptionalCUDAGuard(device_of(vec)), auto_gptq_kernel.cu:448)."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        for v in list(args) + list(kwargs.values()):
+            if isinstance(v, torch.Tensor) and v.is_cuda:
+                if v.device.index == torch.cuda.current_device():
+                    break
+                with torch.cuda.device(v.device):
+                    return fn(*args, **kwargs)
+        return fn(*args, **kwargs)
+    return wrapper
 
 
 def native_supported(bits: int, N: int, K: int, G: int) -> bool:
@@ -45,6 +62,7 @@ def _req_cuda(*ts: Optional[torch.Tensor]) -> None:
 
 
 # ------------------------------------------------------------------ layout transcoders
+@_on_device
 def unpack_codes(packed: torch.Tensor, bits: int, layout: int, N: int, K: int, G: int = GROUP) -> torch.Tensor:
     _req_cuda(packed)
     out = torch.empty((N, K), dtype=torch.uint8, device=packed.device)
@@ -52,38 +70,44 @@ def unpack_codes(packed: torch.Tensor, bits: int, layout: int, N: int, K: int, G
     return out
 
 
+@_on_device
 def repack_gptq(bits: int, qweight: torch.Tensor, scales: torch.Tensor, zeros: torch.Tensor,
                 N: int, K: int, G: int = GROUP) -> torch.Tensor:
     _req_cuda(qweight, scales, zeros)
     nat = torch.empty(native_bytes(bits, N, K), dtype=torch.uint8, device=qweight.device)
     scratch = torch.empty((N, K), dtype=torch.uint8, device=qweight.device)
-    check(lib().amqb_repack_gptq(bits, ptr(qweight), ptr(scales.float().contiguous()), ptr(zeros.float().contiguous()),
-                                 ptr(nat), ptr(scratch), N, K, G, cur_stream()), "repack_gptq")
+    # converted copies are bound to locals: a temporary inside the call expression is freed as soon as ptr() returns
+    # and the caching allocator hands the same block to the next same-sized temporary
+    qw, sc, zs = qweight.contiguous(), scales.float().contiguous(), zeros.float().contiguous()
+    check(lib().amqb_repack_gptq(bits, ptr(qw), ptr(sc), ptr(zs), ptr(nat), ptr(scratch), N, K, G, cur_stream()), "repack_gptq")
     return nat
 
 
+@_on_device
 def repack_ft(qweight: torch.Tensor, scales: torch.Tensor, scaled_zeros: torch.Tensor,
               N: int, K: int, G: int = GROUP) -> torch.Tensor:
     _req_cuda(qweight, scales, scaled_zeros)
     nat = torch.empty(native_bytes(4, N, K), dtype=torch.uint8, device=qweight.device)
     scratch = torch.empty((N, K), dtype=torch.uint8, device=qweight.device)
-    check(lib().amqb_repack_ft(ptr(qweight), ptr(scales.half().contiguous()), ptr(scaled_zeros.half().contiguous()),
-                               ptr(nat), ptr(scratch), N, K, G, cur_stream()), "repack_ft")
+    qw, sc, zs = qweight.contiguous(), scales.half().contiguous(), scaled_zeros.half().contiguous()
+    check(lib().amqb_repack_ft(ptr(qw), ptr(sc), ptr(zs), ptr(nat), ptr(scratch), N, K, G, cur_stream()), "repack_ft")
     return nat
 
 
+@_on_device
 def pack_native(bits: int, codes: torch.Tensor, scale: torch.Tensor, zero: torch.Tensor,
                 zero_is_scaled: bool = False, G: int = GROUP) -> torch.Tensor:
     """codes u8 [N,K]; scale/zero fp16 [N, K/G] (HQQ meta; W = (q - zero) * scale)."""
     _req_cuda(codes, scale, zero)
     N, K = codes.shape
     nat = torch.empty(native_bytes(bits, N, K), dtype=torch.uint8, device=codes.device)
-    check(lib().amqb_pack_native(bits, ptr(codes.contiguous()), ptr(scale.half().contiguous()),
-                                 ptr(zero.half().contiguous()), int(zero_is_scaled), ptr(nat), N, K, G, cur_stream()),
+    cd, sc, zr = codes.contiguous(), scale.half().contiguous(), zero.half().contiguous()
+    check(lib().amqb_pack_native(bits, ptr(cd), ptr(sc), ptr(zr), int(zero_is_scaled), ptr(nat), N, K, G, cur_stream()),
           "pack_native")
     return nat
 
 
+@_on_device
 def gptq_pack(bits: int, W: torch.Tensor, scales: torch.Tensor, zeros: torch.Tensor, G: int):
     """GPTQLinear.pack on the GPU. W fp16 [N,K]; scales/zeros [N,K/G] -> (qweight, scales_f32, zeros_f32)."""
     _req_cuda(W, scales, zeros)
@@ -91,20 +115,21 @@ def gptq_pack(bits: int, W: torch.Tensor, scales: torch.Tensor, zeros: torch.Ten
     qweight = torch.empty((K // 32 * bits, N), dtype=torch.int32, device=W.device)
     s_out = torch.empty((K // G, N), dtype=torch.float32, device=W.device)
     z_out = torch.empty((K // G, N), dtype=torch.float32, device=W.device)
-    check(lib().amqb_gptq_pack(bits, ptr(W.half().contiguous()), ptr(scales.half().contiguous()),
-                               ptr(zeros.half().contiguous()), ptr(qweight), ptr(s_out), ptr(z_out), N, K, G,
+    Wh, sc, zr = W.half().contiguous(), scales.half().contiguous(), zeros.half().contiguous()
+    check(lib().amqb_gptq_pack(bits, ptr(Wh), ptr(sc), ptr(zr), ptr(qweight), ptr(s_out), ptr(z_out), N, K, G,
                                cur_stream()), "gptq_pack")
     return qweight, s_out, z_out
 
 
+@_on_device
 def ft_pack(W: torch.Tensor, scales: torch.Tensor, zeros: torch.Tensor, G: int):
     _req_cuda(W, scales, zeros)
     N, K = W.shape
     qweight = torch.empty((N // 4, K), dtype=torch.int16, device=W.device)
     s_out = torch.empty((K // G, N), dtype=torch.float16, device=W.device)
     z_out = torch.empty((K // G, N), dtype=torch.float16, device=W.device)
-    check(lib().amqb_ft_pack(ptr(W.half().contiguous()), ptr(scales.half().contiguous()), ptr(zeros.half().contiguous()),
-                             ptr(qweight), ptr(s_out), ptr(z_out), N, K, G, cur_stream()), "ft_pack")
+    Wh, sc, zr = W.half().contiguous(), scales.half().contiguous(), zeros.half().contiguous()
+    check(lib().amqb_ft_pack(ptr(Wh), ptr(sc), ptr(zr), ptr(qweight), ptr(s_out), ptr(z_out), N, K, G, cur_stream()), "ft_pack")
     return qweight, s_out, z_out
 
 
@@ -135,6 +160,7 @@ def gemv_grouped(problems: Sequence[GemvProblem], ws: torch.Tensor, pdl: bool = 
           "gemv_grouped")
 
 
+@_on_device
 def gemv(bits: int, w_native: torch.Tensor, x: torch.Tensor, N: int, K: int,
          bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """y fp16 [M,N] = x[M,K] @ dequant(W)^T (+bias), M <= 16, through amqb_gemv_w{2,3,4}."""
@@ -151,6 +177,7 @@ def gemv(bits: int, w_native: torch.Tensor, x: torch.Tensor, N: int, K: int,
     return y
 
 
+@_on_device
 def gemv_gptq_layout(bits: int, qweight: torch.Tensor, scales: torch.Tensor, zeros: torch.Tensor, x: torch.Tensor,
                      N: int, K: int, G: int, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     _req_cuda(qweight, scales, zeros, x)
@@ -178,6 +205,7 @@ def gemm_workspace(M: int, K: int, bits: int, device) -> torch.Tensor:
     return torch.empty(max(need, 256), dtype=torch.uint8, device=device)
 
 
+@_on_device
 def gemm_tc(bits: int, w_native: torch.Tensor, x: torch.Tensor, N: int, K: int,
             bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
             workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -197,15 +225,17 @@ def gemm_tc(bits: int, w_native: torch.Tensor, x: torch.Tensor, N: int, K: int,
 
 
 # ------------------------------------------------------------------ HQQ proxy ops
+@_on_device
 def hqq_dequant(bits: int, W_q: torch.Tensor, scale: torch.Tensor, zero: torch.Tensor, N: int, K: int,
                 G: int = GROUP) -> torch.Tensor:
     _req_cuda(W_q, scale, zero)
     out = torch.empty((N, K), dtype=torch.float16, device=W_q.device)
-    check(lib().amqb_hqq_dequant(bits, ptr(W_q), ptr(scale.half().contiguous()), ptr(zero.half().contiguous()),
-                                 ptr(out), N, K, G, cur_stream()), "hqq_dequant")
+    wq, sc, zr = W_q.contiguous(), scale.half().contiguous(), zero.half().contiguous()
+    check(lib().amqb_hqq_dequant(bits, ptr(wq), ptr(sc), ptr(zr), ptr(out), N, K, G, cur_stream()), "hqq_dequant")
     return out
 
 
+@_on_device
 def hqq_pack(bits: int, codes: torch.Tensor) -> torch.Tensor:
     _req_cuda(codes)
     R, G = codes.shape
@@ -213,20 +243,24 @@ def hqq_pack(bits: int, codes: torch.Tensor) -> torch.Tensor:
         out = torch.empty(((R + 9) // 10, G), dtype=torch.int32, device=codes.device)
     else:
         out = torch.empty((R // (2 if bits == 4 else 4), G), dtype=torch.uint8, device=codes.device)
-    check(lib().amqb_hqq_pack(bits, ptr(codes.to(torch.uint8).contiguous()), ptr(out), R, G, cur_stream()), "hqq_pack")
+    cd = codes.to(torch.uint8).contiguous()
+    check(lib().amqb_hqq_pack(bits, ptr(cd), ptr(out), R, G, cur_stream()), "hqq_pack")
     return out
 
 
+@_on_device
 def hqq_unpack(bits: int, W_q: torch.Tensor, R: Optional[int] = None) -> torch.Tensor:
     _req_cuda(W_q)
     step, G = W_q.shape
     p = {4: 2, 2: 4, 3: 10}[bits]
     Rfull = step * p
     out = torch.empty((Rfull, G), dtype=torch.uint8, device=W_q.device)
-    check(lib().amqb_hqq_unpack(bits, ptr(W_q.contiguous()), ptr(out), Rfull, G, cur_stream()), "hqq_unpack")
+    wq = W_q.contiguous()
+    check(lib().amqb_hqq_unpack(bits, ptr(wq), ptr(out), Rfull, G, cur_stream()), "hqq_unpack")
     return out if R is None else out[:R]
 
 
+@_on_device
 def hqq_quantize(W: torch.Tensor, bits: int, G: int = GROUP, round_zero: Optional[bool] = None):
     """Quantizer.quantize (axis=1) -> (codes u8 [R,G], scale fp32 [R,1], zero fp32 [R,1], iters)."""
     _req_cuda(W)
@@ -241,11 +275,13 @@ def hqq_quantize(W: torch.Tensor, bits: int, G: int = GROUP, round_zero: Optiona
     iters = torch.zeros(1, dtype=torch.int32, device=W.device)
     need = int(L.amqb_hqq_quantize_workspace_bytes(N, K, G))
     wsb = torch.zeros(max(need, 16), dtype=torch.uint8, device=W.device)
-    check(L.amqb_hqq_quantize(bits, ptr(W.half().contiguous()), ptr(codes), ptr(scale), ptr(zero), int(round_zero),
+    Wh = W.half().contiguous()
+    check(L.amqb_hqq_quantize(bits, ptr(Wh), ptr(codes), ptr(scale), ptr(zero), int(round_zero),
                               N, K, G, ptr(wsb), ctypes.c_size_t(wsb.numel()), ptr(iters), cur_stream()), "hqq_quantize")
     return codes, scale, zero, iters
 
 
+@_on_device
 def native_to_dense(bits: int, w_native: torch.Tensor, N: int, K: int) -> torch.Tensor:
     """fp32 [N, K] weights a native buffer encodes: scale * q - zero*scale (test / debugging aid)."""
     codes = unpack_codes(w_native, bits, _lib.LAYOUT_NATIVE, N, K, GROUP).float()

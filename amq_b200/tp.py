@@ -92,10 +92,115 @@ class PeerAllReduce:
         import torch.distributed as dist
         dist.barrier()
 
+    def close(self) -> None:
+        """Unmap the peers' buffers and free this rank's (after every rank is done with them)."""
+        from ._lib import lib
+        if getattr(self, "_mine", None) is None:
+            return
+        torch.cuda.synchronize()
+        L = lib()
+        for p in self._opened:
+            L.amqb_ar_close(p)
+        self._opened = []
+        L.amqb_ar_free(self._mine)
+        self._mine = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     def __call__(self, partial: torch.Tensor, h: torch.Tensor) -> None:
         from ._lib import check, cur_stream, lib, ptr
         check(lib().amqb_allreduce_f16(self._peers, self.rank, self.world, ptr(partial), ptr(h), ptr(h), partial.numel(),
                                        self.max_elems, int(self.pdl), cur_stream()), "allreduce")
+
+
+class LocalAllReduce:
+    """PeerAllReduce for emulated ranks that live in ONE process on ONE device (tp.LocalTPGroup): the exchange buffers
+    are plain device tensors of this process, so the "peer" pointers need no IPC mapping.  Same kernel."""
+
+    def __init__(self, rank: int, world: int, max_elems: int, bufs: List[torch.Tensor], pdl: bool = True):
+        self.rank, self.world, self.max_elems, self.pdl = rank, world, max_elems, pdl
+        self._bufs = bufs
+        self._peers = (ctypes.c_void_p * world)(*[ctypes.c_void_p(b.data_ptr()) for b in bufs])
+
+    def __call__(self, partial: torch.Tensor, h: torch.Tensor) -> None:
+        from ._lib import check, cur_stream, lib, ptr
+        check(lib().amqb_allreduce_f16(self._peers, self.rank, self.world, ptr(partial), ptr(h), ptr(h), partial.numel(),
+                                       self.max_elems, int(self.pdl), cur_stream()), "allreduce")
+
+
+class LocalTPGroup:
+    """`world` tensor-parallel ranks emulated in one process on one device, one stream per rank: every rank runs its
+    own captured decode step (its shard of the weights, its heads' K/V cache) and the all-reduces meet through device
+    memory exactly as they do through NVLink-mapped peer memory.  What it is for: model-level parity of the sharded
+    decoder on a single-GPU box (tests/test_gpu_tp.py) — the driver's test box has one GPU."""
+
+    def __init__(self, full, world: int, max_seq: Optional[int] = None, pdl: bool = True):
+        from ._lib import lib
+        from .model import QuantDecoder
+        self.full, self.world = full, world
+        dev = full.dev
+        shard_plan(full.shape, world)
+        nbytes = int(lib().amqb_ar_buffer_bytes(full.shape.hidden * full.B, world))
+        self._bufs = [torch.zeros(nbytes, dtype=torch.uint8, device=dev) for _ in range(world)]
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(world)]
+        self.ranks = []
+        for r in range(world):
+            m = QuantDecoder(full.shape, full.arch, batch=full.B, max_seq=max_seq or full.max_seq, device=str(dev), seed=0,
+                             n_block=full.n_block, pdl=pdl, tp_rank=r, tp_world=world)
+            m.adopt_shard_of(full)
+            m.allreduce = LocalAllReduce(r, world, full.shape.hidden * full.B, self._bufs, pdl=pdl)
+            self.ranks.append(m)
+        self._captured = False
+
+    def set_tokens(self, tok: torch.Tensor) -> None:
+        for m in self.ranks:
+            m.reset()
+            m.tokens.copy_(tok)
+        torch.cuda.synchronize()
+
+    def _each(self, fn) -> None:
+        cur = torch.cuda.current_stream()
+        for s, m in zip(self.streams, self.ranks):
+            s.wait_stream(cur)
+            with torch.cuda.stream(s):
+                fn(m)
+        for s in self.streams:
+            cur.wait_stream(s)
+
+    def step_eager(self) -> None:
+        """All ranks' launches are issued (asynchronously) before anything is waited for: a rank's all-reduce spins
+        until its peers' partial sums arrive."""
+        def go(m):
+            m.step_eager()
+        self._each(go)
+
+    def capture(self) -> None:
+        saved = [(m.pos.clone(), m.tokens.clone(), m._pos_h) for m in self.ranks]
+        for _ in range(2):
+            self.step_eager()
+        torch.cuda.synchronize()
+        for m, (p, t, ph) in zip(self.ranks, saved):
+            m.pos.copy_(p)
+            m.tokens.copy_(t)
+            m._pos_h = ph
+        torch.cuda.synchronize()
+        for s, m in zip(self.streams, self.ranks):
+            m.graph = m._capture(stream=s, warm=False)
+        self._captured = True
+
+    def step(self) -> None:
+        if not self._captured:
+            self.capture()
+
+        def go(m):
+            m._check_room()
+            m.graph.replay()
+            m._pos_h += 1
+        self._each(go)
 
 
 class NcclAllReduce:
@@ -110,66 +215,107 @@ class NcclAllReduce:
         h.add_(partial)
 
 
-def bench_main(args) -> None:
-    """bench.py --workload llama70b-tp: Llama-2-70B random-init, AMQ avg 3.0 bits, batch-1 decode,
-    tensor-parallel over --gpus ranks (strong scaling: same model, 1/tp of the weights per GPU)."""
+def _peak_gbs() -> float:
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"])
+    return 6650.0
+
+
+def measure_tp70b(steps: int, warmup: int, world: int, rank: int, local: int, tp: Optional[int] = None) -> Optional[dict]:
+    """Config 5: Llama-2-70B random-init, AMQ avg 3.0 bits, batch-1 decode, tensor-parallel over `tp` ranks of the
+    already initialised process group (tp = 1: rank 0 alone, no collective).  CUDA-graph replay, CUDA events, max over
+    the participating ranks.  Returns the record on rank 0, None elsewhere."""
     import torch.distributed as dist
     from .model import QuantDecoder
+    tp = world if tp is None else tp
+    shape = MODELS["Llama-2-70b-hf"]
+    arch = sample_arch(shape, 3.0, seed=0)
+    shard_plan(shape, tp)
+    n_block = int(os.environ.get("AMQB_BLOCKS", shape.n_block))
+    ar_kind = os.environ.get("AMQB_AR", "amqb") if tp > 1 else "none"
+    ms, lps, by = 0.0, 0, None
+    if rank < tp:
+        model = QuantDecoder(shape, arch, batch=1, max_seq=max(256, warmup + steps + 8), device=f"cuda:{local}",
+                             seed=0, n_block=n_block, tp_rank=rank, tp_world=tp)
+        if tp > 1:
+            model.allreduce = PeerAllReduce(rank, tp, shape.hidden) if ar_kind == "amqb" else NcclAllReduce()
+        model.capture()
+        lps = model.launches_per_step
+        by = model.algorithmic_bytes_per_token()
+        model.reset()
+        model.tokens.fill_(1)
+        for _ in range(warmup):
+            model.step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if rank < tp:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            model.step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+    if world > 1:
+        dist.barrier()
+        t = torch.tensor([ms], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    if rank < tp:
+        if tp > 1 and ar_kind == "amqb":
+            model.allreduce.close()
+        del model
+        torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    peak = _peak_gbs()
+    return {"tok_s": steps / (ms * 1e-3), "ms_per_step": ms / steps, "tp": tp, "steps": steps, "warmup": warmup,
+            "model": f"{shape.name} random-init ({n_block} blocks), AMQ avg 3.0 bits, batch-1 decode",
+            "allreduce": ar_kind, "allreduces_per_step": 2 * n_block if tp > 1 else 0,
+            "allreduce_algorithmic_bytes": 2 * shape.hidden, "launches_per_step": lps,
+            "per_gpu_weight_bytes": by["total"],
+            "frac_of_hbm_roofline_per_gpu": (by["total"] / (peak * 1e9)) / (ms / steps * 1e-3)}
+
+
+def nccl_log_summary(path_glob: str) -> dict:
+    """What NCCL itself logged about the communicator (NCCL_DEBUG=INFO redirected to NCCL_DEBUG_FILE by bench.py)."""
+    import glob
+    import re
+    out = {"comm_nranks": None, "nvls": False, "p2p": False}
+    for fn in glob.glob(path_glob):
+        try:
+            txt = open(fn, errors="replace").read()
+        except OSError:
+            continue
+        m = re.search(r"nranks (\d+)", txt)
+        if m:
+            out["comm_nranks"] = max(int(m.group(1)), out["comm_nranks"] or 0)
+        out["nvls"] = out["nvls"] or ("NVLS" in txt)
+        out["p2p"] = out["p2p"] or ("P2P" in txt or "via P2P" in txt)
+    return out
+
+
+def bench_main(args) -> None:
+    """bench.py --workload llama70b-tp: config 5 alone, tensor-parallel over --gpus ranks (strong scaling: same model,
+    1/tp of the weights per GPU)."""
+    import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    shape = MODELS["Llama-2-70b-hf"]
-    arch = sample_arch(shape, 3.0, seed=0)
-    shard_plan(shape, world)
-    n_block = int(os.environ.get("AMQB_BLOCKS", shape.n_block))
-    model = QuantDecoder(shape, arch, batch=1, max_seq=max(256, args.warmup + args.steps + 8), device=f"cuda:{local}",
-                         seed=0, n_block=n_block, tp_rank=rank, tp_world=world)
-    ar_kind = os.environ.get("AMQB_AR", "amqb")
-    if world > 1:
-        model.allreduce = PeerAllReduce(rank, world, shape.hidden) if ar_kind == "amqb" else NcclAllReduce()
-    model.capture()
-    lps = model.launches_per_step
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    model.reset()
-    model.tokens.fill_(1)
-    for _ in range(args.warmup):
-        model.step()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        model.step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=f"cuda:{local}", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t[0])
+    rec = measure_tp70b(args.steps, args.warmup, world, rank, local)
     if rank == 0:
-        by = model.algorithmic_bytes_per_token()
-        peak = 6549.4
-        p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
-        if os.path.exists(p):
-            peak = float(json.load(open(p))["hbm_gbs"])
-        tok_s = args.steps / (ms * 1e-3)
         print(json.dumps({
-            "metric": "batch-1 decode tok/s, Llama-2 70B AMQ 3-bit avg, tensor parallel", "value": tok_s, "unit": "tok/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "metric": "batch-1 decode tok/s, Llama-2 70B AMQ 3-bit avg, tensor parallel", "value": rec["tok_s"], "unit": "tok/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": rec["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16 (fp32 accumulate)",
-            "data": "synthetic",
-            "config": {"workload": f"{shape.name} random-init ({n_block} blocks), AMQ avg 3.0 bits, batch-1 decode, tp={world}",
-                       "allreduce": ar_kind if world > 1 else "none", "launches_per_step": lps,
-                       "per_gpu_weight_bytes": by["total"],
-                       "frac_of_hbm_roofline_per_gpu": (by["total"] / (peak * 1e9)) / (ms / args.steps * 1e-3)},
-            "gpu_launches": lps * args.steps}), flush=True)
+            "data": "synthetic", "config": {"workload": rec["model"] + f", tp={world}", **{k: rec[k] for k in (
+                "allreduce", "launches_per_step", "per_gpu_weight_bytes", "frac_of_hbm_roofline_per_gpu")}},
+            "gpu_launches": rec["launches_per_step"] * args.steps}), flush=True)
     if world > 1:
         dist.destroy_process_group()

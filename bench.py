@@ -15,8 +15,11 @@ path (224 quantized linears + glue + fp16 lm_head) over one batch of synthetic i
 * cpu_baseline / --impl reference: the oracle port of the reference's torch dequant+matmul
              (GPTQLinear.forward, kernel_switch_threshold=0) on the host cores, on a bounded sample.
 N > 1: the 7B path does not shard ("replicas only"): every rank decodes its own
-batch-1 stream, no data-path collective, scaling "weak".  `--workload llama70b-tp` runs config 5
-(tensor-parallel 70B) instead.
+batch-1 stream, no data-path collective, scaling "weak".  The only config that shards (config 5:
+Llama-2-70B, tensor parallel over the N ranks the driver launched) is measured in the SAME run and
+reported as the `tp70b` object of the line (tok/s, ms/step, launches/step, fraction of the per-GPU HBM
+roofline, all-reduce kind, strong-scaling efficiency against the tp = 1 number taken in this run,
+what NCCL logged about the communicator); `--workload llama70b-tp` runs config 5 alone.
 """
 from __future__ import annotations
 
@@ -82,7 +85,7 @@ class ClockSampler:
 _CPU_CACHE = {}
 
 
-def cpu_reference_sample(arch, shape, threads: int):
+def cpu_reference_sample(arch, shape, threads: int, tensors=None):
     """The reference's own CPU path on a bounded sample of this workload: ONE q_proj-shaped
     4096x4096 3-bit group-128 linear, batch 1 (BASELINE.json configs[0]) through the oracle port of
     GPTQLinear.forward's torch branch (autogptq.py:245-283: shift-unpack -> fp16 scales*q - zeros ->
@@ -94,12 +97,17 @@ def cpu_reference_sample(arch, shape, threads: int):
     from oracle import amq_oracle as O
     torch.set_num_threads(threads)
     G, N, K, bits = 128, 4096, 4096, 3
+    if tensors is not None:
+        _CPU_CACHE["layer"] = tensors                 # the very tensors the GPU arm streams (run_ours)
     if "layer" not in _CPU_CACHE:
+        # same recipe as the GPU arm's synthetic layers (amq_b200/model.py synthetic_native): uniform random codes,
+        # realistic fp16 scale range for 3 bits, fractional zero, packed into the reference's GPTQ layout
         rs = np.random.RandomState(0)
-        qweight = rs.randint(-2 ** 31, 2 ** 31 - 1, size=(K * bits // 32, N), dtype=np.int64).astype(np.int32)
-        scales = torch.from_numpy(rs.uniform(0.01, 0.02, size=(K // G, N)).astype(np.float32)).half().float()
-        zeros = torch.from_numpy(rs.uniform(0.02, 0.1, size=(K // G, N)).astype(np.float32)).half().float()
-        _CPU_CACHE["layer"] = (torch.randn(1, K).half(), qweight, scales, zeros)
+        codes = rs.randint(0, 2 ** bits, size=(N, K)).astype(np.int64)
+        qweight = O.gptq_pack_codes(codes, bits)
+        scale = torch.from_numpy(rs.uniform(0.010, 0.023, size=(K // G, N)).astype(np.float32)).half()
+        zero = torch.from_numpy(rs.uniform(0.5, 2 ** bits - 1.5, size=(K // G, N)).astype(np.float32)).half()
+        _CPU_CACHE["layer"] = (torch.randn(1, K).half(), qweight, scale.float(), (zero * scale).float())
     x, q, sc, z = _CPU_CACHE["layer"]
     t0 = time.perf_counter()
     O.gptq_forward_torch(x, q, sc, z, bits, G)
@@ -135,6 +143,28 @@ def run_reference(args, shape, arch):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def cpu_sample_from_model(model):
+    """A 4096 x 4096 3-bit linear of the GPU arm's own model (first q/k/v/o projection drawn at 3 bits), brought to the
+    reference's GPTQ layout for the CPU baseline: codes unpacked from the native buffer, fp16 scale / zero*scale read
+    from its records."""
+    import numpy as np
+    import torch
+    from amq_b200 import _lib, ops
+    from oracle import amq_oracle as O
+    for L in model.layers:
+        for name in ("self_attn.q_proj", "self_attn.o_proj", "self_attn.k_proj", "self_attn.v_proj"):
+            bits, nat, N, K = L[name]
+            if bits == 3 and N == 4096 and K == 4096:
+                codes = ops.unpack_codes(nat, bits, _lib.LAYOUT_NATIVE, N, K, 128).cpu().numpy().astype(np.int64)
+                rec = bits * 512 + 128
+                meta = nat.reshape(-1, rec)[:, bits * 512:].contiguous().view(torch.float16).reshape(N // 32, K // 128, 32, 2)
+                scales = meta[..., 0].permute(1, 0, 2).reshape(K // 128, N).float().cpu()
+                zeros = meta[..., 1].permute(1, 0, 2).reshape(K // 128, N).float().cpu()
+                x = model.embed[1:2].float().cpu().half() * 50.0      # an activation row of the model's own embedding scale
+                return (x, O.gptq_pack_codes(codes, bits), scales, zeros)
+    return None
+
+
 def gemv_roofline(model, iters: int = 5):
     """Time one step's worth of decode-GEMV launches alone (same problems, same order, PDL on, CUDA
     graph, events on the launching stream).  The 2.4 GB of packed weights exceed L2 (126 MB)."""
@@ -176,13 +206,20 @@ def run_ours(args, shape, arch):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    nccl_log = None
     if world > 1:
+        # leave NCCL's own logging on (to a file: stdout carries exactly one JSON line) so that the communicator size
+        # and transport it reports can be quoted next to the tensor-parallel numbers
+        nccl_log = f"/tmp/amqb_nccl_{os.getpid()}_%h_%p.log"
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,GRAPH,ENV")
+        os.environ.setdefault("NCCL_DEBUG_FILE", nccl_log)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     B = 1
     model = QuantDecoder(shape, arch, batch=B, max_seq=max(512, args.warmup + 2 * args.steps + 8), device=f"cuda:{local}", seed=rank)
     model.capture()
-    launches_per_step = model.launches_per_step
+    launches_per_step, model_pdl = model.launches_per_step, model.pdl
 
     def barrier():
         if world > 1:
@@ -241,15 +278,41 @@ def run_ours(args, shape, arch):
         g_ms, g_launch, g_bytes = gemv_roofline(model)
         achieved = g_bytes / (g_ms * 1e-3) / 1e9
         bytes_tok = model.algorithmic_bytes_per_token()
-        cpu_runs = [cpu_reference_sample(arch, shape, os.cpu_count() or 1) for _ in range(12)]
+        cpu_tensors = cpu_sample_from_model(model)
+    del model
+    torch.cuda.empty_cache()
+
+    # ---- config 5 in the same run: Llama-2-70B tensor-parallel over the ranks the driver launched (N = 1: one GPU),
+    # plus, at N > 1, the tp = 1 number on rank 0 so that the strong-scaling efficiency is self-contained
+    from amq_b200 import tp as tpmod
+    tp_steps, tp_warm = max(8, min(args.steps, 48)), max(3, min(args.warmup, 6))
+    tp_rec = tp1_rec = None
+    if os.environ.get("AMQB_SKIP_TP70B") != "1":
+        tp_rec = tpmod.measure_tp70b(tp_steps, tp_warm, world, rank, local)
+        if world > 1:
+            tp1_rec = tpmod.measure_tp70b(max(8, tp_steps // 2), tp_warm, world, rank, local, tp=1)
+    if rank == 0 and tp_rec is not None:
+        base = tp1_rec if tp1_rec is not None else tp_rec
+        tp_rec["tp1_tok_s"] = base["tok_s"]
+        tp_rec["strong_scaling_efficiency"] = tp_rec["tok_s"] / (world * base["tok_s"])
+        if nccl_log is not None:
+            tp_rec["nccl"] = tpmod.nccl_log_summary(f"/tmp/amqb_nccl_{os.getpid()}_*.log")
+
+    if rank == 0:
+        cpu_runs = [cpu_reference_sample(arch, shape, os.cpu_count() or 1, cpu_tensors if i == 0 else None) for i in range(12)]
         cpu_desc = cpu_runs[0][1]
         cpu_tok_s = 1.0 / (sum(r[0] for r in cpu_runs[2:]) / len(cpu_runs[2:]))
         tok_s = world * B * args.steps / (ms_dev * 1e-3)
-        traffic = None            # dram bytes per launch (average over one layer's four launches), from the committed ncu capture
-        tp_ = os.path.join(ROOT, "profiles", "r01_ncu_gemv_traffic.json")
-        if os.path.exists(tp_):
-            with open(tp_) as f:
-                traffic = json.load(f).get("traffic_bytes_per_launch_avg")
+        # dram bytes per launch (average over one layer's four launches): NOT measured in this run — read from the
+        # committed `ncu --set full` capture of the same launches (newest round first)
+        traffic, traffic_src = None, None
+        for name in ("r02_ncu_gemv_traffic.json", "r01_ncu_gemv_traffic.json"):
+            tp_ = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(tp_):
+                with open(tp_) as f:
+                    traffic = json.load(f).get("traffic_bytes_per_launch_avg")
+                traffic_src = f"profiles/{name} (ncu --set full capture of one layer's launches; not measured in this run)"
+                break
         line = {
             "metric": "batch-1 decode tok/s, Llama-2 7B AMQ 3-bit avg", "value": tok_s, "unit": "tok/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
@@ -260,17 +323,18 @@ def run_ours(args, shape, arch):
                                    "seed 0; func.py accounting incl. 0.25 b scale/zero), batch-1 decode, group 128",
                        "l2": "inputs larger than L2: every step streams %.2f GB of packed weights + fp16 lm_head" % (bytes_tok["total"] / 1e9),
                        "parallelism": "replicas only (no data-path collective)" if world > 1 else "single GPU",
-                       "launches_per_step": launches_per_step, "cuda_graph": True, "pdl": model.pdl},
+                       "launches_per_step": launches_per_step, "cuda_graph": True, "pdl": model_pdl},
             "clocks": clocks,
             "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "tok/s",
                     "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 8 * B},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "algorithmic_bytes_per_launch": g_bytes / g_launch, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": g_bytes / g_launch, "peak_source": peak_src,
                          "kernel": "gemv_mma_kernel<MB,kind,prologue> (IMMA decode GEMV family, %d launches per step)" % g_launch,
                          "algorithmic_bytes_per_step": g_bytes, "avg_launch_us": g_ms * 1e3 / g_launch,
                          "step_frac_of_weight_roofline": (bytes_tok["total"] / (peak * 1e9)) / (ms_dev / args.steps * 1e-3)},
             "cpu_baseline": {"value": cpu_tok_s, "unit": "tok/s", "cores": os.cpu_count(), "kind": "port", "sample": cpu_desc},
+            "tp70b": tp_rec,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -202,40 +202,6 @@ int amqb_attn_prefill(void* q_f16, const void* k_f16, const void* v_f16, void* k
                       int pos0, int T, int B, int Hq, int Hkv, int D, int max_seq, const float* rope_cos_sin,
                       void* stream);
 
-/* ---- persistent decode kernel: every decoder layer of one batch-1 token in ONE launch --------
- * Replaces the chain of ~5 dependent launches per layer that amq_speed_benchmark.py times
- * (amq/utils/speed.py:23-46 over the modules of hqq/backends/{autogptq,ft}.py): one CTA per SM stays
- * resident, the weight stream never stops at a layer boundary, phases are separated by grid-wide
- * counters instead of kernel boundaries (csrc/decode_mega.cu).  Batch 1, single GPU, D in {64, 128},
- * hidden / inter / Hq*D multiples of 128; AMQB_ERR_UNSUPPORTED_SHAPE otherwise (use the per-linear
- * launches).  Linear order in a layer: q, k, v, o, gate, up, down. */
-typedef struct {
-  const void* w_native;     /* amqb_native_bytes(bits, N, K) bytes */
-  const void* bias;         /* fp16 [N] or NULL */
-  int bits;                 /* 2, 3 or 4 */
-  int reserved;
-} amqb_mega_linear;
-typedef struct {
-  amqb_mega_linear lin[7];
-  const void* norm1;        /* fp16 [hidden] input RMSNorm weight */
-  const void* norm2;        /* fp16 [hidden] post-attention RMSNorm weight */
-  void* k_cache;            /* fp16 [Hkv, max_seq, D] */
-  void* v_cache;
-  long long reserved;
-} amqb_mega_layer;           /* 208 bytes; an array of n_layers of them in DEVICE memory */
-typedef struct {
-  int hidden, inter, Hq, Hkv, D, max_seq, n_layers;
-  float eps, rope_theta;
-} amqb_mega_shape;
-size_t amqb_decode_layers_barrier_bytes(int n_layers);
-/* h: fp16 [hidden] residual stream (in: embedding of the token, out: input of the final norm).
- * qkv / attn / gu: fp16 scratch of (Hq+2*Hkv)*D, Hq*D, 2*inter elements.  barrier_dev:
- * amqb_decode_layers_barrier_bytes() bytes (zeroed by the call); err_dev: device int, set non-zero if
- * a grid-wide wait timed out (never in a correct run).  Graph-capturable. */
-int amqb_decode_layers(const amqb_mega_shape* shape_host, const amqb_mega_layer* layers_dev,
-                       void* h, void* qkv, void* attn, void* gu, const int* pos_dev,
-                       const float* rope_cos_sin, void* barrier_dev, int* err_dev, int pdl, void* stream);
-
 /* ---- tensor parallel (config 5): one-shot all-reduce over NVLink peer memory ------------- */
 /* Exchange buffers are the one thing this library allocates itself, explicitly (cudaMalloc, so the
  * block can be exported through CUDA IPC): create with amqb_ar_alloc, hand the 64-byte handle to

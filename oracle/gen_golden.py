@@ -38,6 +38,29 @@ def import_reference():
     return BitPack, Quantizer, BaseQuantizeConfig, GPTQLinear, pack_intweight
 
 
+def hqqlinear_state_fixtures(out_dir, report):
+    """A state dict WRITTEN BY THE REFERENCE's HQQLinear (quantize.py:643-682), in both forms the reference produces:
+    encoded (the default: every non-tensor entry as a tensor, core/utils.py:37-69) and plain (what
+    BaseHQQModel.serialize_weights stores in qmodel.pt, models/base.py:405-422), plus the reference's own forward on it."""
+    import torch.nn as nn
+    from hqq.core.quantize import HQQLinear, BaseQuantizeConfig
+    for nbits in (2, 3, 4):
+        torch.manual_seed(50 + nbits)
+        lin = nn.Linear(256, 64, bias=(nbits != 2)).half()
+        lin.weight.data = (torch.randn(64, 256) * 0.02).half()
+        layer = HQQLinear(lin, BaseQuantizeConfig(nbits=nbits, group_size=128), compute_dtype=torch.float16, device="cpu")
+        enc = {k: (v.data.clone() if isinstance(v, torch.Tensor) else v) for k, v in layer.state_dict().items()}
+        layer.encoded_state_dict = False
+        plain = {k: (v.data.clone() if isinstance(v, torch.Tensor) else v) for k, v in layer.state_dict().items()}
+        torch.manual_seed(3)
+        x = torch.randn(5, 256).half()
+        y = layer.forward_pytorch(x)
+        y32 = x.float() @ layer.dequantize().float().t() + (layer.bias.float() if layer.bias is not None else 0.0)
+        torch.save({"encoded": enc, "plain": plain, "x": x, "y_ref_fp16": y, "y_fp32": y32, "W_deq": layer.dequantize()},
+                   os.path.join(out_dir, f"hqqlinear_state_{nbits}bit.pt"))
+    report.append("HQQLinear state dicts (encoded + plain) written by the reference")
+
+
 def main():
     from oracle import amq_oracle as O
     BitPack, Quantizer, BaseQuantizeConfig, GPTQLinear, pack_intweight = import_reference()
@@ -126,6 +149,8 @@ def main():
                 gptq_qweight=layer.qweight.numpy(), gptq_scales=layer.scales.numpy(),
                 gptq_zeros=layer.zeros.numpy(), solver_iters=np.int32(n_it), **fx, **extra)
     report.append("quantize/dequant/gptq/ft ok")
+
+    hqqlinear_state_fixtures(out_dir, report)
 
     # ---- 3. arch selection rule (amq_speed_benchmark.py:209-229) on a synthetic stats file
     import json

@@ -125,15 +125,14 @@ def test_hqqlinear_fused_backend(amq, bits):
         ref = x.float() @ W.t() + hq.bias.float()
         assert y.shape == x.shape[:-1] + (N,) and y.dtype == torch.float16
         assert O.max_rel(y.reshape(-1, N).cpu(), ref.reshape(-1, N).cpu()) <= 1e-3
-        amq.HQQLinear.set_backend("pytorch")
-        try:
-            y_pt = hq(x)
-        finally:
-            amq.HQQLinear.set_backend("fused")
+        # the reference's own form: x @ dequantize().T + bias in fp16 (quantize.py:893-898), computed here by the test
+        y_pt = torch.matmul(x, hq.dequantize().t()) + hq.bias
         assert O.max_rel(y.reshape(-1, N).cpu(), y_pt.reshape(-1, N).float().cpu()) <= 2e-3
+    amq.HQQLinear.set_backend("pytorch")                   # reference backend names are accepted and map onto the fused kernels
+    assert amq.HQQLinear.backend == "fused"
     with pytest.raises(ValueError):
-        amq.HQQLinear.set_backend("aten")
-    # a shape the kernel does not take (N % 32 != 0): falls to the dequantise + matmul backend, still correct
+        amq.HQQLinear.set_backend("no-such-backend")
+    # a shape the native record grid does not take (N % 32 != 0): converted once to the GPTQ layout, any-shape kernel
     hq48 = amq.HQQLinear(nn.Linear(256, 48, bias=False).half(), amq.BaseQuantizeConfig(nbits=bits, group_size=G),
                          compute_dtype=torch.float16, device="cuda")
     assert hq48.native_weight() is None

@@ -59,6 +59,30 @@ ar(pad, out)
 torch.cuda.synchronize()
 full = O.gptq_forward_fp32(x, qw.numpy(), sc, ze, bits, 128).reshape(-1)
 assert O.max_rel(out[:N].cpu(), full) <= 2e-3, O.max_rel(out[:N].cpu(), full)
+# 3. model level: the sharded decoder (every rank adopts its shard of the SAME full model) against the unsharded one
+from amq_b200.arch import ModelShape, LINEARS
+from amq_b200.model import QuantDecoder
+shape = ModelShape("tiny-gqa", 512, 1024, 8, 4, 2, 512, head_dim=64)
+rs = np.random.RandomState(3)
+arch = {n: rs.choice([2, 3, 4], size=2).tolist() for n in LINEARS}
+full = QuantDecoder(shape, arch, batch=1, max_seq=32, device=f"cuda:{local}", seed=11)
+for kind in ("amqb", "nccl"):
+    m = QuantDecoder(shape, arch, batch=1, max_seq=32, device=f"cuda:{local}", seed=0, tp_rank=rank, tp_world=world)
+    m.adopt_shard_of(full)
+    m.allreduce = tp.PeerAllReduce(rank, world, shape.hidden) if kind == "amqb" else tp.NcclAllReduce()
+    tok = torch.tensor([17], device=dev)
+    for mm in (full, m):
+        mm.reset(); mm.tokens.copy_(tok)
+    for pos in range(6):
+        m.tokens.copy_(full.tokens)              # same token stream on both
+        full.step(); m.step()                    # graph-replayed (captured on first call)
+        torch.cuda.synchronize()
+        rel = float((m.logits - full.logits).abs().max() / full.logits.abs().max())
+        assert rel <= 2e-2, (kind, pos, rel)
+    lg = [torch.empty_like(m.logits) for _ in range(world)]
+    dist.all_gather(lg, m.logits)
+    assert all(torch.equal(g, lg[0]) for g in lg), kind          # every rank holds bit-identical logits
+    dist.barrier()
 dist.barrier()
 dist.destroy_process_group()
 print("ok", rank)
@@ -76,3 +100,40 @@ def test_allreduce_and_row_parallel(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("ok") == n
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("batch", [1, 2])
+def test_tp_decoder_matches_unsharded_emulated(world, batch):
+    """Model-level tensor-parallel parity on ONE GPU: `world` emulated ranks (tp.LocalTPGroup: one stream
+    per rank, each with its Megatron shard of the same weights and its own heads' K/V cache, the one-shot all-reduce
+    meeting through device memory) against the unsharded decoder: logits within 2e-2 (fp16 activations; the shards
+    round their partial sums separately), bit-identical on every rank, eager and graph-replayed."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import numpy as np
+    from amq_b200 import tp
+    from amq_b200.arch import LINEARS, ModelShape
+    from amq_b200.model import QuantDecoder
+    shape = ModelShape("tiny-gqa", 512, 1024, 8, 4, 2, 512, head_dim=64, qkv_bias=(batch == 2))
+    rs = np.random.RandomState(world)
+    arch = {n: rs.choice([2, 3, 4], size=2).tolist() for n in LINEARS}
+    full = QuantDecoder(shape, arch, batch=batch, max_seq=32, seed=5)
+    grp = tp.LocalTPGroup(full, world)
+    tok = torch.randint(0, shape.vocab, (batch,), device=full.dev)
+    full.reset(); full.tokens.copy_(tok)
+    grp.set_tokens(tok)
+    for pos in range(8):
+        for m in grp.ranks:
+            m.tokens.copy_(full.tokens)
+        torch.cuda.synchronize()
+        if pos < 2:
+            full.step_eager(); grp.step_eager()
+        else:
+            full.step(); grp.step()
+        torch.cuda.synchronize()
+        ref = full.logits
+        for m in grp.ranks:
+            assert torch.equal(m.logits, grp.ranks[0].logits)
+        rel = float((grp.ranks[0].logits - ref).abs().max() / ref.abs().max())
+        assert rel <= 2e-2, (world, batch, pos, rel)
