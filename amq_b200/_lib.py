@@ -9,11 +9,18 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libamqb.so")
+# AMQB_LIB: load another in-tree build of the same library (compile-time A/B variants made by tools/build_variant.sh)
+LIB_PATH = os.environ.get("AMQB_LIB") or os.path.join(_HERE, "lib", "libamqb.so")
 _lib: Optional[ctypes.CDLL] = None
 
 LAYOUT_HQQ, LAYOUT_GPTQ, LAYOUT_FT, LAYOUT_NATIVE = 0, 1, 2, 3
 PRO_NONE, PRO_RMSNORM, PRO_SILU_MUL = 0, 1, 2
+
+
+class ArCtx(ctypes.Structure):
+    """amqb_ar_ctx (include/amqb.h)."""
+    _fields_ = [("peer_bufs", ctypes.c_void_p * 16), ("rank", ctypes.c_int), ("world", ctypes.c_int),
+                ("max_elems", ctypes.c_int), ("pos_dev", ctypes.c_void_p), ("gen_dev", ctypes.c_void_p)]
 
 
 class GemvProblem(ctypes.Structure):
@@ -24,6 +31,7 @@ class GemvProblem(ctypes.Structure):
         ("y", ctypes.c_void_p), ("ldy", ctypes.c_int),
         ("bias", ctypes.c_void_p), ("residual", ctypes.c_void_p),
         ("prologue", ctypes.c_int), ("gamma", ctypes.c_void_p), ("eps", ctypes.c_float),
+        ("allreduce", ctypes.POINTER(ArCtx)), ("ar_call", ctypes.c_int),
     ]
 
 

@@ -19,6 +19,9 @@ LIB = os.path.join(LIBDIR, "libamqb.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+LIBDIR = os.environ.get("AMQB_LIBDIR", LIBDIR)      # tools/build_variant.sh: compile-time variants side by side
+LIB = os.path.join(LIBDIR, "libamqb.so")
+FLAGS += os.environ.get("AMQB_CFLAGS", "").split()
 if os.environ.get("AMQB_TIMELINE") == "1":          # debug build: per-CTA clock stamps in the decode kernel (tools/timeline.py)
     FLAGS.append("-DAMQB_TIMELINE")
 

@@ -71,7 +71,19 @@ __global__ void __launch_bounds__(1024) allreduce_push_kernel(const ArArgs A) {
   if (threadIdx.x < A.world) {
     st_release_sys(reinterpret_cast<uint32_t*>(s_peer[threadIdx.x] + kArHeader + 128 * A.rank), epoch);
     const uint32_t* f = reinterpret_cast<const uint32_t*>(mine + kArHeader + 128 * threadIdx.x);
-    while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {}    // wrap-safe: a faster peer may already be one epoch ahead
+    // wrap-safe compare (a faster peer may already be one epoch ahead); bounded: a peer that never arrives (a rank
+    // that died, or emulated ranks starving each other of SMs) must not hang the GPU: after ~4 s give up and leave a
+    // mark in word 1 of the header (amqb_ar_timeouts reads it)
+    long long t0 = 0;
+    unsigned spins = 0;
+    while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
+      if ((++spins & 0xFFFu) == 0) {
+        long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 4000000000LL) { atomicAdd(reinterpret_cast<uint32_t*>(mine) + 1, 1u); break; }
+      }
+    }
   }
   __syncthreads();
   // 4. reduce in rank order (+ residual); all loads of a vector are issued before the first add
@@ -149,6 +161,15 @@ int amqb_ar_close(void* dev_ptr) {
 int amqb_ar_free(void* dev_ptr) {
   cudaError_t e = cudaFree(dev_ptr);
   if (e != cudaSuccess) { set_error("ar_free: %s", cudaGetErrorString(e)); return AMQB_ERR_LAUNCH; }
+  return AMQB_OK;
+}
+
+int amqb_ar_timeouts(const void* own_buf_dev, int* count_out) {
+  if (!own_buf_dev || !count_out) return fail(AMQB_ERR_BAD_ARG, "ar_timeouts: bad argument");
+  uint32_t v = 0;
+  cudaError_t e = cudaMemcpy(&v, (const uint8_t*)own_buf_dev + 4, 4, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { set_error("ar_timeouts: %s", cudaGetErrorString(e)); return AMQB_ERR_LAUNCH; }
+  *count_out = (int)v;
   return AMQB_OK;
 }
 

@@ -98,7 +98,7 @@ static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, 
     const int per_group = xp_group_bytes(P.bits, M);
     int kc = kXprimeBudget / per_group;
     if (kc >= slice) kc = slice;
-    else kc = (kc / kStageRecs) * kStageRecs;       // whole pipeline stages per chunk
+    else kc = (kc / kCW) * kCW;                     // a chunk is whole half-stages: group gl stays with consumer warp gl % kCW
     if (kc < 1) return fail(AMQB_ERR_UNSUPPORTED_SHAPE, "gemv: x' chunk does not fit shared memory");
     P.kc = kc;
     if (kc > max_kc) max_kc = kc;
@@ -121,17 +121,21 @@ static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, 
     const char* e = getenv("AMQB_COPY_RECS");
     L.copy_recs = e ? atoi(e) : 8;
     if (L.copy_recs < 1) L.copy_recs = 1;
+    L.pair = getenv("AMQB_NO_PAIR") ? 0 : 1;
     const char* d = getenv("AMQB_DBG_DELAY_NS");
     L.dbg_delay_ns = d ? atoi(d) : 0;
   }
-  const int stage_recs = max_slice < kStageRecs ? max_slice : kStageRecs;
-  L.stage_bytes = stage_recs * max_rec;
   L.xprime_bytes = (max_xp + 127) & ~127;
   L.xp_variants = (M == 1 && count > 1 && 3 * L.xprime_bytes <= 96 * 1024) ? 3 : 1;
   L.xs_floats = (2 * max_kc * MB * 8 + 31) & ~31;
+  const size_t rs = red_stride(M);
   const size_t fixed = 384 + (size_t)L.xs_floats * 4 + 16 * kCW * 4 + (size_t)L.xp_variants * L.xprime_bytes +
-                       (size_t)2 * kCW * 2 * MB * 128 * 4 + (size_t)acc_blocks * 2 * MB * 128 * 4 +
-                       (S > 1 ? (size_t)count * S * 2 * MB * 128 * 4 : 0) + 128;
+                       (size_t)2 * kCW * rs * 4 + (size_t)acc_blocks * rs * 4 + (S > 1 ? (size_t)count * S * rs * 4 : 0) + 128;
+  // stage = two records per consumer warp; one when that would leave fewer than two stages (M > 1 with a large x')
+  int stage_recs = max_slice < kStageRecs ? max_slice : kStageRecs;
+  if (fixed + 2 * (size_t)stage_recs * max_rec > (size_t)kSmemTarget && stage_recs > kCW) stage_recs = kCW;
+  L.stage_recs = stage_recs;
+  L.stage_bytes = stage_recs * max_rec;
   if (fixed + 2 * (size_t)L.stage_bytes > (size_t)kSmemTarget)
     return fail(AMQB_ERR_UNSUPPORTED_SHAPE, "gemv: shared memory budget exceeded");
   int ns = (int)(((size_t)kSmemTarget - fixed) / L.stage_bytes);
@@ -204,6 +208,7 @@ int amqb_gemv_grouped(const amqb_gemv_problem* pr, int count, void* workspace, s
       return fail(AMQB_ERR_BAD_ARG, "gemv: x must be 8-byte aligned with ldx % 4 == 0, w 16-byte aligned");
     if (q.prologue < AMQB_PRO_NONE || q.prologue > AMQB_PRO_SILU_MUL) return fail(AMQB_ERR_BAD_ARG, "gemv: bad prologue");
     if (q.prologue == AMQB_PRO_RMSNORM && !q.gamma) return fail(AMQB_ERR_BAD_ARG, "gemv: rmsnorm prologue needs gamma");
+    if (q.prologue == AMQB_PRO_RMSNORM && ((uintptr_t)q.x & 15)) return fail(AMQB_ERR_BAD_ARG, "gemv: rmsnorm prologue needs 16-byte aligned x");
   }
   // one launch per prologue kind present in the group (normally one), in first-appearance order
   bool done[kMaxProblems] = {false, false, false, false};

@@ -35,7 +35,7 @@ __device__ __forceinline__ long long gtime() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-// debug timeline: per-CTA SM clock stamps (slot 0 = entry) written by thread 0.  Compiled in only with
+// debug timeline: per-CTA SM-clock stamps (slot 0 = entry; slot 12 = globaltimer ns at entry, which aligns CTAs and launches) written by thread 0.  Compiled in only with
 // -DAMQB_TIMELINE (AMQB_TIMELINE=1 python -m amq_b200.build --force): the stamps cost issue slots on the
 // launch's critical path.
 #ifdef AMQB_TIMELINE
@@ -49,7 +49,7 @@ __device__ __forceinline__ long long gtime() {
 constexpr int kCW = 16;                      // consumer warps
 constexpr int kCThreads = kCW * 32;
 constexpr int kThreads = kCThreads + 64;     // + producer warp + reducer warp = 576 threads
-constexpr int kStageRecs = kCW;              // records per pipeline stage: one per consumer warp
+constexpr int kStageRecs = 2 * kCW;          // records per pipeline stage: two per consumer warp (w and w + kCW)
 constexpr int kMaxProblems = 4;
 constexpr int kXprimeBudget = 72 * 1024;
 constexpr int kSmemTarget = 222 * 1024;
@@ -65,6 +65,8 @@ constexpr int kKindWide = 2;    // M = 3..16: column block `digit * MB + hb` hol
 // number of 8-column output blocks and x' geometry
 AMQB_HD constexpr int out_blocks(int M) { return M <= 8 ? 1 : 2; }
 AMQB_HD constexpr int xp_group_bytes(int bits, int M) { return mmas_per_group(bits) * 3 * M * 32; }
+// floats one warp deposits per row block (and per cluster-partial / chunk accumulator slot): batch 1 keeps one value per row
+AMQB_HD constexpr int red_stride(int M) { return M == 1 ? 32 : 2 * out_blocks(M) * 128; }
 
 struct DevProblem {
   const uint8_t* w;
@@ -92,12 +94,14 @@ struct GemvLaunch {
   int log2S;
   int n_stages;          // ring depth
   int stage_bytes;
+  int stage_recs;        // records per stage: 2 * kCW, or kCW when shared memory is short (M > 1 with a large x')
   int xprime_bytes;      // x' region
   int xs_floats;         // floats in the (xsum, delta) region
   int accbuf_blocks;     // row blocks per CTA that need a smem accumulator (chunked K), else 0
   int copy_recs;         // records per cp.async.bulk (a stage is issued as several bulk copies)
   int dbg_delay_ns;      // debug: consumers idle this long after building x' (0 in production)
   int xp_variants;       // 3: x' kept per bit width so problems sharing x reuse it; 1: rebuilt per problem
+  int pair;              // 1: consumers take two pipeline stages per iteration (A/B switch AMQB_NO_PAIR=1 clears it)
   long long* dbg;        // optional per-CTA timeline (16 x int64 per CTA), NULL in production
 };
 
@@ -134,13 +138,13 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
 // first MMA of a group: D = A*B + magic (the accumulators start at the bit pattern of 1.5 * 2^23 without being
 // initialised register by register: the C operand is a loop-invariant register)
 __device__ __forceinline__ void imma_16832_first(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, int magic) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
       : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(magic));
 }
 __device__ __forceinline__ void imma_16832(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -192,39 +196,43 @@ __device__ __forceinline__ void emit_reg(uint8_t* dst, int dstride, const float 
   }
 }
 
+// The four values of a lane's item as floats in byte order (beta 0..3 = pair 2I el 0, pair 2I+1 el 0, pair 2I el 1,
+// pair 2I+1 el 1), after the launch's prologue:
+//   SILU_MUL  silu(gate) * up, fp16 op by op like the HF MLP (the product is an fp16 tensor there too)
+//   RMSNORM   gamma * x * rs in fp32.  rs is a per-row scalar: the batch-1 kernel passes rs = 1 here and multiplies the
+//             finished dot products by rs in the reducer's epilogue instead (y = rs * W (gamma o x)), which takes the
+//             sum of squares, its cross-warp barrier and the rsqrt off the path between x arriving and the first MMA.
+//             fp32 because gamma * x, unlike gamma * (x * rs), can leave the fp16 range.
 template <int pro>
-__device__ __forceinline__ void finish_item(uint2 a, uint2 b, float rs, __half2& lo, __half2& hi) {
+__device__ __forceinline__ void finish_item(uint2 a, uint2 b, float rs, float (&xf)[4]) {
   const __half2* ah = reinterpret_cast<const __half2*>(&a);
   const __half2* bh = reinterpret_cast<const __half2*>(&b);
-  if (pro == AMQB_PRO_SILU_MUL) {          // silu(gate) * up, fp16 op by op like the HF MLP
+  if (pro == AMQB_PRO_SILU_MUL) {
     float2 g0 = __half22float2(ah[0]), g1 = __half22float2(ah[1]);
     g0.x = __fdividef(g0.x, 1.f + __expf(-g0.x)); g0.y = __fdividef(g0.y, 1.f + __expf(-g0.y));
     g1.x = __fdividef(g1.x, 1.f + __expf(-g1.x)); g1.y = __fdividef(g1.y, 1.f + __expf(-g1.y));
-    lo = __hmul2(__float22half2_rn(g0), bh[0]);
-    hi = __hmul2(__float22half2_rn(g1), bh[1]);
-  } else if (pro == AMQB_PRO_RMSNORM) {    // gamma * fp16(x * rsqrt(mean x^2 + eps))
-    float2 x0 = __half22float2(ah[0]), x1 = __half22float2(ah[1]);
-    x0.x *= rs; x0.y *= rs; x1.x *= rs; x1.y *= rs;
-    lo = __hmul2(bh[0], __float22half2_rn(x0));
-    hi = __hmul2(bh[1], __float22half2_rn(x1));
+    const float2 lo = __half22float2(__hmul2(__float22half2_rn(g0), bh[0]));
+    const float2 hi = __half22float2(__hmul2(__float22half2_rn(g1), bh[1]));
+    xf[0] = lo.x; xf[1] = hi.x; xf[2] = lo.y; xf[3] = hi.y;
+  } else if (pro == AMQB_PRO_RMSNORM) {
+    const float2 x0 = __half22float2(ah[0]), x1 = __half22float2(ah[1]);
+    const float2 w0 = __half22float2(bh[0]), w1 = __half22float2(bh[1]);
+    xf[0] = x0.x * rs * w0.x; xf[1] = x1.x * rs * w1.x; xf[2] = x0.y * rs * w0.y; xf[3] = x1.y * rs * w1.y;
   } else {
-    lo = ah[0]; hi = ah[1];
+    const float2 lo = __half22float2(ah[0]), hi = __half22float2(ah[1]);
+    xf[0] = lo.x; xf[1] = hi.x; xf[2] = lo.y; xf[3] = hi.y;
   }
 }
 
-// group statistics of one item: effective exponent e of the largest magnitude, the four values as floats in
-// byte order (beta 0..3 = pair 2I el 0, pair 2I+1 el 0, pair 2I el 1, pair 2I+1 el 1), and (sum of x-hat, delta')
-__device__ __forceinline__ float2 item_stats(__half2 lo, __half2 hi, float (&xf)[4], int& e_out) {
-  const uint32_t ua = *reinterpret_cast<const uint32_t*>(&lo) & 0x7FFF7FFFu;
-  const uint32_t ub = *reinterpret_cast<const uint32_t*>(&hi) & 0x7FFF7FFFu;
-  uint32_t mx = __vmaxu2(ua, ub);
-  mx = max(mx & 0xFFFFu, mx >> 16);
-  mx = __reduce_max_sync(0xffffffffu, mx);
-  int e = (int)(mx >> 10);
-  e = e > 30 ? 30 : (e < 1 ? 1 : e);
+// group statistics of one item: exponent e of the group's largest magnitude on fp16's scale (|x| < 2^(e - 14); for fp16
+// inputs this is the half's biased exponent, fp32 prologue products may fall outside 1..30) and (sum of x-hat, delta')
+__device__ __forceinline__ float2 item_stats(const float (&xf)[4], int& e_out) {
+  const uint32_t u0 = (uint32_t)__float_as_int(xf[0]) & 0x7FFFFFFFu, u1 = (uint32_t)__float_as_int(xf[1]) & 0x7FFFFFFFu;
+  const uint32_t u2 = (uint32_t)__float_as_int(xf[2]) & 0x7FFFFFFFu, u3 = (uint32_t)__float_as_int(xf[3]) & 0x7FFFFFFFu;
+  const uint32_t mx = __reduce_max_sync(0xffffffffu, max(max(u0, u1), max(u2, u3)));
+  int e = (int)(mx >> 23) - 112;
+  e = e > 48 ? 48 : (e < -24 ? -24 : e);
   e_out = e;
-  const float2 a = __half22float2(lo), b = __half22float2(hi);
-  xf[0] = a.x; xf[1] = b.x; xf[2] = a.y; xf[3] = b.y;
   // sum of x over the group in 18-bit fixed point relative to the group's largest exponent (exact integer adds)
   const float F18 = __int_as_float((127 + 32 - e) << 23);          // |x| < 2^(e-14)  ->  |x * F18| < 2^18
   uint32_t sum = 0;
@@ -236,7 +244,7 @@ __device__ __forceinline__ float2 item_stats(__half2 lo, __half2 hi, float (&xf)
   r.y = __int_as_float((127 + e - 36) << 23);                      // delta' = 2^(e - 36): dot = delta' * (2^16 c0 + 2^8 c1 + c2)
   // non-finite policy: an integer dot product cannot carry inf / NaN, so a group holding one poisons its activation
   // row (delta' = NaN -> every output of the row is NaN) instead of contributing finite garbage
-  if (mx >= 0x7C00u) r.y = __int_as_float(0x7FC00000);
+  if (mx >= 0x7F800000u) r.y = __int_as_float(0x7FC00000);
   return r;
 }
 
@@ -257,12 +265,11 @@ __device__ __forceinline__ void store_xsd(float2* xsd_g, int M, int MB, int mm, 
 
 // everything one item writes: all requested bit-width variants + its (xsum, delta) entries
 template <int KIND>
-__device__ __forceinline__ void emit_item(__half2 lo, __half2 hi, const XLane (&xl)[3], int mask, uint8_t* const (&vbase)[3],
+__device__ __forceinline__ void emit_item(const float (&xf)[4], const XLane (&xl)[3], int mask, uint8_t* const (&vbase)[3],
                                           const int (&gbytes)[3], int gl, int dstride, float2* xsd_g, int M, int MB, int mm,
                                           int lane, bool valid) {
-  float xf[4];
   int e;
-  const float2 sd = item_stats(lo, hi, xf, e);
+  const float2 sd = item_stats(xf, e);
 #pragma unroll
   for (int v = 0; v < 3; ++v)
     if (mask & (4 << v)) {                               // warp-uniform
@@ -273,37 +280,22 @@ __device__ __forceinline__ void emit_item(__half2 lo, __half2 hi, const XLane (&
   store_xsd<KIND>(xsd_g, M, MB, mm, lane, sd, valid);
 }
 
-template <int PRO>
-__device__ __forceinline__ void load_item(const DevProblem& P, int col, int group, int koff, uint2& a, uint2& b) {
-  // activations are read through L2 (ld.global.cg): the previous launch wrote them and nothing here re-reads them
-  const __half* xr = P.x + (size_t)col * P.ldx + group * kGroup + koff;
-  a.x = __ldcg(reinterpret_cast<const uint32_t*>(xr));
-  a.y = __ldcg(reinterpret_cast<const uint32_t*>(xr + 8));
-  b = make_uint2(0u, 0u);
-  if (PRO == AMQB_PRO_SILU_MUL) {
-    b.x = __ldcg(reinterpret_cast<const uint32_t*>(xr + P.K));
-    b.y = __ldcg(reinterpret_cast<const uint32_t*>(xr + P.K + 8));
-  } else if (PRO == AMQB_PRO_RMSNORM) {
-    const __half* gr = P.gamma + group * kGroup + koff;
-    b.x = *reinterpret_cast<const uint32_t*>(gr);
-    b.y = *reinterpret_cast<const uint32_t*>(gr + 8);
-  }
-}
-
 // Batch 1: x' of groups [g_lo, g_lo + len) of problem P, built inside the CTA.  Warp cw builds exactly the groups
 // it will consume (local index gl with gl % kCW == cw: record i of every pipeline stage goes to warp i), so no
-// CTA-wide barrier is needed; only the RMSNorm statistic crosses warps.  Two items per iteration, branch-free
-// (predicated stores), so the two dependency chains interleave.
+// CTA-wide barrier is needed and nothing crosses warps (the RMSNorm scale is applied by the reducer warp).
+// A load of x right after the dependency resolves costs ~0.5 us (L2 round trip to a line another SM has just
+// written): kPre items are requested at once; gamma (a weight) is fetched before griddepcontrol.wait.  Items are then
+// processed two at a time, branch-free (predicated stores), so two dependency chains interleave.
+#ifndef AMQB_KPRE
+#define AMQB_KPRE 2      // measured: 4 and 8 shorten the SiLU builder of down_proj but the longer code costs every launch more
+#endif
+constexpr int kPre = AMQB_KPRE;
 template <int PRO>
-__device__ __forceinline__ void build_xprime(const DevProblem& P, int S, int g_lo, int len, uint8_t* xp,
-                                             float2* xsd, float* sred, int cw, int lane, bool have_stats, float& rs1,
-                                             int mask, int variants, int var_stride, const XLane (&xl)[3],
+__device__ __forceinline__ void build_xprime(const DevProblem& P, int g_lo, int len, uint8_t* xp, float2* xsd, int cw,
+                                             int lane, int mask, int variants, int var_stride, const XLane (&xl)[3],
                                              bool& waited, long long* dbgp = nullptr) {
   const int koff = 16 * (lane >> 2) + 2 * (lane & 3);     // this lane's first k inside a group (second pair at + 8)
-  AMQB_DBG(if (dbgp) dbgp[3] = clock64();)
   const int items = len > cw ? (len - cw + kCW - 1) / kCW : 0;      // gl = cw, cw + kCW, ...
-  uint2 a0, b0, a1, b1;
-  bool preloaded = false;
   uint8_t* vbase[3];
   int gbytes[3];
 #pragma unroll
@@ -311,63 +303,48 @@ __device__ __forceinline__ void build_xprime(const DevProblem& P, int S, int g_l
     vbase[v] = xp + (size_t)(variants == 3 ? v : 0) * var_stride;
     gbytes[v] = xp_group_bytes(v + 2, 1);
   }
-  if (!waited) { pdl_wait(); waited = true; }      // first read of x below: everything above overlapped the previous kernel
-  if (PRO == AMQB_PRO_RMSNORM && !have_stats) {
-    float ss = 0.f;
-    if (S == 1 && items <= 2) {
-      // one pass (K <= 4096): the warp's items are loaded once; the squares are summed from the registers that are
-      // normalised afterwards, so the statistic costs no second trip to L2
-      if (items > 0) {
-        const bool v1 = items > 1;
-        load_item<PRO>(P, 0, g_lo + cw, koff, a0, b0);
-        load_item<PRO>(P, 0, g_lo + (v1 ? cw + kCW : cw), koff, a1, b1);
-        const float2 p0 = __half22float2(*reinterpret_cast<const __half2*>(&a0.x)), p1 = __half22float2(*reinterpret_cast<const __half2*>(&a0.y));
-        ss = p0.x * p0.x + p0.y * p0.y + p1.x * p1.x + p1.y * p1.y;
-        if (v1) {
-          const float2 r0 = __half22float2(*reinterpret_cast<const __half2*>(&a1.x)), r1 = __half22float2(*reinterpret_cast<const __half2*>(&a1.y));
-          ss += r0.x * r0.x + r0.y * r0.y + r1.x * r1.x + r1.y * r1.y;
+  for (int base = 0; base < items; base += kPre) {
+    uint2 a[kPre], b[kPre];
+    if (PRO == AMQB_PRO_RMSNORM) {
+#pragma unroll
+      for (int i = 0; i < kPre; ++i) {
+        b[i] = make_uint2(0u, 0u);
+        if (base + i < items) {
+          const __half* gr = P.gamma + (g_lo + cw + (base + i) * kCW) * kGroup + koff;
+          b[i].x = *reinterpret_cast<const uint32_t*>(gr);
+          b[i].y = *reinterpret_cast<const uint32_t*>(gr + 8);
         }
-        preloaded = true;
       }
-    } else if (S == 1) {
-      // every warp sums the squares of the groups it owns; together the warps cover the whole row
-      for (int gl = cw; gl < len; gl += kCW) {
-        const uint2 v = __ldcg(reinterpret_cast<const uint2*>(P.x + (g_lo + gl) * kGroup + 4 * lane));
-        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
-        const float2 b2 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
-        ss += a.x * a.x + a.y * a.y + b2.x * b2.x + b2.y * b2.y;
-      }
-    } else {   // K split across the cluster: the statistic still spans the FULL row
-      const uint2* xr = reinterpret_cast<const uint2*>(P.x);
-      for (int i = cw * 32 + lane; i < P.K / 4; i += kCThreads) {
-        const uint2 v = __ldcg(xr + i);
-        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
-        const float2 b2 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
-        ss += a.x * a.x + a.y * a.y + b2.x * b2.x + b2.y * b2.y;
+    }
+    if (!waited) { pdl_wait(); waited = true; AMQB_DBG(if (dbgp) dbgp[15] = clock64();) }   // first read of x below
+#pragma unroll
+    for (int i = 0; i < kPre; ++i) {
+      a[i] = make_uint2(0u, 0u);
+      if (PRO != AMQB_PRO_RMSNORM) b[i] = make_uint2(0u, 0u);
+      if (base + i < items) {
+        // activations are read through L2 (ld.global.cg): the previous launch wrote them and nothing here re-reads them
+        const __half* xr = P.x + (g_lo + cw + (base + i) * kCW) * kGroup + koff;
+        a[i].x = __ldcg(reinterpret_cast<const uint32_t*>(xr));
+        a[i].y = __ldcg(reinterpret_cast<const uint32_t*>(xr + 8));
+        if (PRO == AMQB_PRO_SILU_MUL) {
+          b[i].x = __ldcg(reinterpret_cast<const uint32_t*>(xr + P.K));
+          b[i].y = __ldcg(reinterpret_cast<const uint32_t*>(xr + P.K + 8));
+        }
       }
     }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    if (lane == 0) sred[cw] = ss;
-    named_bar_sync(1, kCThreads);
-    float tt = 0.f;
-#pragma unroll
-    for (int w = 0; w < kCW; ++w) tt += sred[w];
-    rs1 = rsqrtf(tt / (float)P.K + P.eps);
-  }
-  for (int it = 0; it < items; it += 2) {
-    const bool v1 = it + 1 < items;
-    const int gl0 = cw + it * kCW, gl1 = v1 ? gl0 + kCW : gl0;
-    if (!(preloaded && it == 0)) {
-      load_item<PRO>(P, 0, g_lo + gl0, koff, a0, b0);
-      load_item<PRO>(P, 0, g_lo + gl1, koff, a1, b1);
+    for (int i = 0; i < kPre; i += 2) {
+      if (base + i < items) {                                       // warp-uniform
+        const bool v1 = base + i + 1 < items;
+        const int gl0 = cw + (base + i) * kCW, gl1 = v1 ? gl0 + kCW : gl0;
+        float x0[4], x1[4];
+        finish_item<PRO>(a[i], b[i], 1.f, x0);
+        finish_item<PRO>(v1 ? a[i + 1] : a[i], v1 ? b[i + 1] : b[i], 1.f, x1);
+        AMQB_DBG(if (dbgp && base + i == 0) dbgp[14] = clock64() + (x0[0] == 1.2345e-30f);)
+        emit_item<kKindM1>(x0, xl, mask, vbase, gbytes, gl0, 32, xsd + (size_t)gl0 * 8, 1, 1, 0, lane, true);
+        emit_item<kKindM1>(x1, xl, mask, vbase, gbytes, gl1, 32, xsd + (size_t)gl1 * 8, 1, 1, 0, lane, v1);
+      }
     }
-    __half2 lo0, hi0, lo1, hi1;
-    finish_item<PRO>(a0, b0, rs1, lo0, hi0);
-    finish_item<PRO>(a1, b1, rs1, lo1, hi1);
-    AMQB_DBG(if (dbgp && it == 0) dbgp[14] = clock64() + ((*reinterpret_cast<uint32_t*>(&lo0) ^ *reinterpret_cast<uint32_t*>(&lo1)) == 0x12345678u);)
-    emit_item<kKindM1>(lo0, hi0, xl, mask, vbase, gbytes, gl0, 32, xsd + (size_t)gl0 * 8, 1, 1, 0, lane, true);
-    emit_item<kKindM1>(lo1, hi1, xl, mask, vbase, gbytes, gl1, 32, xsd + (size_t)gl1 * 8, 1, 1, 0, lane, v1);
   }
   __syncwarp();
 }
@@ -437,11 +414,11 @@ __global__ void __launch_bounds__(kXgWarps * 32) xprime_global_kernel(const XgAr
       b.x = *reinterpret_cast<const uint32_t*>(A.gamma + gl * kGroup + koff);
       b.y = *reinterpret_cast<const uint32_t*>(A.gamma + gl * kGroup + koff + 8);
     }
-    __half2 lo, hi;
-    finish_item<PRO>(a, b, rs, lo, hi);
+    float xf[4];
+    finish_item<PRO>(a, b, rs, xf);
     float2* xsd_g = A.xsg + (size_t)gl * A.MB * 8;
-    if (wide) emit_item<kKindWide>(lo, hi, xl, A.mask, vbase, gbytes, gl, cstride * 32, xsd_g, M, A.MB, col, lane, true);
-    else emit_item<kKindSmall>(lo, hi, xl, A.mask, vbase, gbytes, gl, cstride * 32, xsd_g, M, A.MB, col, lane, true);
+    if (wide) emit_item<kKindWide>(xf, xl, A.mask, vbase, gbytes, gl, cstride * 32, xsd_g, M, A.MB, col, lane, true);
+    else emit_item<kKindSmall>(xf, xl, A.mask, vbase, gbytes, gl, cstride * 32, xsd_g, M, A.MB, col, lane, true);
   }
 }
 
@@ -576,23 +553,99 @@ __device__ __forceinline__ void process_record(const uint8_t* rec, const uint8_t
   }
 }
 
-// problem p of the launch descriptor, read with STATIC indices: constant-bank operands with immediate offsets instead of
-// register-indexed constant loads on the dependent path between two problems of a grouped launch
-__device__ __forceinline__ DevProblem load_problem(const GemvLaunch& L, int p) {
-  switch (p) {
-    case 0: return L.prob[0];
-    case 1: return L.prob[1];
-    case 2: return L.prob[2];
-    default: return L.prob[3];
+// M = 1 / 2: NR (1 or 2) records of the SAME row block (different k groups) in one go.  A single record is a chain of
+// NM dependent IMMAs per tile: with four warps per scheduler all in the same pipeline phase the tensor pipe and the
+// issue slots sit idle behind that latency chain (measured: ~400 clk per record per scheduler against ~140 issue slots).
+// Two records give four independent accumulator chains per warp, interleaved MMA by MMA.
+// shared-memory loads by 32-bit shared-space address (no generic-pointer arithmetic / cvta in the record loop)
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint2 lds_v2(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ __half2 lds_h2(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return *reinterpret_cast<__half2*>(&v);
+}
+
+template <int BITS, int KIND, int NR>
+__device__ __forceinline__ void process_records(const uint32_t (&rec)[NR], const uint32_t (&xpg)[NR],
+                                                const uint32_t (&xsd)[NR], int M, int lane, float (&acc)[2][1][4]) {
+  constexpr int NWR = words_per_row(BITS), NV = vecs_per_rec(BITS), NM = mmas_per_group(BITS);
+  if (KIND == kKindM1) M = 1;
+  const int g = lane >> 2, t = lane & 3;
+  uint32_t w[NR][4 * NWR];                    // [record][tile][row half][word]
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const uint4 q = lds_v4(rec[r] + (v * 32 + lane) * 16);
+      w[r][4 * v] = q.x; w[r][4 * v + 1] = q.y; w[r][4 * v + 2] = q.z; w[r][4 * v + 3] = q.w;
+    }
+  }
+  // columns: 4 mm + digit (digit 3 unused: those lanes re-read digit 2 and are multiplied by a zero delta)
+  int mm = g >> 2;
+  if (mm > M - 1) mm = M - 1;
+  const int dg = (g & 3) > 2 ? 2 : (g & 3);
+  const int C = 3 * M;
+  const int boff = ((3 * mm + dg) * 4 + t) * 8;
+  int c[NR][2][4];
+#pragma unroll
+  for (int m = 0; m < NM; ++m) {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const uint2 b = lds_v2(xpg[r] + boff + m * C * 32);
+#pragma unroll
+      for (int tile = 0; tile < 2; ++tile) {
+        const uint32_t* Wg = w[r] + (tile * 2) * NWR;
+        const uint32_t* Wh = Wg + NWR;
+        uint32_t a[4];
+        a[0] = Wg[rho_word(BITS, 2 * m)] & rho_mask(BITS, 2 * m);
+        a[1] = Wh[rho_word(BITS, 2 * m)] & rho_mask(BITS, 2 * m);
+        a[2] = Wg[rho_word(BITS, 2 * m + 1)] & rho_mask(BITS, 2 * m + 1);
+        a[3] = Wh[rho_word(BITS, 2 * m + 1)] & rho_mask(BITS, 2 * m + 1);
+        if (m == 0) imma_16832_first(c[r][tile], a, b.x, b.y, (int)kMagicI);
+        else imma_16832(c[r][tile], a, b.x, b.y);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    const float4 xd = lds_f4(xsd[r] + 16 * t);             // (xsum, delta) of columns 2t, 2t+1
+    const uint32_t meta = rec[r] + rec_code_bytes(BITS);
+#pragma unroll
+    for (int tile = 0; tile < 2; ++tile) {
+      // group epilogue: acc += scale * delta * I - (zero*scale) * xsum
+      const float2 m0 = __half22float2(lds_h2(meta + (tile * 16 + g) * 4));
+      const float2 m1 = __half22float2(lds_h2(meta + (tile * 16 + g + 8) * 4));
+      const float f0 = __int_as_float(c[r][tile][0]) - kMagicF, f1 = __int_as_float(c[r][tile][1]) - kMagicF;
+      const float f2 = __int_as_float(c[r][tile][2]) - kMagicF, f3 = __int_as_float(c[r][tile][3]) - kMagicF;
+      const float v0 = fmaf(f0, xd.y, f1 * xd.w), v1 = fmaf(f2, xd.y, f3 * xd.w);
+      acc[tile][0][0] = fmaf(-m0.y, xd.x, fmaf(m0.x, v0, acc[tile][0][0]));
+      acc[tile][0][2] = fmaf(-m1.y, xd.x, fmaf(m1.x, v1, acc[tile][0][2]));
+    }
   }
 }
+
 
 __device__ __forceinline__ int first_rb(int cid, int rot, int ncl) {
   const int r = cid - rot;
   return r < 0 ? r + ncl : r;
 }
 
-__device__ __forceinline__ void store_out(const DevProblem& P, int n, int col, float v) {
+__device__ __forceinline__ void store_out(const DevProblem& P, int n, int col, float v, float rs = 1.f) {
+  v *= rs;
   if (P.bias) v += __half2float(P.bias[n]);
   if (P.residual) v += __half2float(__ushort_as_half(__ldcg(reinterpret_cast<const unsigned short*>(P.residual) + (size_t)col * P.ldy + n)));
   P.y[(size_t)col * P.ldy + n] = __float2half_rn(v);
@@ -602,6 +655,7 @@ __device__ __forceinline__ void store_out(const DevProblem& P, int n, int col, f
 template <int MB, int KIND, int PRO>
 __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_constant__ GemvLaunch L) {
   constexpr bool M1 = KIND == kKindM1;
+  constexpr int RS = M1 ? 32 : 2 * MB * 128;            // red_stride(M): floats one warp deposits per row block
   extern __shared__ __align__(1024) uint8_t smem[];
   // smem map: [0,384) barriers | (xsum, delta) | sred | x' | red[2] | accbuf | part[4][S] | ring
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);      // [0,NS) full, [NS,2NS) empty, [24,28) cluster-reduce, 28..32 misc
@@ -609,9 +663,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
   float* sred = reinterpret_cast<float*>(smem + 384) + L.xs_floats;     // 16 * kCW floats
   uint8_t* xp = reinterpret_cast<uint8_t*>(sred + 16 * kCW);
   float* red = reinterpret_cast<float*>(xp + (size_t)L.xp_variants * L.xprime_bytes);   // [2][kCW][2*MB*128]
-  float* accbuf = red + 2 * kCW * 2 * MB * 128;                        // [accbuf_blocks][2*MB*128]
-  float* part = accbuf + (size_t)L.accbuf_blocks * 2 * MB * 128;       // [count][S][2*MB*128] (S > 1)
-  uint8_t* ring = reinterpret_cast<uint8_t*>(part + (L.S > 1 ? L.count * L.S * 2 * MB * 128 : 0));
+  float* accbuf = red + 2 * kCW * RS;                        // [accbuf_blocks][2*MB*128]
+  float* part = accbuf + (size_t)L.accbuf_blocks * RS;       // [count][S][2*MB*128] (S > 1)
+  uint8_t* ring = reinterpret_cast<uint8_t*>(part + (L.S > 1 ? L.count * L.S * RS : 0));
   ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ring) + 127) & ~uintptr_t(127));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -622,6 +676,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
   const int M = M1 ? 1 : L.M;
 
   AMQB_STAMP(0);
+  AMQB_DBG(if (L.dbg && tid == 0) L.dbg[blockIdx.x * 16 + 12] = gtime();)
+  // The problem descriptors are copied from the kernel-parameter bank into shared memory by one load per thread, all in
+  // flight at once: a first touch of a parameter line costs ~0.5 us (measured: every switch to the next problem of a
+  // grouped launch stalled that long on its descriptor), and three roles x four problems would pay it one after another.
+  __shared__ DevProblem sprob[kMaxProblems];
+  {
+    constexpr int kWords = (int)(sizeof(DevProblem) * kMaxProblems / 4);
+    static_assert(kWords <= kThreads, "descriptor copy: one word per thread");
+    if (tid >= kThreads - kWords) {
+      const int i = tid - (kThreads - kWords);
+      reinterpret_cast<uint32_t*>(sprob)[i] = reinterpret_cast<const uint32_t*>(&L.prob[0])[i];
+    }
+  }
   if (tid < 40) {                     // one barrier per thread: [0,NS) full, [NS,2NS) empty, 24.. misc
     int cnt = 0;
     if (tid < NS) cnt = 1;                                   // full: producer's expect_tx arrive
@@ -636,6 +703,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
   if (S > 1) cluster_sync_all();   // barriers initialised and peers' shared memory live before any DSMEM traffic
   else __syncthreads();
   pdl_launch_dependents();
+  AMQB_STAMP(13);
 
   if (warp == kCW) {
     // ===== producer: weights do not depend on the previous kernel, so no griddepcontrol.wait here
@@ -645,15 +713,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
       int s = 0, ph = 0;
       bool wrapped = false;
       for (int p = 0; p < L.count; ++p) {
-        const DevProblem P = load_problem(L, p);
+        const DevProblem P = sprob[p];
         const uint32_t rbytes = rec_bytes(P.bits);
         const int g_lo = (P.n_g * rank) >> L.log2S, g_hi = (P.n_g * (rank + 1)) >> L.log2S;
         for (int c_lo = g_lo; c_lo < g_hi; c_lo += P.kc) {
           const int c_hi = (c_lo + P.kc) < g_hi ? (c_lo + P.kc) : g_hi;
           for (int rb = first_rb(cid, P.rot, ncl); rb < P.n_rb; rb += ncl) {
             const uint8_t* src = P.w + ((size_t)rb * P.n_g + c_lo) * rbytes;
-            for (int g = c_lo; g < c_hi; g += kStageRecs) {
-              const int nrec = (c_hi - g) < kStageRecs ? (c_hi - g) : kStageRecs;
+            for (int g = c_lo; g < c_hi; g += L.stage_recs) {
+              const int nrec = (c_hi - g) < L.stage_recs ? (c_hi - g) : L.stage_recs;
               if (wrapped) mbar_wait(smem_u32(&bars[NS + s]), ph ^ 1);
               const uint32_t bytes = nrec * rbytes;
               mbar_expect_tx(smem_u32(&bars[s]), bytes);
@@ -677,9 +745,27 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
     // fixed order and stores / hands off, so no consumer warp is ever held up by the epilogue
     pdl_wait();                      // bias / residual / y belong to the dependency chain
     int nblk = 0;
+    // batch-1 RMSNorm prologue: the row's scale rs = rsqrt(mean x^2 + eps) is computed HERE, by the warp that has
+    // nothing to do until the first row block is finished, and multiplies the finished sums (see finish_item)
+    float rs_ep = 1.f;
+    const __half* rs_x = nullptr;
     for (int p = 0; p < L.count; ++p) {
-      const DevProblem P = load_problem(L, p);
+      const DevProblem P = sprob[p];
       if (first_rb(cid, P.rot, ncl) >= P.n_rb) continue;
+      if (PRO == AMQB_PRO_RMSNORM && M1 && P.x != rs_x) {
+        rs_x = P.x;
+        float ss = 0.f;
+        const uint4* xr = reinterpret_cast<const uint4*>(P.x);
+        for (int i = lane; i < P.K / 8; i += 32) {
+          const uint4 v = __ldcg(xr + i);
+          const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { const float2 f = __half22float2(h[q]); ss = fmaf(f.x, f.x, fmaf(f.y, f.y, ss)); }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        rs_ep = rsqrtf(ss / (float)P.K + P.eps);
+      }
       const int g_lo = (P.n_g * rank) >> L.log2S, g_hi = (P.n_g * (rank + 1)) >> L.log2S;
       const bool chunked = (g_hi - g_lo) > P.kc;
       for (int c_lo = g_lo; c_lo < g_hi; c_lo += P.kc) {
@@ -698,14 +784,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
               if (P.residual) addend += __half2float(__ushort_as_half(__ldcg(reinterpret_cast<const unsigned short*>(P.residual) + n)));
             }
             mbar_wait(smem_u32(&bars[28 + buf]), use & 1);
-            const float* rbase = red + (size_t)buf * kCW * 2 * MB * 128;
+            const float* rbase = red + (size_t)buf * kCW * RS;
             constexpr int EPT = M1 ? 1 : 8 * MB;                 // output elements per lane
 #pragma unroll
             for (int q = 0; q < EPT; ++q) {
               const int e = M1 ? lane : q * 32 + lane;
               float v = 0.f;
 #pragma unroll
-              for (int w = 0; w < kCW; ++w) v += rbase[w * 2 * MB * 128 + e];
+              for (int w = 0; w < kCW; ++w) v += rbase[w * RS + e];
               int row, col;
               if (M1) { row = e; col = 0; }
               else {
@@ -715,17 +801,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
                 col = hb * 8 + 2 * (ln & 3) + (ci & 1);
               }
               if (chunked) {
-                float* ab = accbuf + (size_t)j * 2 * MB * 128 + e;
+                float* ab = accbuf + (size_t)j * RS + e;
                 if (!first_chunk) v += *ab;
                 if (!last_chunk) *ab = v;
               }
               if (last_chunk) {
                 if (S == 1) {
-                  if (pre) P.y[rb * 32 + row] = __float2half_rn(v + addend);
-                  else if (col < M) store_out(P, rb * 32 + row, col, v);
+                  if (pre) P.y[rb * 32 + row] = __float2half_rn(fmaf(v, rs_ep, addend));
+                  else if (col < M) store_out(P, rb * 32 + row, col, v, rs_ep);
                 } else {
                   // K was split across the cluster: partial sums meet in rank 0's shared memory (DSMEM)
-                  float* pslot = part + (size_t)(p * S + rank) * 2 * MB * 128 + e;
+                  float* pslot = part + (size_t)(p * S + rank) * RS + e;
                   if (rank != 0) st_dsmem_f32(smem_u32(pslot), 0, v);
                   else *pslot = v;
                 }
@@ -750,8 +836,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
                   }
                   if (col < M) {
                     float tt = 0.f;
-                    for (int r = 0; r < S; ++r) tt += part[(size_t)(p * S + r) * 2 * MB * 128 + e];
-                    store_out(P, rb * 32 + row, col, tt);
+                    for (int r = 0; r < S; ++r) tt += part[(size_t)(p * S + r) * RS + e];
+                    store_out(P, rb * 32 + row, col, tt, rs_ep);
                   }
                 }
               }
@@ -761,6 +847,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
         }
       }
     }
+    AMQB_DBG(if (L.dbg && lane == 0) L.dbg[blockIdx.x * 16 + 3] = clock64();)
     return;
   }
 
@@ -783,21 +870,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
   int s = 0, ph = 0, nblk = 0;
   AMQB_DBG(int dbg_round = 0;)
   const __half* cur_x = nullptr;     // x' cache: problems of a group that share x (q/k/v, gate/up)
-  int cur_K = 0, built_mask = 0, stat_par = 0, run_mask = 0;
+  int cur_K = 0, built_mask = 0, run_mask = 0;
   uint32_t xphase = 0;
-  float rs1 = 1.f;
   for (int p = 0; p < L.count; ++p) {
-    const DevProblem P = load_problem(L, p);
+    const DevProblem P = sprob[p];
     const uint32_t rbytes = rec_bytes(P.bits);
     const int gbytes = xp_group_bytes(P.bits, M);
     const int g_lo = (P.n_g * rank) >> L.log2S, g_hi = (P.n_g * (rank + 1)) >> L.log2S;
     const bool chunked = (g_hi - g_lo) > P.kc;
     AMQB_STAMP(4 + 4 * p);
     const bool same_x = (P.x == cur_x) && (P.K == cur_K);
-    if (!same_x) { built_mask = 0; cur_x = P.x; cur_K = P.K; stat_par ^= 1; }   // new x: new statistics buffer
+    if (!same_x) { built_mask = 0; cur_x = P.x; cur_K = P.K; }
     if (P.build_mask) run_mask = P.build_mask;
     if (first_rb(cid, P.rot, ncl) >= P.n_rb) continue;          // (after the bookkeeping: a later problem may rely on this run's mask)
     uint8_t* xpv = xp + (L.xp_variants == 3 ? (size_t)(P.bits - 2) * L.xprime_bytes : 0);
+    const uint32_t ring_u = smem_u32(ring), xpv_u = smem_u32(xpv), xsd_u = smem_u32(xsd), warp_rec = warp * rbytes;
     for (int c_lo = g_lo; c_lo < g_hi; c_lo += P.kc) {
       const int c_hi = (c_lo + P.kc) < g_hi ? (c_lo + P.kc) : g_hi;
       // x' variants to (re)build now: chunked K or a single variant buffer -> this problem's own; else
@@ -818,44 +905,73 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
       } else {
         const int want = (chunked || L.xp_variants != 3) ? (1 << P.bits) : ((run_mask | (1 << P.bits)) & ~built_mask);
         if (want && M1)
-          build_xprime<PRO>(P, S, c_lo, c_hi - c_lo, xp, xsd, sred + (stat_par ? kCW : 0), warp, lane,
-                            same_x && built_mask != 0, rs1, want, L.xp_variants, L.xprime_bytes, xl, waited
+          build_xprime<PRO>(P, c_lo, c_hi - c_lo, xp, xsd, warp, lane, want, L.xp_variants, L.xprime_bytes, xl, waited
                             AMQB_DBG(, (L.dbg && tid == 0) ? L.dbg + blockIdx.x * 16 : nullptr));
         built_mask |= want | (1 << P.bits);
       }
       AMQB_DBG(if (L.dbg_delay_ns > 0) { const long long t_end = gtime() + L.dbg_delay_ns; while (gtime() < t_end) {} })
       AMQB_STAMP(5 + 4 * p);
       for (int rb = first_rb(cid, P.rot, ncl); rb < P.n_rb; rb += ncl, ++nblk) {
+        AMQB_DBG(if (L.dbg && tid == 0 && nblk < 8) L.dbg[148 * 16 + blockIdx.x * 32 + 3 * nblk] = clock64();)
 #pragma unroll
         for (int a = 0; a < 2; ++a)
 #pragma unroll
           for (int hb = 0; hb < MB; ++hb)
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[a][hb][i] = 0.f;
-        for (int g = c_lo; g < c_hi; g += kStageRecs) {
-          const int nrec = (c_hi - g) < kStageRecs ? (c_hi - g) : kStageRecs;
+        for (int g = c_lo; g < c_hi; g += L.stage_recs) {
+          const int nrec = (c_hi - g) < L.stage_recs ? (c_hi - g) : L.stage_recs;
           mbar_wait(smem_u32(&bars[s]), ph);
-          if (warp < nrec) {
-            const uint8_t* rec = ring + (size_t)s * L.stage_bytes + (size_t)warp * rbytes;
-            const int gl = g - c_lo + warp;
-            const uint8_t* xpg = xpv + (size_t)gl * gbytes;
-            const float2* xsg = xsd + gl * MB * 8;
-            if (P.bits == 3) process_record<3, MB, KIND>(rec, xpg, xsg, M, lane, acc);
-            else if (P.bits == 4) process_record<4, MB, KIND>(rec, xpg, xsg, M, lane, acc);
-            else process_record<2, MB, KIND>(rec, xpg, xsg, M, lane, acc);
+          AMQB_DBG(if (L.dbg && L.count == 1 && tid == 0 && dbg_round < 2) L.dbg[blockIdx.x * 16 + 8 + 2 * dbg_round] = clock64();)
+          const int gl = g - c_lo + warp;
+          if (KIND != kKindWide) {
+            // records `warp` and `warp + kCW` of the stage: four independent IMMA chains per warp
+            const uint32_t r0 = ring_u + s * L.stage_bytes + warp_rec, x0 = xpv_u + gl * gbytes, d0 = xsd_u + gl * 64;
+            if (warp + kCW < nrec && L.pair) {
+              const uint32_t rec[2] = {r0, r0 + kCW * rbytes};
+              const uint32_t xpg[2] = {x0, x0 + kCW * gbytes};
+              const uint32_t xsg[2] = {d0, d0 + kCW * 64};
+              if (P.bits == 3) process_records<3, KIND, 2>(rec, xpg, xsg, M, lane, acc);
+              else if (P.bits == 4) process_records<4, KIND, 2>(rec, xpg, xsg, M, lane, acc);
+              else process_records<2, KIND, 2>(rec, xpg, xsg, M, lane, acc);
+            } else {
+#pragma unroll 1
+              for (int h = 0; h < 2; ++h) {
+                if (warp + h * kCW >= nrec) break;
+                const uint32_t rec[1] = {r0 + h * kCW * rbytes};
+                const uint32_t xpg[1] = {x0 + h * kCW * gbytes};
+                const uint32_t xsg[1] = {d0 + h * kCW * 64};
+                if (P.bits == 3) process_records<3, KIND, 1>(rec, xpg, xsg, M, lane, acc);
+                else if (P.bits == 4) process_records<4, KIND, 1>(rec, xpg, xsg, M, lane, acc);
+                else process_records<2, KIND, 1>(rec, xpg, xsg, M, lane, acc);
+              }
+            }
+          } else {
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+              const int ri = warp + h * kCW;
+              if (ri >= nrec) break;
+              const uint8_t* rec = ring + (size_t)s * L.stage_bytes + (size_t)ri * rbytes;
+              const uint8_t* xpg = xpv + (size_t)(gl + h * kCW) * gbytes;
+              const float2* xsg = xsd + (gl + h * kCW) * MB * 8;
+              if (P.bits == 3) process_record<3, MB, KIND>(rec, xpg, xsg, M, lane, acc);
+              else if (P.bits == 4) process_record<4, MB, KIND>(rec, xpg, xsg, M, lane, acc);
+              else process_record<2, MB, KIND>(rec, xpg, xsg, M, lane, acc);
+            }
           }
           __syncwarp();
+          AMQB_DBG(if (L.dbg && L.count == 1 && tid == 0 && dbg_round < 2) L.dbg[blockIdx.x * 16 + 9 + 2 * dbg_round++] = clock64();)
           if (lane == 0) mbar_arrive(smem_u32(&bars[NS + s]));
           if (++s == NS) { s = 0; ph ^= 1; }
-          AMQB_DBG(if (L.dbg && L.count == 1 && tid == 0 && dbg_round < 8) L.dbg[blockIdx.x * 16 + 8 + dbg_round++] = clock64();)
         }
         AMQB_STAMP(6 + 4 * p);
+        AMQB_DBG(if (L.dbg && tid == 0 && nblk < 8) L.dbg[148 * 16 + blockIdx.x * 32 + 3 * nblk + 1] = clock64();)
         // ---- (chunk of a) row block done.  Every warp deposits its partial sums in a double-buffered
         // shared-memory area and moves straight on; ONE warp waits for all deposits, sums them in
         // fixed order and stores / hands off.  mbarriers only: no CTA-wide barrier on this path.
         const int buf = nblk & 1, use = nblk >> 1;
         if (use > 0) mbar_wait(smem_u32(&bars[30 + buf]), (use - 1) & 1);       // red[buf] free again
-        float* myred = red + (size_t)(buf * kCW + warp) * 2 * MB * 128;
+        float* myred = red + (size_t)(buf * kCW + warp) * RS;
         if (KIND != kKindWide) {
           // the digits of one output sit in lanes t and t^1: fold them, lanes with even t hold row totals of mm = t >> 1
 #pragma unroll
@@ -888,6 +1004,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars[28 + buf]));
         AMQB_STAMP(7 + 4 * p);
+        AMQB_DBG(if (L.dbg && tid == 0 && nblk < 8) L.dbg[148 * 16 + blockIdx.x * 32 + 3 * nblk + 2] = clock64();)
       }
     }
   }

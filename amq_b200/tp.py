@@ -138,9 +138,13 @@ class LocalTPGroup:
     memory exactly as they do through NVLink-mapped peer memory.  What it is for: model-level parity of the sharded
     decoder on a single-GPU box (tests/test_gpu_tp.py) — the driver's test box has one GPU."""
 
-    def __init__(self, full, world: int, max_seq: Optional[int] = None, pdl: bool = True):
+    def __init__(self, full, world: int, max_seq: Optional[int] = None):
         from ._lib import lib
         from .model import QuantDecoder
+        # No programmatic dependent launch between the emulated ranks' kernels: a dependent GEMV launched early sits on
+        # its SM (222 KB of shared memory) waiting for an all-reduce that waits for a PEER rank's kernels, which then
+        # find no free SM on the one shared device.  Real ranks own a GPU each and keep PDL on.
+        pdl = False
         self.full, self.world = full, world
         dev = full.dev
         shard_plan(full.shape, world)
@@ -152,9 +156,21 @@ class LocalTPGroup:
             m = QuantDecoder(full.shape, full.arch, batch=full.B, max_seq=max_seq or full.max_seq, device=str(dev), seed=0,
                              n_block=full.n_block, pdl=pdl, tp_rank=r, tp_world=world)
             m.adopt_shard_of(full)
+            # own workspace (the M > 1 pre-pass writes the integer activations there; ops.workspace is per stream)
+            m.ws = torch.zeros_like(m.ws)
             m.allreduce = LocalAllReduce(r, world, full.shape.hidden * full.B, self._bufs, pdl=pdl)
             self.ranks.append(m)
         self._captured = False
+
+    def timeouts(self) -> int:
+        """Flag waits that gave up (0 in a correct run)."""
+        from ._lib import check, lib
+        n = 0
+        for b in self._bufs:
+            c = ctypes.c_int(0)
+            check(lib().amqb_ar_timeouts(ctypes.c_void_p(b.data_ptr()), ctypes.byref(c)), "ar_timeouts")
+            n += c.value
+        return n
 
     def set_tokens(self, tok: torch.Tensor) -> None:
         for m in self.ranks:

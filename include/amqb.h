@@ -92,6 +92,19 @@ int amqb_ft_pack(const void* W_f16, const void* scales_f16, const void* zeros_f1
                  int N, int K, int G, void* stream);
 
 /* ---- decode: fused dequant GEMV / skinny GEMM, M = 1..16 ---------------- */
+/* Tensor-parallel context of a row-parallel linear (config 5): with `allreduce` set in a problem, the
+ * kernel's epilogue pushes this rank's fp32 partial sums straight into every peer's exchange buffer over NVLink
+ * (8-byte value + epoch stores, no separate flag or fence), waits for the peers' and writes
+ * y = residual + bias + sum over ranks (rank order, identical bits on every rank): the all-reduce is part of the GEMV
+ * launch.  Buffers: amqb_ar_alloc / amqb_ar_open (amqb_ar_buffer_bytes(max_elems >= M * N, world)). */
+typedef struct {
+  void* peer_bufs[16];      /* rank r's exchange buffer as mapped into this process ([rank] = own) */
+  int rank, world;
+  int max_elems;            /* the max_elems the buffers were sized with */
+  const int* pos_dev;       /* device int: token position of the step (part of the epoch; same on every rank) */
+  const int* gen_dev;       /* device int: bumped by the host whenever positions restart (QuantDecoder.reset) */
+} amqb_ar_ctx;
+
 typedef struct {
   int bits;                 /* 2, 3 or 4 */
   int M, N, K;              /* rows of x, out features, in features */
@@ -105,6 +118,8 @@ typedef struct {
   int prologue;             /* amqb_prologue */
   const void* gamma;        /* fp16 [K] RMSNorm weight (AMQB_PRO_RMSNORM) */
   float eps;
+  const amqb_ar_ctx* allreduce; /* host pointer or NULL: fuse the tensor-parallel all-reduce into the epilogue */
+  int ar_call;              /* index of this all-reduce inside the step (0 .. 255; consecutive calls alternate parity) */
 } amqb_gemv_problem;
 
 /* One launch over `count` independent problems sharing M (q/k/v or gate/up, mixed bit-widths
@@ -210,6 +225,9 @@ size_t amqb_ar_buffer_bytes(int max_elems, int world);
 int amqb_ar_alloc(size_t bytes, void** dev_ptr, void* ipc_handle_out64);
 int amqb_ar_open(const void* ipc_handle64, void** dev_ptr);
 int amqb_ar_close(void* dev_ptr);
+/* Number of flag waits of this rank's all-reduces that gave up after ~4 s (0 in a correct run): a peer that never
+ * arrives must not hang the GPU.  Synchronises the device. */
+int amqb_ar_timeouts(const void* own_buf_dev, int* count_out);
 int amqb_ar_free(void* dev_ptr);
 /* out = residual + sum over ranks of partial (fp16 [n_elems], fp32 accumulation in rank order).
  * peer_bufs_host[r]: rank r's exchange buffer as mapped into this process ([rank] = own).  Every

@@ -449,3 +449,4 @@ def test_full_size_llama70b_layer_and_tp8_shards():
         rel = float((grp.ranks[0].logits - full.logits).abs().max() / full.logits.abs().max())
         assert rel < 2e-2, ("tp8", pos, rel)
         assert all(torch.equal(r.logits, grp.ranks[0].logits) for r in grp.ranks)
+    assert grp.timeouts() == 0

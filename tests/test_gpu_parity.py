@@ -159,6 +159,34 @@ def test_gemv_model_shapes(ops, N, K, bits):
 
 
 @pytest.mark.parametrize("bits", [2, 3, 4])
+def test_gemv_group_count_sweep(ops, bits, monkeypatch):
+    """Every k-group count around the pipeline-stage boundaries (a stage is 16 records; the batch-1 / batch-2 consumers
+    take two stages per iteration: 1, 15..17, 31..33, 47..49 groups exercise the single-stage tail, the half-filled
+    second stage and the odd stage count), both row-block parities, with and without the two-stage pairing
+    (AMQB_NO_PAIR): the pairing must not change a single bit (same per-warp accumulation order)."""
+    dev = "cuda"
+    for n_g in (1, 2, 15, 16, 17, 31, 32, 33, 47, 48, 49, 64, 86):
+        K = 128 * n_g
+        for N in (32, 96):
+            codes, scale, zero = _synthetic(N, K, bits, seed=n_g + N)
+            cg = torch.from_numpy(codes).to(dev)
+            sg, zg = scale.to(dev), zero.to(dev)
+            nat = ops.pack_native(bits, cg, sg, zg)
+            W = (cg.float().reshape(N, K // G, G) * sg.float()[..., None] - (zg * sg).float()[..., None]).reshape(N, K)
+            for M in (1, 2):
+                x = torch.randn(M, K, device=dev).half()
+                ref = x.float() @ W.t()
+                monkeypatch.delenv("AMQB_NO_PAIR", raising=False)
+                y = ops.gemv(bits, nat, x, N, K)
+                assert O.max_rel(y.cpu(), ref.cpu()) <= TOL, (bits, n_g, N, M, O.max_rel(y.cpu(), ref.cpu()))
+                monkeypatch.setenv("AMQB_NO_PAIR", "1")
+                y1 = ops.gemv(bits, nat, x, N, K)
+                torch.cuda.synchronize()
+                assert torch.equal(y, y1), (bits, n_g, N, M)
+    monkeypatch.delenv("AMQB_NO_PAIR", raising=False)
+
+
+@pytest.mark.parametrize("bits", [2, 3, 4])
 def test_config1_vs_cpu_oracle(ops, bits):
     """Config 1: 4096x4096 q_proj-shaped linear, batch-1, against the CPU oracle end to end
     (oracle pack -> our repack -> our GEMV vs oracle fp32 and the oracle's fp16 torch path)."""

@@ -96,8 +96,10 @@ def test_gemv_adversarial_activations(ops, bits, kind):
         if kind == "all_zero":
             assert (y == 0).all()
             continue
-        err = O.max_rel(y.float().cpu(), ref.cpu())
-        assert err <= TOL, (bits, kind, M, err)
+        # outputs in fp16's subnormal range are quantised to multiples of 2^-24 whatever the kernel does: the bound is
+        # TOL relative to the largest output, plus half of that step
+        err = float((y.float() - ref).abs().max())
+        assert err <= TOL * float(ref.abs().max()) + 2.0 ** -25, (bits, kind, M, err, float(ref.abs().max()))
         if kind == "outlier_some_groups":
             # the groups WITHOUT an outlier must keep their own precision (per-group exponent): check the rows' error
             # against the magnitude the quiet groups alone produce, not against the outlier-dominated maximum
@@ -116,8 +118,8 @@ def test_prefill_gemm_adversarial_activations(ops, bits, kind):
     y = ops.gemm_tc(bits, nat, x, N, K)
     ref = x.float() @ W.t()
     assert torch.isfinite(y).all()
-    err = O.max_rel(y.float().cpu(), ref.cpu())
-    assert err <= TOL, (bits, kind, err)
+    err = float((y.float() - ref).abs().max())
+    assert err <= TOL * float(ref.abs().max()) + 2.0 ** -25, (bits, kind, err, float(ref.abs().max()))
 
 
 @pytest.mark.parametrize("bits", [2, 3, 4])

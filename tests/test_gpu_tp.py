@@ -137,3 +137,4 @@ def test_tp_decoder_matches_unsharded_emulated(world, batch):
             assert torch.equal(m.logits, grp.ranks[0].logits)
         rel = float((grp.ranks[0].logits - ref).abs().max() / ref.abs().max())
         assert rel <= 2e-2, (world, batch, pos, rel)
+    assert grp.timeouts() == 0

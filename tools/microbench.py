@@ -59,17 +59,20 @@ def bench_case(N, K, bits, M, pool_mb=384, iters=20, pdl=False, simt=False):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--tiny", action="store_true")
     ap.add_argument("--out", default="gpurun_out/microbench.jsonl")
     a = ap.parse_args()
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     shapes = [(4096, 4096), (11008, 4096), (4096, 11008)]
-    if not a.quick:
+    if a.tiny:
+        shapes = [(4096, 4096), (11008, 4096)]
+    if not a.quick and not a.tiny:
         shapes += [(8192, 8192), (28672, 8192), (8192, 28672), (1024, 4096)]
     rows = []
     for (N, K) in shapes:
         for bits in (2, 3, 4):
-            for M in ((1,) if a.quick else (1, 4, 16)):
-                for pdl in (False, True):
+            for M in ((1,) if (a.quick or a.tiny) else (1, 4, 16)):
+                for pdl in ((True,) if a.tiny else (False, True)):
                     r = bench_case(N, K, bits, M, pdl=pdl)
                     rows.append(r)
                     print(json.dumps(r), flush=True)

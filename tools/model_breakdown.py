@@ -10,7 +10,14 @@ import ctypes
 shape = MODELS["Llama-2-7b-hf"]
 arch = sample_arch(shape, 3.0, seed=0)
 B = int(os.environ.get("B", "1"))
-m = QuantDecoder(shape, arch, batch=B, max_seq=256)
+nb = int(os.environ.get("BLOCKS", shape.n_block))
+m = QuantDecoder(shape, arch, batch=B, max_seq=256, n_block=nb)
+if os.environ.get("ALIAS_LAYERS") == "1":      # every layer reads layer 0's weights: the 82 MB stay in L2 (upper bound of a perfect prefetcher)
+    from amq_b200.arch import LINEARS
+    for Lr in m.layers[1:]:
+        for name in LINEARS:
+            Lr[name] = m.layers[0][name]
+    m._build_problems()
 m.pos.fill_(100)
 L = lib()
 L.amqb_set_pdl(1)
@@ -48,4 +55,5 @@ def head():
 print(f"lm_head+argmax: {timeit(head, 1):6.2f} us")
 def full():
     m._step_launches()
-print(f"full step: {timeit(full, 1):8.1f} us")
+t_full = timeit(full, 1)
+print(f"full step: {t_full:8.1f} us  ({nb} blocks: {(t_full - 52.0) / nb:6.2f} us per layer excluding ~52 us of embed / lm_head / argmax)")
