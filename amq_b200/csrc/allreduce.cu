@@ -125,9 +125,15 @@ using namespace amqb;
 
 extern "C" {
 
+/* [header | flags | fp16 slots [2][world][max_elems] (amqb_allreduce_f16) | LL slots [2][world][max_elems] x 8 B (the
+ * all-reduce fused into the GEMV epilogue, gemv_mma.cuh ar_push / ar_collect)] */
+size_t amqb_ar_ll_offset(int max_elems, int world) {
+  if (max_elems <= 0 || world < 1 || world > kArMaxWorld) return 0;
+  return (kArHeader + 128 * (size_t)world + 2 * (size_t)world * max_elems * 2 + 127) & ~(size_t)127;
+}
 size_t amqb_ar_buffer_bytes(int max_elems, int world) {
   if (max_elems <= 0 || world < 1 || world > kArMaxWorld) return 0;
-  return kArHeader + 128 * (size_t)world + 2 * (size_t)world * max_elems * 2;
+  return amqb_ar_ll_offset(max_elems, world) + 2 * (size_t)world * max_elems * 8;
 }
 
 int amqb_ar_alloc(size_t bytes, void** dev_ptr, void* ipc_handle_out64) {

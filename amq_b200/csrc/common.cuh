@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/amqb.h"
 #include "layout.cuh"
@@ -38,14 +39,18 @@ struct PerDeviceOnce {
     return true;
   }
 };
+extern int g_sm_limit;
 inline int sm_count() {
   static int cached[kMaxDevices] = {};
   const int d = current_device();
   if (cached[d] == 0) {
     cudaDeviceGetAttribute(&cached[d], cudaDevAttrMultiProcessorCount, d);
     if (cached[d] <= 0) cached[d] = 148;
+
   }
-  return cached[d];
+  // amqb_debug_set_sm_limit: grids sized as if the device had fewer SMs.  For emulating several tensor-parallel ranks on
+  // one GPU (tp.LocalTPGroup): a rank's kernel that waits for its peers' partial sums must leave them SMs to run on.
+  return (g_sm_limit > 0 && g_sm_limit < cached[d]) ? g_sm_limit : cached[d];
 }
 
 inline int fail(int code, const char* msg) {

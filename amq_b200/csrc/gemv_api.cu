@@ -7,6 +7,7 @@
 namespace amqb {
 
 long long* g_dbg = nullptr;       // debug timeline buffer (amqb_debug_set_timeline)
+int g_sm_limit = 0;               // amqb_debug_set_sm_limit
 
 // One launch: problems sharing M and prologue kind (bit widths may differ).
 static size_t xg_xsd_bytes(int n_g, int MB) { return ((size_t)n_g * MB * 8 * sizeof(float2) + 255) & ~size_t(255); }
@@ -38,6 +39,23 @@ static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, 
     P.bias = (const __half*)q.bias; P.residual = (const __half*)q.residual; P.gamma = (const __half*)q.gamma;
     P.eps = q.eps; P.bits = q.bits; P.N = q.N; P.K = q.K; P.ldx = q.ldx; P.ldy = q.ldy; P.prologue = q.prologue;
     P.n_rb = q.N / 32; P.n_g = q.K / kGroup;
+    P.ar = 0;
+    if (q.allreduce && q.allreduce->world > 1) {
+      const amqb_ar_ctx& C = *q.allreduce;
+      if (C.world > kArFuseMaxWorld || C.rank < 0 || C.rank >= C.world || !C.pos_dev || !C.gen_dev || (long long)M * q.N > C.max_elems)
+        return fail(AMQB_ERR_BAD_ARG, "gemv: bad all-reduce context (world <= 8, M * N <= max_elems, pos / gen set)");
+      if (L.ar.world > 1 && (L.ar.call != (q.ar_call & 0xFF) || L.ar.mine != (uint8_t*)C.peer_bufs[C.rank]))
+        return fail(AMQB_ERR_BAD_ARG, "gemv: one fused all-reduce per launch");
+      for (int r = 0; r < C.world; ++r) {
+        if (!C.peer_bufs[r]) return fail(AMQB_ERR_BAD_ARG, "gemv: all-reduce context with a null peer buffer");
+        L.ar.peer[r] = (uint8_t*)C.peer_bufs[r];
+      }
+      L.ar.mine = (uint8_t*)C.peer_bufs[C.rank];
+      L.ar.pos = C.pos_dev; L.ar.gen = C.gen_dev;
+      L.ar.rank = C.rank; L.ar.world = C.world; L.ar.max_elems = C.max_elems; L.ar.call = q.ar_call & 0xFF;
+      L.ar.ll_off = amqb_ar_ll_offset(C.max_elems, C.world);
+      P.ar = 1;
+    }
     if (P.n_rb > max_rb) max_rb = P.n_rb;
     if (P.n_g < min_g) min_g = P.n_g;
     if (rec_bytes(q.bits) > max_rec) max_rec = rec_bytes(q.bits);
@@ -157,6 +175,11 @@ extern "C" {
 /* debug: per-CTA globaltimer stamps (8 x int64 per CTA) written by the next decode launches */
 int amqb_debug_set_timeline(void* buf) {
   g_dbg = (long long*)buf;
+  return AMQB_OK;
+}
+
+int amqb_debug_set_sm_limit(int n) {
+  g_sm_limit = n > 0 ? n : 0;
   return AMQB_OK;
 }
 

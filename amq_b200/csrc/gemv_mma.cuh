@@ -84,10 +84,26 @@ struct DevProblem {
   int rot;               // row block rb goes to cluster (rb + rot) % ncl: spreads the remainder blocks of
                          // consecutive problems over different CTAs
   int build_mask;        // bit b set: build the x' variant of bit width b when this problem starts (0: reuse)
+  int ar;                // 1: row-parallel problem of a tensor-parallel model: the epilogue all-reduces across L.ar ranks
+};
+
+// Tensor-parallel all-reduce fused into the epilogue (amqb_ar_ctx, include/amqb.h).  "LL" exchange: every partial sum
+// travels as ONE 8-byte store {fp32 value, epoch} into slot [parity][source rank][element] of every rank's buffer, so
+// there is no separate flag, no fence and no extra launch; the receiver polls the slot until the epoch matches.  Two
+// parities because a rank can be at most one all-reduce ahead of a peer (it needs that peer's partials to finish one).
+constexpr int kArFuseMaxWorld = 8;
+struct ArDev {
+  uint8_t* peer[kArFuseMaxWorld];   // every rank's exchange buffer as mapped here
+  uint8_t* mine;                    // = peer[rank]
+  const int* pos;                   // token position (same on every rank): part of the epoch
+  const int* gen;                   // generation: bumped whenever positions restart
+  unsigned long long ll_off;        // byte offset of the LL slots inside an exchange buffer
+  int rank, world, max_elems, call;
 };
 
 struct GemvLaunch {
   DevProblem prob[kMaxProblems];
+  ArDev ar;              // ar.world <= 1: no fused all-reduce in this launch
   int count;
   int M;
   int S;                 // cluster size = K split (power of two)
@@ -639,6 +655,48 @@ __device__ __forceinline__ void process_records(const uint32_t (&rec)[NR], const
 }
 
 
+__device__ __forceinline__ uint32_t ar_epoch(const ArDev& A) {
+  const uint32_t gen = (uint32_t)*reinterpret_cast<const volatile int*>(A.gen);
+  const uint32_t pos = (uint32_t)*reinterpret_cast<const volatile int*>(A.pos);
+  return (gen << 24) | (((pos + 1u) & 0xFFFFu) << 8) | ((uint32_t)A.call & 0xFFu);
+}
+__device__ __forceinline__ size_t ar_slot(const ArDev& A, int src, int idx) {
+  return (size_t)A.ll_off + ((size_t)((A.call & 1) * A.world + src) * A.max_elems + idx) * 8;
+}
+// this rank's partial sum of element idx -> slot [rank] of EVERY rank's buffer (NVLink stores; own buffer included)
+__device__ __forceinline__ void ar_push(const ArDev& A, uint32_t epoch, int idx, float v) {
+  const size_t off = ar_slot(A, A.rank, idx);
+#pragma unroll
+  for (int p = 0; p < kArFuseMaxWorld; ++p)
+    if (p < A.world)
+      asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(A.peer[p] + off), "r"(__float_as_uint(v)), "r"(epoch) : "memory");
+}
+// sum over ranks, in rank order (identical bits on every rank), of element idx; waits for every rank's slot.  Bounded:
+// a peer that never arrives must not hang the GPU (mark in word 1 of the buffer header, amqb_ar_timeouts)
+__device__ __forceinline__ float ar_collect(const ArDev& A, uint32_t epoch, int idx) {
+  float tot = 0.f;
+#pragma unroll
+  for (int r = 0; r < kArFuseMaxWorld; ++r) {
+    if (r >= A.world) break;
+    const uint8_t* slot = A.mine + ar_slot(A, r, idx);
+    uint32_t val, flag;
+    unsigned spins = 0;
+    long long t0 = 0;
+    for (;;) {
+      asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(val), "=r"(flag) : "l"(slot) : "memory");
+      if (flag == epoch) break;
+      if ((++spins & 0x3FFu) == 0) {
+        long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 4000000000LL) { atomicAdd(reinterpret_cast<unsigned int*>(A.mine) + 1, 1u); break; }
+      }
+    }
+    tot += __uint_as_float(val);
+  }
+  return tot;
+}
+
 __device__ __forceinline__ int first_rb(int cid, int rot, int ncl) {
   const int r = cid - rot;
   return r < 0 ? r + ncl : r;
@@ -749,6 +807,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
     // nothing to do until the first row block is finished, and multiplies the finished sums (see finish_item)
     float rs_ep = 1.f;
     const __half* rs_x = nullptr;
+    const bool ar_on = L.ar.world > 1;
+    const uint32_t epoch = ar_on ? ar_epoch(L.ar) : 0u;
     for (int p = 0; p < L.count; ++p) {
       const DevProblem P = sprob[p];
       if (first_rb(cid, P.rot, ncl) >= P.n_rb) continue;
@@ -777,7 +837,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
             // batch 1, unsplit K: bias and residual of this row block are fetched BEFORE waiting for the consumers'
             // partial sums, so the store follows the last deposit without an L2 round trip
             float addend = 0.f;
-            const bool pre = M1 && S == 1 && !chunked;
+            const bool fuse = ar_on && P.ar;              // partial sums go to the peers, the row block is finished below
+            const bool pre = M1 && S == 1 && !chunked && !fuse;
             if (pre) {
               const int n = rb * 32 + lane;
               if (P.bias) addend += __half2float(P.bias[n]);
@@ -808,7 +869,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
               if (last_chunk) {
                 if (S == 1) {
                   if (pre) P.y[rb * 32 + row] = __float2half_rn(fmaf(v, rs_ep, addend));
-                  else if (col < M) store_out(P, rb * 32 + row, col, v, rs_ep);
+                  else if (col < M) {
+                    if (fuse) ar_push(L.ar, epoch, col * P.N + rb * 32 + row, v * rs_ep);
+                    else store_out(P, rb * 32 + row, col, v, rs_ep);
+                  }
                 } else {
                   // K was split across the cluster: partial sums meet in rank 0's shared memory (DSMEM)
                   float* pslot = part + (size_t)(p * S + rank) * RS + e;
@@ -837,13 +901,39 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
                   if (col < M) {
                     float tt = 0.f;
                     for (int r = 0; r < S; ++r) tt += part[(size_t)(p * S + r) * RS + e];
-                    store_out(P, rb * 32 + row, col, tt, rs_ep);
+                    if (fuse) ar_push(L.ar, epoch, col * P.N + rb * 32 + row, tt * rs_ep);
+                    else store_out(P, rb * 32 + row, col, tt, rs_ep);
                   }
                 }
               }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bars[30 + buf]));
+        }
+      }
+    }
+    // fused tensor-parallel all-reduce, second half: every row block this CTA finished waits for the peers' partial
+    // sums of ITS rows (pushed above, block by block, so the NVLink latency overlapped the remaining blocks), adds them
+    // in rank order and writes y = residual + bias + sum
+    if (ar_on && (S == 1 || rank == 0)) {
+      for (int p = 0; p < L.count; ++p) {
+        const DevProblem P = sprob[p];
+        if (!P.ar) continue;
+        for (int rb = first_rb(cid, P.rot, ncl); rb < P.n_rb; rb += ncl) {
+          constexpr int EPT = M1 ? 1 : 8 * MB;
+#pragma unroll
+          for (int q = 0; q < EPT; ++q) {
+            const int e = M1 ? lane : q * 32 + lane;
+            int row, col;
+            if (M1) { row = e; col = 0; }
+            else {
+              const int ci = e & 3, ln = (e >> 2) & 31, tn = e >> 7;
+              const int tile = tn / MB, hb = tn - tile * MB;
+              row = tile * 16 + (ln >> 2) + 8 * (ci >> 1);
+              col = hb * 8 + 2 * (ln & 3) + (ci & 1);
+            }
+            if (col < M) store_out(P, rb * 32 + row, col, ar_collect(L.ar, epoch, col * P.N + rb * 32 + row));
+          }
         }
       }
     }

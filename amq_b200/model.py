@@ -120,9 +120,26 @@ class QuantDecoder:
         self._pos_h = 0
         self.graph_long: Optional[torch.cuda.CUDAGraph] = None
         self.graph: Optional[torch.cuda.CUDAGraph] = None
-        self.allreduce = None          # set by amq_b200.tp for tensor-parallel runs
+        self.allreduce = None          # set by attach_allreduce (amq_b200.tp) for tensor-parallel runs
+        self.ar_ctx = None             # amqb_ar_ctx when the all-reduce is fused into the row-parallel GEMVs' epilogue
+        self.ar_gen = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.launches_per_step = 0
         self._build_problems()
+
+    # ---------------------------------------------------------------- tensor parallel
+    def attach_allreduce(self, ar, fused: bool = True) -> None:
+        """ar: tp.PeerAllReduce / LocalAllReduce / NcclAllReduce.  fused (peer-memory kinds only): o_proj and down_proj
+        push their fp32 partial sums to the peers from their own epilogue and finish h = h + sum over ranks there
+        (amqb_gemv_problem.allreduce) — no all-reduce launch; otherwise one all-reduce call follows each of them."""
+        self.allreduce = ar
+        self.ar_ctx = ar.make_ctx(self.pos, self.ar_gen) if (fused and hasattr(ar, "make_ctx")) else None
+        self._build_problems()
+        self.graph = self.graph_long = None
+
+    def bump_generation(self) -> None:
+        """Whenever positions restart (reset, the rewind after a capture warm-up) the fused all-reduce's epoch
+        (generation, position, call index) must not repeat: slots still hold the earlier pass's values."""
+        self.ar_gen.add_(1)
 
     # ---------------------------------------------------------------- tensor-parallel shard of another decoder
     def adopt_shard_of(self, full: "QuantDecoder") -> None:
@@ -194,9 +211,17 @@ class QuantDecoder:
                    prob(vb, vw, self.h, self.qkv.data_ptr() + 2 * (self.q_dim + self.kv_dim), vn, vk, self.H, qkv_ld,
                         bptr(self.q_dim + self.kv_dim), None, PRO_RMSNORM, L["norm1"])]
             ob, ow, on, ok = L["self_attn.o_proj"]
-            tp = self.tp_world > 1
-            o = [prob(ob, ow, self.attn, (self.part if tp else self.h).data_ptr(), on, ok, self.q_dim, self.H, None,
-                      None if tp else self.h)]
+            tp = self.tp_world > 1 and self.ar_ctx is None     # partial sums to `part`, a separate all-reduce adds them to h
+            li = len(self._plan)
+
+            def fuse(p, call):
+                if self.ar_ctx is not None:
+                    p.allreduce = ctypes.pointer(self.ar_ctx)
+                    p.ar_call = call & 0xFF
+                return p
+
+            o = [fuse(prob(ob, ow, self.attn, (self.part if tp else self.h).data_ptr(), on, ok, self.q_dim, self.H, None,
+                           None if tp else self.h), 2 * li)]
             gb, gw, gn, gk = L["mlp.gate_proj"]
             ub, uw, un, uk = L["mlp.up_proj"]
             gu_ld = self.gu.stride(0)
@@ -204,8 +229,8 @@ class QuantDecoder:
                   prob(ub, uw, self.h, self.gu.data_ptr() + 2 * self.I_loc, un, uk, self.H, gu_ld, None, None, PRO_RMSNORM,
                        L["norm2"])]
             db, dw, dn, dk = L["mlp.down_proj"]
-            down = [prob(db, dw, self.gu, (self.part if tp else self.h).data_ptr(), dn, dk, gu_ld, self.H, None,
-                         None if tp else self.h, PRO_SILU_MUL)]
+            down = [fuse(prob(db, dw, self.gu, (self.part if tp else self.h).data_ptr(), dn, dk, gu_ld, self.H, None,
+                              None if tp else self.h, PRO_SILU_MUL), 2 * li + 1)]
             self._plan.append({"qkv": (ops.GemvProblem * 3)(*qkv), "o": (ops.GemvProblem * 1)(*o),
                                "gu": (ops.GemvProblem * 2)(*gu), "down": (ops.GemvProblem * 1)(*down), "L": L})
 
@@ -231,12 +256,12 @@ class QuantDecoder:
                                             ctypes.c_size_t(self.attn_ws.numel()), st), "attn_decode_split")
             self.launches_per_step += 1
             self._gemv(P["o"], 1)
-            if self.allreduce is not None:
+            if self.allreduce is not None and self.ar_ctx is None:
                 self.allreduce(self.part, self.h)          # h += sum over ranks of part
                 self.launches_per_step += 1
             self._gemv(P["gu"], 2)
             self._gemv(P["down"], 1)
-            if self.allreduce is not None:
+            if self.allreduce is not None and self.ar_ctx is None:
                 self.allreduce(self.part, self.h)
                 self.launches_per_step += 1
         check(Lb.amqb_lm_head(ptr(self.lm_head), ptr(self.h), ptr(self.final_norm), ctypes.c_float(S.rms_eps),
@@ -271,6 +296,7 @@ class QuantDecoder:
                     self._step_launches()
                 self.pos.copy_(saved_pos)           # the step advances position and input ids itself: undo the warm-up's
                 self.tokens.copy_(saved_tok)
+                self.bump_generation()
             s.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=s):
@@ -333,6 +359,7 @@ class QuantDecoder:
     def reset(self) -> None:
         self.pos.zero_()
         self._pos_h = 0
+        self.bump_generation()
 
     # ---------------------------------------------------------------- prompt prefill (all prompt rows at once)
     @torch.inference_mode()

@@ -92,8 +92,15 @@ class PeerAllReduce:
         import torch.distributed as dist
         dist.barrier()
 
+    def make_ctx(self, pos_dev: torch.Tensor, gen_dev: torch.Tensor):
+        """amqb_ar_ctx for the all-reduce fused into the row-parallel GEMV's epilogue (amqb_gemv_problem.allreduce)."""
+        return _make_ctx(self._peers, self.rank, self.world, self.max_elems, pos_dev, gen_dev)
+
     def close(self) -> None:
-        """Unmap the peers' buffers and free this rank's (after every rank is done with them)."""
+        """COLLECTIVE: every rank unmaps its peers' buffers, then (after a barrier: nobody may free a buffer a peer
+        still has mapped) frees its own.  Never called implicitly — a destructor would run at a different time on
+        every rank."""
+        import torch.distributed as dist
         from ._lib import lib
         if getattr(self, "_mine", None) is None:
             return
@@ -102,19 +109,25 @@ class PeerAllReduce:
         for p in self._opened:
             L.amqb_ar_close(p)
         self._opened = []
+        if dist.is_initialized():
+            dist.barrier()
         L.amqb_ar_free(self._mine)
         self._mine = None
-
-    def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass
 
     def __call__(self, partial: torch.Tensor, h: torch.Tensor) -> None:
         from ._lib import check, cur_stream, lib, ptr
         check(lib().amqb_allreduce_f16(self._peers, self.rank, self.world, ptr(partial), ptr(h), ptr(h), partial.numel(),
                                        self.max_elems, int(self.pdl), cur_stream()), "allreduce")
+
+
+def _make_ctx(peers, rank: int, world: int, max_elems: int, pos_dev: torch.Tensor, gen_dev: torch.Tensor):
+    from ._lib import ArCtx
+    c = ArCtx()
+    for r in range(world):
+        c.peer_bufs[r] = peers[r]
+    c.rank, c.world, c.max_elems = rank, world, max_elems
+    c.pos_dev, c.gen_dev = pos_dev.data_ptr(), gen_dev.data_ptr()
+    return c
 
 
 class LocalAllReduce:
@@ -125,6 +138,9 @@ class LocalAllReduce:
         self.rank, self.world, self.max_elems, self.pdl = rank, world, max_elems, pdl
         self._bufs = bufs
         self._peers = (ctypes.c_void_p * world)(*[ctypes.c_void_p(b.data_ptr()) for b in bufs])
+
+    def make_ctx(self, pos_dev: torch.Tensor, gen_dev: torch.Tensor):
+        return _make_ctx(self._peers, self.rank, self.world, self.max_elems, pos_dev, gen_dev)
 
     def __call__(self, partial: torch.Tensor, h: torch.Tensor) -> None:
         from ._lib import check, cur_stream, lib, ptr
@@ -138,7 +154,7 @@ class LocalTPGroup:
     memory exactly as they do through NVLink-mapped peer memory.  What it is for: model-level parity of the sharded
     decoder on a single-GPU box (tests/test_gpu_tp.py) — the driver's test box has one GPU."""
 
-    def __init__(self, full, world: int, max_seq: Optional[int] = None):
+    def __init__(self, full, world: int, max_seq: Optional[int] = None, fused: bool = True):
         from ._lib import lib
         from .model import QuantDecoder
         # No programmatic dependent launch between the emulated ranks' kernels: a dependent GEMV launched early sits on
@@ -158,9 +174,16 @@ class LocalTPGroup:
             m.adopt_shard_of(full)
             # own workspace (the M > 1 pre-pass writes the integer activations there; ops.workspace is per stream)
             m.ws = torch.zeros_like(m.ws)
-            m.allreduce = LocalAllReduce(r, world, full.shape.hidden * full.B, self._bufs, pdl=pdl)
+            m.attach_allreduce(LocalAllReduce(r, world, full.shape.hidden * full.B, self._bufs, pdl=pdl), fused=fused)
             self.ranks.append(m)
         self._captured = False
+        # a GEMV whose epilogue waits for the peers' partial sums (fused all-reduce) keeps its SMs: every emulated rank
+        # sizes its grids for 1 / world of the device so that all ranks' kernels can be resident at once
+        self._sm_limit = max(1, torch.cuda.get_device_properties(dev).multi_processor_count // world) if fused else 0
+
+    def _limit(self, on: bool) -> None:
+        from ._lib import lib
+        lib().amqb_debug_set_sm_limit(self._sm_limit if on else 0)
 
     def timeouts(self) -> int:
         """Flag waits that gave up (0 in a correct run)."""
@@ -192,7 +215,9 @@ class LocalTPGroup:
         until its peers' partial sums arrive."""
         def go(m):
             m.step_eager()
+        self._limit(True)
         self._each(go)
+        self._limit(False)
 
     def capture(self) -> None:
         saved = [(m.pos.clone(), m.tokens.clone(), m._pos_h) for m in self.ranks]
@@ -203,9 +228,12 @@ class LocalTPGroup:
             m.pos.copy_(p)
             m.tokens.copy_(t)
             m._pos_h = ph
+            m.bump_generation()                 # positions were rewound: stale all-reduce slots must not match
         torch.cuda.synchronize()
+        self._limit(True)
         for s, m in zip(self.streams, self.ranks):
             m.graph = m._capture(stream=s, warm=False)
+        self._limit(False)
         self._captured = True
 
     def step(self) -> None:
@@ -250,13 +278,18 @@ def measure_tp70b(steps: int, warmup: int, world: int, rank: int, local: int, tp
     arch = sample_arch(shape, 3.0, seed=0)
     shard_plan(shape, tp)
     n_block = int(os.environ.get("AMQB_BLOCKS", shape.n_block))
-    ar_kind = os.environ.get("AMQB_AR", "amqb") if tp > 1 else "none"
+    # fused: the all-reduce is part of the row-parallel GEMV launch (default); amqb: separate one-shot push kernel;
+    # nccl: ncclAllReduce + residual add (baseline)
+    ar_kind = os.environ.get("AMQB_AR", "fused") if tp > 1 else "none"
     ms, lps, by = 0.0, 0, None
     if rank < tp:
         model = QuantDecoder(shape, arch, batch=1, max_seq=max(256, warmup + steps + 8), device=f"cuda:{local}",
                              seed=0, n_block=n_block, tp_rank=rank, tp_world=tp)
         if tp > 1:
-            model.allreduce = PeerAllReduce(rank, tp, shape.hidden) if ar_kind == "amqb" else NcclAllReduce()
+            if ar_kind == "nccl":
+                model.attach_allreduce(NcclAllReduce(), fused=False)
+            else:
+                model.attach_allreduce(PeerAllReduce(rank, tp, shape.hidden), fused=(ar_kind == "fused"))
         model.capture()
         lps = model.launches_per_step
         by = model.algorithmic_bytes_per_token()
@@ -281,8 +314,8 @@ def measure_tp70b(steps: int, warmup: int, world: int, rank: int, local: int, tp
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t[0])
     if rank < tp:
-        if tp > 1 and ar_kind == "amqb":
-            model.allreduce.close()
+        if tp > 1 and ar_kind != "nccl":
+            model.allreduce.close()             # collective over the tp ranks (tp == world here)
         del model
         torch.cuda.empty_cache()
     if rank != 0:

@@ -54,6 +54,8 @@ const char* amqb_last_error_string(void);
 int amqb_version(void);
 /* debug aid: when buf != NULL the next decode launches write 8 int64 globaltimer stamps per CTA */
 int amqb_debug_set_timeline(void* buf);
+/* debug aid: size grids as if the device had n SMs (0: all).  Lets several emulated tensor-parallel ranks share one GPU. */
+int amqb_debug_set_sm_limit(int n);
 
 /* ---- sizes ------------------------------------------------------------- */
 /* Bytes of the native weight buffer (codes + fp16 scale / zero*scale, interleaved
@@ -222,6 +224,7 @@ int amqb_attn_prefill(void* q_f16, const void* k_f16, const void* v_f16, void* k
  * block can be exported through CUDA IPC): create with amqb_ar_alloc, hand the 64-byte handle to
  * the other ranks (any host channel), map theirs with amqb_ar_open. */
 size_t amqb_ar_buffer_bytes(int max_elems, int world);
+size_t amqb_ar_ll_offset(int max_elems, int world);   /* where the fused all-reduce's 8-byte slots start in a buffer */
 int amqb_ar_alloc(size_t bytes, void** dev_ptr, void* ipc_handle_out64);
 int amqb_ar_open(const void* ipc_handle64, void** dev_ptr);
 int amqb_ar_close(void* dev_ptr);
