@@ -23,6 +23,10 @@ class Quantizer:
     pack = {"4bit_u8": BitPack.pack_4bit_u8, "3bit_32": BitPack.pack_3bit_32, "2bit_u8": BitPack.pack_2bit_u8}
     unpack = {"4bit_u8": BitPack.unpack_4bit_u8, "3bit_32": BitPack.unpack_3bit_32, "2bit_u8": BitPack.unpack_2bit_u8}
     unpack_view_dtype = {"4bit_u8": uint8, "3bit_32": int32, "2bit_u8": uint8}
+    # Arithmetic of the half-quadratic solver.  The reference picks it from the DEVICE (optimize.py:231: fp16 on CUDA,
+    # fp32 on the CPU).  None = like the reference on a GPU (fp16); torch.float32 = its CPU branch, which is the one the
+    # oracle pins and this library reproduces bit for bit.  AMQB_HQQ_SOLVER=fp32|fp16 overrides.
+    solver_dtype = None
 
     @classmethod
     def quantize(cls, tensor: Tensor, nbits: float = 4, channel_wise: bool = True, group_size: int = 64,
@@ -41,12 +45,21 @@ class Quantizer:
         if not W.is_cuda:
             raise RuntimeError("amq_b200.Quantizer.quantize: CUDA device required (no CPU path)")
         shape = W.shape
-        codes, scale, zero, _ = ops.hqq_quantize(W.reshape(shape[0], -1), int(nbits), group_size, round_zero)
+        import os
+        sd = {"fp32": torch.float32, "fp16": torch.float16}.get(os.environ.get("AMQB_HQQ_SOLVER", ""), cls.solver_dtype)
+        if sd is None:
+            sd = torch.float16
+        packable = bitpack and (nbits == 3 or (W.numel() // group_size) % (2 if nbits == 4 else 4) == 0)
+        res = ops.hqq_quantize(W.reshape(shape[0], -1), int(nbits), group_size, round_zero, solver_dtype=sd,
+                               packed=bool(packable), want_codes=not packable)
+        codes, scale, zero = res[0], res[1], res[2]
         meta = {"nbits": nbits, "group_size": group_size, "shape": shape, "scale": scale, "zero": zero,
                 "axis": axis, "packing": Quantizer.bit_to_packing[nbits]}
         meta["unpack_view_dtype"] = Quantizer.unpack_view_dtype[meta["packing"]]
         meta["view_as_float"] = view_as_float
-        if bitpack:
+        if packable:
+            W_q = res[4]                                    # packed in the quantize pass itself
+        elif bitpack:
             W_q = Quantizer.pack[meta["packing"]](codes)
         else:
             W_q = codes.to(tensor.dtype)

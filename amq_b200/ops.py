@@ -261,24 +261,39 @@ def hqq_unpack(bits: int, W_q: torch.Tensor, R: Optional[int] = None) -> torch.T
 
 
 @_on_device
-def hqq_quantize(W: torch.Tensor, bits: int, G: int = GROUP, round_zero: Optional[bool] = None):
-    """Quantizer.quantize (axis=1) -> (codes u8 [R,G], scale fp32 [R,1], zero fp32 [R,1], iters)."""
+def hqq_quantize(W: torch.Tensor, bits: int, G: int = GROUP, round_zero: Optional[bool] = None,
+                 solver_dtype: torch.dtype = torch.float32, packed: bool = False, want_codes: bool = True):
+    """Quantizer.quantize (axis=1) -> (codes u8 [R,G] or None, scale fp32 [R,1], zero fp32 [R,1], iters[, W_q]).
+    solver_dtype: torch.float32 = the arithmetic of the reference's CPU branch (bit-exact with it), torch.float16 = its
+    CUDA branch (optimize.py:231: every solver op rounded to fp16).  packed: also return HQQ's packed W_q (BitPack
+    layout), written in the same pass as the codes."""
     _req_cuda(W)
     if round_zero is None:
         round_zero = bits == 4
     N, K = W.shape
     R = N * K // G
     L = lib()
-    codes = torch.empty((R, G), dtype=torch.uint8, device=W.device)
+    codes = torch.empty((R, G), dtype=torch.uint8, device=W.device) if (want_codes or not packed) else None
     scale = torch.empty((R, 1), dtype=torch.float32, device=W.device)
     zero = torch.empty((R, 1), dtype=torch.float32, device=W.device)
     iters = torch.zeros(1, dtype=torch.int32, device=W.device)
     need = int(L.amqb_hqq_quantize_workspace_bytes(N, K, G))
-    wsb = torch.zeros(max(need, 16), dtype=torch.uint8, device=W.device)
+    wsb = torch.empty(max(need, 16), dtype=torch.uint8, device=W.device)
     Wh = W.half().contiguous()
-    check(L.amqb_hqq_quantize(bits, ptr(Wh), ptr(codes), ptr(scale), ptr(zero), int(round_zero),
-                              N, K, G, ptr(wsb), ctypes.c_size_t(wsb.numel()), ptr(iters), cur_stream()), "hqq_quantize")
-    return codes, scale, zero, iters
+    if not packed:
+        if solver_dtype != torch.float32:
+            raise ValueError("hqq_quantize: the fp16 solver is served by the packed entry point (packed=True)")
+        check(L.amqb_hqq_quantize(bits, ptr(Wh), ptr(codes), ptr(scale), ptr(zero), int(round_zero),
+                                  N, K, G, ptr(wsb), ctypes.c_size_t(wsb.numel()), ptr(iters), cur_stream()), "hqq_quantize")
+        return codes, scale, zero, iters
+    if bits == 3:
+        W_q = torch.empty(((R + 9) // 10, G), dtype=torch.int32, device=W.device)
+    else:
+        W_q = torch.empty((R // (2 if bits == 4 else 4), G), dtype=torch.uint8, device=W.device)
+    check(L.amqb_hqq_quantize_packed(bits, ptr(Wh), ptr(W_q), ptr(codes), ptr(scale), ptr(zero), int(round_zero),
+                                     int(solver_dtype == torch.float16), N, K, G, ptr(wsb), ctypes.c_size_t(wsb.numel()),
+                                     ptr(iters), cur_stream()), "hqq_quantize_packed")
+    return codes, scale, zero, iters, W_q
 
 
 @_on_device

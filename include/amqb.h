@@ -166,6 +166,13 @@ size_t amqb_hqq_quantize_workspace_bytes(int N, int K, int G);
 int amqb_hqq_quantize(int bits, const void* W_f16, uint8_t* codes, float* scale, float* zero,
                       int round_zero, int N, int K, int G, void* workspace, size_t workspace_bytes,
                       int* iters_run_out, void* stream);
+/* Same, writing HQQ's packed W_q (BitPack layout: u8 [R/2, G] / u8 [R/4, G] / int32 [ceil(R/10), G]) in the same pass;
+ * codes_or_null: optional u8 [R, G] copy of the codes.  solver_fp16 != 0: the solver's arithmetic is rounded to fp16 after
+ * every op like the reference's CUDA branch (optimize.py:231); 0: the fp32 arithmetic of its CPU branch, bit-exact with
+ * the reference (oracle-pinned). */
+int amqb_hqq_quantize_packed(int bits, const void* W_f16, void* W_q, uint8_t* codes_or_null, float* scale, float* zero,
+                             int round_zero, int solver_fp16, int N, int K, int G, void* workspace, size_t workspace_bytes,
+                             int* iters_run_out, void* stream);
 
 /* ---- decode-step glue ----------------------------- */
 /* enable != 0: the glue kernels below launch with programmatic stream serialization too, so a whole

@@ -38,6 +38,48 @@ def import_reference():
     return BitPack, Quantizer, BaseQuantizeConfig, GPTQLinear, pack_intweight
 
 
+def fp16_solver_fixtures(out_dir, report):
+    """The reference's CUDA branch runs the solver in fp16 (optimize.py:231).  No GPU here, so its own step function
+    (optimize_weights_proximal_legacy_step, unmodified) is driven on fp16 CPU tensors through the same loop as
+    optimize_weights_proximal_legacy (:234-247) and the final rounding of :254; the oracle's solver_dtype=fp16 mode must
+    agree exactly.  This pins the fp16 MODE's op sequence; the reference's CUDA kernels may still round a pow or a mean
+    differently from torch's CPU fp16 kernels in rare last-bit cases."""
+    from oracle import amq_oracle as O
+    from hqq.core.optimize import optimize_weights_proximal_legacy_step as step
+    G = 128
+    for nbits in (2, 3, 4):
+        torch.manual_seed(2000 + nbits)
+        N, K = 256, 512
+        W = (torch.randn(N, K) * 0.02).half()
+        Wf = W.float().reshape(-1, G)
+        mn, mx = Wf.min(1, keepdim=True)[0], Wf.max(1, keepdim=True)[0]
+        max_v = round(2 ** nbits - 1)
+        scale = (max_v / (mx - mn))
+        scale = torch.where((mx - mn).abs() <= 1e-4, torch.full_like(scale, 1.0), scale).clamp(max=2e4)
+        zero = -mn * scale
+        if nbits == 4:
+            zero = torch.round(zero)
+        W_f, sc, ze = Wf.half(), scale.half(), zero.half()
+        best = torch.tensor(torch.inf, dtype=torch.float32)
+        n_it = 0
+        for _ in range(20):
+            n_it += 1
+            W_r, W_q, ze, sc = step(W_f, sc, ze, [0, max_v], 1e1, 0.7, 1)
+            cur = torch.abs(W_f - W_r).mean().float()
+            if cur < best:
+                best = cur
+            else:
+                break
+        W_q = torch.round(Wf * sc + ze).clamp_(0, max_v)
+        codes, o_scale, o_zero, o_it = O.hqq_quantize(W, nbits, G, solver_dtype=torch.float16)
+        assert o_it == n_it, ("fp16 solver iterations", nbits, o_it, n_it)
+        assert np.array_equal(codes, W_q.to(torch.uint8).numpy()), ("fp16 solver codes", nbits)
+        assert torch.equal(o_zero, ze) and torch.equal(o_scale, 1.0 / sc), ("fp16 solver meta", nbits)
+        np.savez_compressed(os.path.join(out_dir, f"hqq_fp16solver_{nbits}bit.npz"), W=W.numpy(), codes=codes,
+                            scale=o_scale.float().numpy(), zero=o_zero.float().numpy(), solver_iters=np.int32(n_it))
+    report.append("fp16-solver fixtures (reference step function on fp16 CPU tensors) ok")
+
+
 def hqqlinear_state_fixtures(out_dir, report):
     """A state dict WRITTEN BY THE REFERENCE's HQQLinear (quantize.py:643-682), in both forms the reference produces:
     encoded (the default: every non-tensor entry as a tensor, core/utils.py:37-69) and plain (what
@@ -151,6 +193,7 @@ def main():
     report.append("quantize/dequant/gptq/ft ok")
 
     hqqlinear_state_fixtures(out_dir, report)
+    fp16_solver_fixtures(out_dir, report)
 
     # ---- 3. arch selection rule (amq_speed_benchmark.py:209-229) on a synthetic stats file
     import json

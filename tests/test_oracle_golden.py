@@ -115,3 +115,30 @@ def test_oracle_forward_linearity_and_bits_accounting():
     arch = {"linear": {"a": [2, 4], "b": [3, 3]}}
     want = (4 * 256 * (2.25 + 4.25) + 8 * 128 * (3.25 + 3.25)) / (4 * 256 + 8 * 128)
     assert abs(O.get_bits_usage(arch, cfg) - want) < 1e-12
+
+
+def test_sleef_powf_restatement_matches_torch(tmp_path):
+    """oracle/sleef_powf.c restates Sleef's powf (the kernel behind torch's CPU x.pow(p - 1) in the HQQ solver's shrink
+    operator, optimize.py:96-108) in scalar C; the CUDA solver carries the same operation sequence.  Pin: bit-equal to
+    torch.pow on 2 M positive inputs spanning the solver's range (single thread, numel % 16 == 0: torch's vector path)."""
+    import ctypes
+    import subprocess
+    import torch
+    src = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "sleef_powf.c")
+    so = tmp_path / "libsleefpow.so"
+    subprocess.run(["gcc", "-O2", "-mfma", "-ffp-contract=off", "-shared", "-fPIC", "-o", str(so), src, "-lm"], check=True)
+    L = ctypes.CDLL(str(so))
+    torch.manual_seed(0)
+    a = torch.cat([torch.rand(1_000_000) * 0.05 + 1e-7, torch.exp(torch.empty(1_000_000).uniform_(-30.0, 2.0))]).float()
+    y = 0.7 - 1
+    nt = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        p = a.pow(y).numpy()
+    finally:
+        torch.set_num_threads(nt)
+    x = a.numpy().copy()
+    out = np.empty_like(x)
+    L.sleef_powf(x.ctypes.data_as(ctypes.c_void_p), ctypes.c_float(np.float32(y)), out.ctypes.data_as(ctypes.c_void_p),
+                 ctypes.c_long(x.size))
+    assert np.array_equal(p.view(np.int32), out.view(np.int32))
