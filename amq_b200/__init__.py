@@ -10,5 +10,6 @@ from .backends.ft import FT_QuantLinear, pack_intweight, patch_hqq_to_ft, patch_
 from .core.bitpack import BitPack  # noqa: F401
 from .core.quantize import BaseQuantizeConfig, HQQLinear, Quantizer  # noqa: F401
 from .utils.patching import prepare_for_inference  # noqa: F401
+from .hf import AutoHQQHFModel  # noqa: F401
 
 __version__ = "0.1.0"

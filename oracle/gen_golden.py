@@ -80,6 +80,81 @@ def fp16_solver_fixtures(out_dir, report):
     report.append("fp16-solver fixtures (reference step function on fp16 CPU tensors) ok")
 
 
+def _tiny_llama(seed):
+    import transformers
+    cfg = transformers.LlamaConfig(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
+                                   num_key_value_heads=2, vocab_size=512, max_position_embeddings=128, rms_norm_eps=1e-5,
+                                   tie_word_embeddings=False)
+    torch.manual_seed(seed)
+    model = transformers.LlamaForCausalLM(cfg).half().eval()
+    for p in model.parameters():                      # N(0, 0.02) linears like the survey's parity recipe
+        p.requires_grad = False
+    return model
+
+
+def proxy_checkpoint_fixture(out_dir, report):
+    """A tiny Llama quantized and SAVED BY THE REFERENCE (AutoHQQHFModel.quantize_model + save_quantized,
+    models/base.py:267-434) -> tests/golden/qmodel_tiny_llama_3bit/{config.json, qmodel.pt}, plus the reference model's own
+    logits on a fixed prompt (CPU).  `accelerate` (only used by the reference's create_model) is stubbed."""
+    if "accelerate" not in sys.modules:
+        acc = types.ModuleType("accelerate")
+        import contextlib
+        acc.init_empty_weights = contextlib.nullcontext
+        sys.modules["accelerate"] = acc
+    from hqq.models.hf.base import AutoHQQHFModel
+    from hqq.core.quantize import BaseQuantizeConfig, HQQLinear
+    model = _tiny_llama(7)
+    AutoHQQHFModel.quantize_model(model, BaseQuantizeConfig(nbits=3, group_size=128), compute_dtype=torch.float16, device="cpu")
+    save_dir = os.path.join(out_dir, "qmodel_tiny_llama_3bit")
+    AutoHQQHFModel.save_quantized(model, save_dir)
+    ids = torch.tensor([[3, 17, 256, 99, 5, 480, 42, 7]])
+    with torch.no_grad():
+        logits = model(ids).logits.float()
+    torch.save({"input_ids": ids, "logits": logits}, os.path.join(save_dir, "reference_logits.pt"))
+    n_q = sum(type(m) is HQQLinear for m in model.modules())
+    report.append(f"proxy checkpoint written by the reference: {n_q} HQQLinear layers, logits {tuple(logits.shape)}")
+
+
+def hf_dropin_fixture(out_dir, report):
+    """The survey's model-level oracle: a tiny HF Llama whose 14 linears are the REFERENCE's GPTQLinear
+    modules (mixed 2/3/4 bits: HQQ quantize -> dequantize -> GPTQLinear.pack, kernel_switch_threshold = 0 so that forward
+    is the reference's own torch dequant + matmul, autogptq.py:245-283), assembled by setattr like
+    amq/amq_speed_benchmark.py:231-251, run on CPU: logits of a prompt and greedy tokens.  The fixture carries the fp16
+    model (state dict of the non-quantized parts), every linear's reference buffers and bit width, and the outputs."""
+    from hqq.core.quantize import Quantizer, BaseQuantizeConfig
+    from hqq.backends.autogptq import GPTQLinear
+    model = _tiny_llama(11)
+    rs = np.random.RandomState(5)
+    names = ["self_attn.q_proj", "self_attn.k_proj", "self_attn.v_proj", "self_attn.o_proj",
+             "mlp.gate_proj", "mlp.up_proj", "mlp.down_proj"]
+    arch = {n: rs.choice([2, 3, 4], size=2).tolist() for n in names}
+    linears = {}
+    for li, layer in enumerate(model.model.layers):
+        for name in names:
+            mod, lin = name.split(".")
+            src = getattr(getattr(layer, mod), lin)
+            bits = int(arch[name][li])
+            W = src.weight.data
+            cfg = BaseQuantizeConfig(nbits=bits, group_size=128)["weight_quant_params"]
+            W_q, meta = Quantizer.quantize(W, device="cpu", compute_dtype=torch.float16, **cfg)
+            meta16 = dict(meta, scale=meta["scale"].half(), zero=meta["zero"].half(), compute_dtype=torch.float16)
+            W_deq = Quantizer.dequantize(W_q, meta16)
+            N, K = W.shape
+            g = GPTQLinear(bits, 128, K, N, bias=False, kernel_switch_threshold=0)
+            g.pack(W_deq, meta16["scale"].reshape(N, -1), meta16["zero"].reshape(N, -1))
+            delattr(getattr(layer, mod), lin)
+            setattr(getattr(layer, mod), lin, g)
+            linears[f"{li}.{name}"] = {"bits": bits, "qweight": g.qweight.clone(), "scales": g.scales.clone(), "zeros": g.zeros.clone()}
+    ids = torch.tensor([[3, 17, 256, 99, 5, 480, 42, 7]])
+    with torch.no_grad():
+        logits = model(ids).logits.float()
+        gen = model.generate(ids, max_new_tokens=8, do_sample=False)
+    rest = {k: v.clone() for k, v in model.state_dict().items() if not any(t in k for t in ("qweight", "scales", "zeros"))}
+    torch.save({"config": model.config.to_dict(), "arch": arch, "linears": linears, "rest": rest, "input_ids": ids,
+                "logits": logits, "generated": gen}, os.path.join(out_dir, "hf_dropin_tiny_llama.pt"))
+    report.append(f"HF drop-in fixture: reference GPTQLinear modules in a tiny Llama, greedy tokens {gen[0, ids.shape[1]:].tolist()}")
+
+
 def hqqlinear_state_fixtures(out_dir, report):
     """A state dict WRITTEN BY THE REFERENCE's HQQLinear (quantize.py:643-682), in both forms the reference produces:
     encoded (the default: every non-tensor entry as a tensor, core/utils.py:37-69) and plain (what
@@ -194,6 +269,8 @@ def main():
 
     hqqlinear_state_fixtures(out_dir, report)
     fp16_solver_fixtures(out_dir, report)
+    proxy_checkpoint_fixture(out_dir, report)
+    hf_dropin_fixture(out_dir, report)
 
     # ---- 3. arch selection rule (amq_speed_benchmark.py:209-229) on a synthetic stats file
     import json

