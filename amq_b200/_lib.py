@@ -31,7 +31,7 @@ class GemvProblem(ctypes.Structure):
         ("y", ctypes.c_void_p), ("ldy", ctypes.c_int),
         ("bias", ctypes.c_void_p), ("residual", ctypes.c_void_p),
         ("prologue", ctypes.c_int), ("gamma", ctypes.c_void_p), ("eps", ctypes.c_float),
-        ("allreduce", ctypes.POINTER(ArCtx)), ("ar_call", ctypes.c_int),
+        ("allreduce", ctypes.POINTER(ArCtx)), ("ar_call", ctypes.c_int), ("after_gemv", ctypes.c_int),
     ]
 
 

@@ -108,13 +108,28 @@ static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, 
   int ncl = B / S;
   if (ncl > max_rb) ncl = max_rb;
   if (ncl < 1) ncl = 1;
+  // Co-resident build variant only (AMQB_CW=8, see the geometry note in gemv_mma.cuh).  Batch-1 launch types.  Two 10-warp CTAs fit an SM; they must always belong
+  // to CONSECUTIVE launches (measured without precautions: the block scheduler put two CTAs of one launch on 33 SMs and
+  // none on 53).  Type A: more than half of an SM's shared memory, so a second CTA of the same launch never fits; safe
+  // on an idle chip.  Type B (the caller's after_gemv hint: the previous kernel on the stream is a batch-1 GEMV launch):
+  // the remaining shared memory; it is placed while that predecessor holds a CTA on EVERY SM (place-holder CTAs top a
+  // launch up to the SM count), so only one fits per SM: predecessor + B fill the register file, A + B fill the shared
+  // memory.  In a decoder layer: q|k|v B (after down_proj), o_proj A (after attention), gate|up B, down_proj B.
+  int smem_target = kSmemTarget, xp_budget = kXprimeBudget;
+  size_t smem_min = 0;
+  if (M == 1 && kCoresident) {
+    const bool typeB = pr[0]->after_gemv != 0 && !getenv("AMQB_NO_CORESIDENT");
+    smem_target = typeB ? kSmemB : kSmemA;
+    smem_min = typeB ? 0 : kSmemAMin;
+    xp_budget = kXprimeBudgetM1;
+  }
   // x' chunking along K when M * K is too large for shared memory
   int max_xp = 0, max_kc = 0, acc_blocks = 0, max_slice = 0;
   for (int i = 0; i < count; ++i) {
     DevProblem& P = L.prob[i];
     const int slice = (P.n_g + S - 1) / S;
     const int per_group = xp_group_bytes(P.bits, M);
-    int kc = kXprimeBudget / per_group;
+    int kc = xp_budget / per_group;
     if (kc >= slice) kc = slice;
     else kc = (kc / kCW) * kCW;                     // a chunk is whole half-stages: group gl stays with consumer warp gl % kCW
     if (kc < 1) return fail(AMQB_ERR_UNSUPPORTED_SHAPE, "gemv: x' chunk does not fit shared memory");
@@ -144,23 +159,34 @@ static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, 
     L.dbg_delay_ns = d ? atoi(d) : 0;
   }
   L.xprime_bytes = (max_xp + 127) & ~127;
-  L.xp_variants = (M == 1 && count > 1 && 3 * L.xprime_bytes <= 96 * 1024) ? 3 : 1;
+  L.xp_variants = (M == 1 && count > 1 && 3 * L.xprime_bytes <= (kCoresident ? 40 : 96) * 1024) ? 3 : 1;
   L.xs_floats = (2 * max_kc * MB * 8 + 31) & ~31;
   const size_t rs = red_stride(M);
   const size_t fixed = 384 + (size_t)L.xs_floats * 4 + 16 * kCW * 4 + (size_t)L.xp_variants * L.xprime_bytes +
                        (size_t)2 * kCW * rs * 4 + (size_t)acc_blocks * rs * 4 + (S > 1 ? (size_t)count * S * rs * 4 : 0) + 128;
   // stage = two records per consumer warp; one when that would leave fewer than two stages (M > 1 with a large x')
   int stage_recs = max_slice < kStageRecs ? max_slice : kStageRecs;
-  if (fixed + 2 * (size_t)stage_recs * max_rec > (size_t)kSmemTarget && stage_recs > kCW) stage_recs = kCW;
+  if (fixed + 2 * (size_t)stage_recs * max_rec > (size_t)smem_target && stage_recs > kCW) stage_recs = kCW;
   L.stage_recs = stage_recs;
   L.stage_bytes = stage_recs * max_rec;
-  if (fixed + 2 * (size_t)L.stage_bytes > (size_t)kSmemTarget)
+  if (fixed + 2 * (size_t)L.stage_bytes > (size_t)smem_target)
     return fail(AMQB_ERR_UNSUPPORTED_SHAPE, "gemv: shared memory budget exceeded");
-  int ns = (int)(((size_t)kSmemTarget - fixed) / L.stage_bytes);
+  int ns = (int)(((size_t)smem_target - fixed) / L.stage_bytes);
   if (ns > 8) ns = 8;
   L.n_stages = ns;
-  const size_t smem = fixed + (size_t)ns * L.stage_bytes;
-  const int grid = ncl * S;
+  {
+    const char* e = getenv("AMQB_WINDOW_KB");              // 0: no window (the whole ring is requested at once)
+    const int wkb = e ? atoi(e) : 64;
+    int w = wkb > 0 ? (wkb * 1024 + L.stage_bytes / 2) / L.stage_bytes : ns;
+    if (w < 1) w = 1;
+    if (w > ns) w = ns;
+    L.window = w;
+  }
+  size_t smem = fixed + (size_t)ns * L.stage_bytes;
+  if (smem < smem_min) smem = smem_min;
+  L.ncl = ncl;
+  int grid = ncl * S;
+  if (M == 1 && kCoresident && grid < B) grid = (B / S) * S;          // place holders: every SM holds a CTA of this launch
   if (pro == AMQB_PRO_NONE) return launch_pro0(L, grid, smem, pdl, st);
   if (pro == AMQB_PRO_RMSNORM) return launch_pro1(L, grid, smem, pdl, st);
   return launch_pro2(L, grid, smem, pdl, st);

@@ -46,13 +46,29 @@ __device__ __forceinline__ long long gtime() {
 #define AMQB_DBG(...)
 #endif
 
-constexpr int kCW = 16;                      // consumer warps
+// Geometry (AMQB_CW, compile time).  Shipped: 16 consumer warps + producer + reducer, one CTA per SM with a 222 KB ring.
+// AMQB_CW=8 builds the CO-RESIDENT variant: 10-warp CTAs at 96 registers, two per SM, sized (gemv_api.cu) so that the two
+// are always CTAs of CONSECUTIVE launches - launch i+1 becomes resident next to launch i (programmatic dependent launch)
+// and fills its ring while launch i computes.  Measured on B200 (profiles/r02_coresident_experiment.txt): the placement
+// scheme works (one CTA of each launch per SM, rings full before griddepcontrol.wait returns), but eight consumer warps
+// run both the x' builder and the record loop ~2x slower than sixteen (two warps per scheduler do not hide the
+// LDS -> LOP3 -> IMMA latencies), and two CTAs of sixteen do not fit the register file: 1.47-1.58 ms per step against
+// 1.07 ms.  Kept as a build variant, not shipped.
+#ifndef AMQB_CW
+#define AMQB_CW 16
+#endif
+constexpr int kCW = AMQB_CW;                 // consumer warps
 constexpr int kCThreads = kCW * 32;
-constexpr int kThreads = kCThreads + 64;     // + producer warp + reducer warp = 576 threads
+constexpr int kThreads = kCThreads + 64;     // + producer warp + reducer warp
 constexpr int kStageRecs = 2 * kCW;          // records per pipeline stage: two per consumer warp (w and w + kCW)
 constexpr int kMaxProblems = 4;
-constexpr int kXprimeBudget = 72 * 1024;
-constexpr int kSmemTarget = 222 * 1024;
+constexpr int kXprimeBudget = 72 * 1024;     // M > 1 launches (one CTA per SM)
+constexpr int kSmemTarget = 222 * 1024;      //   "
+// batch 1: shared memory per CTA by launch type.  Type A (may be placed on an idle SM): more than half an SM, so that
+// two CTAs of the same launch can never share one.  Type B (placed while its predecessor holds every SM): the rest.
+constexpr int kSmemA = 118 * 1024, kSmemAMin = 116 * 1024, kSmemB = 106 * 1024;
+constexpr int kXprimeBudgetM1 = 44 * 1024;
+constexpr bool kCoresident = AMQB_CW <= 8;
 constexpr int kMaxCluster = 8;
 constexpr uint32_t kMagicI = 0x4B400000u;    // int32 accumulators start at the bit pattern of 1.5 * 2^23 ...
 constexpr float kMagicF = 12582912.f;        // ... so that (float&)acc - 1.5 * 2^23 == the integer sum (|sum| < 2^22)
@@ -117,6 +133,8 @@ struct GemvLaunch {
   int copy_recs;         // records per cp.async.bulk (a stage is issued as several bulk copies)
   int dbg_delay_ns;      // debug: consumers idle this long after building x' (0 in production)
   int xp_variants;       // 3: x' kept per bit width so problems sharing x reuse it; 1: rebuilt per problem
+  int ncl;               // clusters (CTAs at S == 1) that own row blocks; the grid's remaining clusters are place holders
+  int window;            // stages the producer keeps in flight (see the producer loop)
   int pair;              // 1: consumers take two pipeline stages per iteration (A/B switch AMQB_NO_PAIR=1 clears it)
   long long* dbg;        // optional per-CTA timeline (16 x int64 per CTA), NULL in production
 };
@@ -303,13 +321,17 @@ __device__ __forceinline__ void emit_item(const float (&xf)[4], const XLane (&xl
 // written): kPre items are requested at once; gamma (a weight) is fetched before griddepcontrol.wait.  Items are then
 // processed two at a time, branch-free (predicated stores), so two dependency chains interleave.
 #ifndef AMQB_KPRE
-#define AMQB_KPRE 2      // measured: 4 and 8 shorten the SiLU builder of down_proj but the longer code costs every launch more
+#define AMQB_KPRE (AMQB_CW <= 8 ? 4 : 2)      // items requested at once (K = 4096: 32 groups / consumer warps); measured at 16 warps: 4 and 8 shorten the SiLU builder of down_proj but the longer code costs every launch more
 #endif
-constexpr int kPre = AMQB_KPRE;
+#ifndef AMQB_KPRE_SILU
+#define AMQB_KPRE_SILU AMQB_KPRE
+#endif
+template <int PRO> struct PreItems { static constexpr int value = PRO == AMQB_PRO_SILU_MUL ? AMQB_KPRE_SILU : AMQB_KPRE; };
 template <int PRO>
 __device__ __forceinline__ void build_xprime(const DevProblem& P, int g_lo, int len, uint8_t* xp, float2* xsd, int cw,
                                              int lane, int mask, int variants, int var_stride, const XLane (&xl)[3],
                                              bool& waited, long long* dbgp = nullptr) {
+  constexpr int kPre = PreItems<PRO>::value;
   const int koff = 16 * (lane >> 2) + 2 * (lane & 3);     // this lane's first k inside a group (second pair at + 8)
   const int items = len > cw ? (len - cw + kCW - 1) / kCW : 0;      // gl = cw, cw + kCW, ...
   uint8_t* vbase[3];
@@ -711,7 +733,7 @@ __device__ __forceinline__ void store_out(const DevProblem& P, int n, int col, f
 
 // ---------------------------------------------------------------------------------------------
 template <int MB, int KIND, int PRO>
-__global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_constant__ GemvLaunch L) {
+__global__ void __launch_bounds__(kThreads, kCoresident ? 2 : 1) gemv_mma_kernel(const __grid_constant__ GemvLaunch L) {
   constexpr bool M1 = KIND == kKindM1;
   constexpr int RS = M1 ? 32 : 2 * MB * 128;            // red_stride(M): floats one warp deposits per row block
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -729,12 +751,23 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = L.S;
   const int rank = S > 1 ? (int)cluster_ctarank() : 0;
-  const int cid = blockIdx.x >> L.log2S, ncl = gridDim.x >> L.log2S;
+  const int cid = blockIdx.x >> L.log2S, ncl = L.ncl;
   const int NS = L.n_stages;
   const int M = M1 ? 1 : L.M;
 
+  if (cid >= ncl) {
+    // Place holder: a launch with fewer row blocks than SMs (N = 4096: 128) still occupies EVERY SM, because the next
+    // launch relies on finding one CTA of this one on each SM (a CTA slot left free would let the block scheduler put
+    // two CTAs of the next launch there and none elsewhere).  It holds its slot until the next launch has been placed:
+    // that needs the launch before this one to retire, which is when griddepcontrol.wait returns here; the margin
+    // covers the placement itself.  (All CTAs of a cluster are place holders together: no cluster barrier is skipped.)
+    pdl_launch_dependents();
+    pdl_wait();
+    __nanosleep(1500);
+    return;
+  }
   AMQB_STAMP(0);
-  AMQB_DBG(if (L.dbg && tid == 0) L.dbg[blockIdx.x * 16 + 12] = gtime();)
+  AMQB_DBG(if (L.dbg && tid == 0) { L.dbg[blockIdx.x * 16 + 12] = gtime(); uint32_t sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); L.dbg[148 * 16 + blockIdx.x * 32 + 31] = sm + 1; L.dbg[148 * 16 + blockIdx.x * 32 + 30] = gtime(); })
   // The problem descriptors are copied from the kernel-parameter bank into shared memory by one load per thread, all in
   // flight at once: a first touch of a parameter line costs ~0.5 us (measured: every switch to the next problem of a
   // grouped launch stalled that long on its descriptor), and three roles x four problems would pay it one after another.
@@ -768,7 +801,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
     if (lane == 0) {
       AMQB_DBG(if (L.dbg_delay_ns < -1) { const long long t_end = gtime() - L.dbg_delay_ns; while (gtime() < t_end) {} })
       const uint64_t pol = policy_evict_first();
-      int s = 0, ph = 0;
+      int s = 0, ph = 0, it = 0;
       bool wrapped = false;
       for (int p = 0; p < L.count; ++p) {
         const DevProblem P = sprob[p];
@@ -781,6 +814,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_mma_kernel(const __grid_cons
             for (int g = c_lo; g < c_hi; g += L.stage_recs) {
               const int nrec = (c_hi - g) < L.stage_recs ? (c_hi - g) : L.stage_recs;
               if (wrapped) mbar_wait(smem_u32(&bars[NS + s]), ph ^ 1);
+              // in-flight window: the copy engine serves its outstanding bulk copies side by side, not first come first
+              // served, so with a whole ring requested at once the FIRST stage lands only when most of the ring has
+              // (measured: 5.6 us after entry for gate|up, consumers idle until then).  Keeping only `window` stages
+              // in flight (enough bytes to cover the HBM latency-bandwidth product) makes the stages land in order.
+              if (it >= L.window) {
+                const int j = it - L.window;
+                mbar_wait(smem_u32(&bars[j % NS]), (j / NS) & 1);
+              }
+              ++it;
               const uint32_t bytes = nrec * rbytes;
               mbar_expect_tx(smem_u32(&bars[s]), bytes);
               for (int r0 = 0; r0 < nrec; r0 += L.copy_recs) {
@@ -1106,7 +1148,17 @@ template <int MB, int KIND, int PRO>
 static int launch_variant(const GemvLaunch& L, int grid, size_t smem, int pdl, cudaStream_t st) {
   auto kern = gemv_mma_kernel<MB, KIND, PRO>;
   static PerDeviceOnce attr;
-  if (attr.first()) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+  if (attr.first()) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    // the shared-memory / L1 split is per kernel: without this the driver may pick a carve-out that holds ONE of these
+    // CTAs even when two would fit the SM's other limits
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (getenv("AMQB_DBG_OCC")) {
+      int nb = -1;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem);
+      fprintf(stderr, "gemv<%d,%d,%d>: %d threads, %zu B dynamic smem -> %d CTAs per SM\n", MB, KIND, PRO, kThreads, smem, nb);
+    }
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreads);

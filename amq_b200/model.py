@@ -231,6 +231,13 @@ class QuantDecoder:
             db, dw, dn, dk = L["mlp.down_proj"]
             down = [fuse(prob(db, dw, self.gu, (self.part if tp else self.h).data_ptr(), dn, dk, gu_ld, self.H, None,
                               None if tp else self.h, PRO_SILU_MUL), 2 * li + 1)]
+            # scheduling hint (include/amqb.h, after_gemv): which launches directly follow another batch-1 GEMV launch on the
+            # stream.  q|k|v follows the previous layer's down_proj, gate|up follows o_proj, down_proj follows gate|up;
+            # o_proj follows the attention kernel, and a separate all-reduce kernel breaks the chain as well.
+            separate_ar = self.allreduce is not None and self.ar_ctx is None
+            qkv[0].after_gemv = int(li > 0 and not separate_ar)
+            gu[0].after_gemv = int(not separate_ar)
+            down[0].after_gemv = 1
             self._plan.append({"qkv": (ops.GemvProblem * 3)(*qkv), "o": (ops.GemvProblem * 1)(*o),
                                "gu": (ops.GemvProblem * 2)(*gu), "down": (ops.GemvProblem * 1)(*down), "L": L})
 

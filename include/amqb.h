@@ -122,6 +122,10 @@ typedef struct {
   float eps;
   const amqb_ar_ctx* allreduce; /* host pointer or NULL: fuse the tensor-parallel all-reduce into the epilogue */
   int ar_call;              /* index of this all-reduce inside the step (0 .. 255; consecutive calls alternate parity) */
+  int after_gemv;           /* scheduling hint, batch 1 (first problem of a launch counts): nonzero = the kernel launched on
+                             * this stream right before this one is an amqb batch-1 GEMV launch.  Such a launch is sized to
+                             * sit NEXT TO its predecessor on every SM and stream its weights while the predecessor still
+                             * computes; 0 (unknown / follows another kernel) is always safe */
 } amqb_gemv_problem;
 
 /* One launch over `count` independent problems sharing M (q/k/v or gate/up, mixed bit-widths

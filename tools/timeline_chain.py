@@ -18,8 +18,11 @@ L.amqb_set_pdl(1)
 bufs = []
 orig = m._gemv
 names = ["qkv", "o", "gu", "down"]
+# buffers are allocated BEFORE the capture: a torch.zeros inside it would put a fill kernel between the decode launches
+# and break the programmatic-dependent-launch chain this tool is meant to observe
+pool = [torch.zeros(148 * 16 + 148 * 32, dtype=torch.int64, device=m.dev) for _ in range(4 * nb)]
 def hooked(arr, n):
-    b = torch.zeros(148 * 16 + 148 * 32, dtype=torch.int64, device=m.dev)
+    b = pool[len(bufs)]
     bufs.append((names[len(bufs) % 4], n, b))
     L.amqb_debug_set_timeline(ctypes.c_void_p(b.data_ptr()))
     orig(arr, n)
@@ -37,7 +40,6 @@ else:
         with torch.cuda.graph(g, stream=st_):
             m._step_launches()
         for _ in range(3):
-            m.pos.fill_(100)
             g.replay()
     st_.synchronize()
 torch.cuda.synchronize()
@@ -50,11 +52,12 @@ for i, (name, n, b) in enumerate(bufs):
     live = d[:, 0] > 0
     rbs = rbs[live]
     d = d[d[:, 0] > 0]
+    gt = full_b[148 * 16:].view(148, 32)[live][:, 30]       # int64 globaltimer at entry (slot 12 is reused by the third problem's stamps)
     if t0 is None:
-        t0 = d[:, 12].min()
+        t0 = int(gt.min())
     if i < 4 * (nb - 3):         # print the last three layers
         continue
-    ent = (d[:, 12] - t0) / 1e3            # us, globaltimer at entry
+    ent = (gt - t0).double() / 1e3          # us, globaltimer at entry (subtracted as integers: 1.8e18 ns does not fit a double)
     def st(col):                            # SM clocks since the CTA's own entry -> us
         c = d[:, col]; ok = c > 0
         c = (c[ok] - d[ok, 0]) / 1965.0
@@ -62,6 +65,10 @@ for i, (name, n, b) in enumerate(bufs):
     print(f"{name:5s} ctas {d.shape[0]:3d} | entry(abs) {ent.min():7.2f} {ent.median():7.2f} {ent.max():7.2f} | since entry: init {st(13)} | pre-wait {st(1)} | "
           f"waited {st(15)} | x arrived {st(14)} | x' built {st(5)} | it0 data {st(8)} done {st(9)} | it1 data {st(10)} done {st(11)} | recs done(last p) {st(6 + 4 * (n - 1))} | cons exit {st(2)} | reducer done {st(3)}")
 
+    smid = rbs[:, 31].long() - 1
+    cnt = torch.bincount(smid[smid >= 0], minlength=148)
+    endt = ent + (d[:, 3] - d[:, 0]).clamp(min=0) / 1965.0
+    print(f"      SMs with 0/1/2+ CTAs of this launch: {(cnt == 0).sum().item()}/{(cnt == 1).sum().item()}/{(cnt >= 2).sum().item()} | reducer done(abs) {endt.min():7.2f} {endt.median():7.2f} {endt.max():7.2f}")
     if os.environ.get("ROWBLOCKS") == "1" and name in ("gu", "qkv"):
         ent0 = d[:, 0]
         line = []
