@@ -200,3 +200,99 @@ class AutoHQQHFModel:
         model.hqq_quantized = True
         model.base_class = cls
         return model
+
+
+class GraphedHFDecoder:
+    """Greedy token-by-token decoding of an HF causal LM THROUGH ITS OWN forward — the module path of the reference's
+    benchmark (amq/amq_speed_benchmark.py:231-251: linears swapped for GPTQLinear / FT_QuantLinear by setattr,
+    amq/utils/speed.py:23-46: generate) — with the single-token forward captured once in a CUDA graph over a static KV
+    cache.  The arithmetic is HF's module tree calling this library's module forwards; the graph only removes the host
+    work between the ~1500 launches of a token (HF eager: ~17 ms of Python per token on the 7B shape; the graph: GPU time).
+
+        dec = GraphedHFDecoder(model, max_cache_len=256)
+        tokens = dec.generate(input_ids, max_new_tokens=128)          # [B, prompt + new], greedy
+
+    The next-token argmax, its feedback into the input buffer and the position advance are part of the captured step, so a
+    replay needs no host input at all."""
+
+    def __init__(self, model: nn.Module, max_cache_len: int):
+        from transformers import StaticCache
+        self.model = model
+        self.max_cache_len = int(max_cache_len)
+        self.device = next(p for p in model.parameters()).device
+        self._StaticCache = StaticCache
+        self.cache = None
+        self.ids = None
+        self.pos = torch.zeros(1, dtype=torch.long, device=self.device)
+        self.graph = None
+        self.logits = None
+
+    def _forward_step(self):
+        out = self.model(self.ids, past_key_values=self.cache, cache_position=self.pos, use_cache=True)
+        self.logits = out.logits
+        self.ids.copy_(out.logits[:, -1:].argmax(-1))
+        self.pos.add_(1)
+
+    @torch.inference_mode()
+    def prefill(self, input_ids: torch.Tensor) -> None:
+        """Consume the prompt eagerly (one forward over all prompt tokens), leave the first generated token in self.ids."""
+        B, T = input_ids.shape
+        if T + 1 > self.max_cache_len:
+            raise ValueError("GraphedHFDecoder: prompt does not fit max_cache_len")
+        if self.cache is None or self.ids is None or self.ids.shape[0] != B:
+            self.cache = self._StaticCache(config=self.model.config, max_cache_len=self.max_cache_len)
+            self.ids = torch.zeros(B, 1, dtype=torch.long, device=self.device)
+            self.graph = None
+        else:
+            self.cache.reset()
+        out = self.model(input_ids.to(self.device), past_key_values=self.cache,
+                         cache_position=torch.arange(T, device=self.device), use_cache=True)
+        self.ids.copy_(out.logits[:, -1:].argmax(-1))
+        self.pos.fill_(T)
+        self._pos_h = T
+
+    @torch.inference_mode()
+    def _capture(self) -> None:
+        ids0, pos0 = self.ids.clone(), self.pos.clone()
+        # a static cache layer keeps its own device-side fill count (transformers 5.x StaticLayer.cumulative_length, advanced
+        # in place by every update): the warm-up steps must leave it where it was
+        counters = [l.cumulative_length for l in getattr(self.cache, "layers", []) if torch.is_tensor(getattr(l, "cumulative_length", None))]
+        saved = [c.clone() for c in counters]
+
+        def rewind():
+            self.ids.copy_(ids0); self.pos.copy_(pos0)
+            for c, v in zip(counters, saved):
+                c.copy_(v)
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for _ in range(2):                       # warm-up at the current position (writes the cache row a real step rewrites)
+                rewind()
+                self._forward_step()
+            rewind()
+            s.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
+                self._forward_step()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        self.graph = g
+
+    @torch.inference_mode()
+    def step(self) -> torch.Tensor:
+        """One token: replays the captured forward; returns the device buffer holding the NEW token ids [B, 1]."""
+        if self._pos_h + 1 > self.max_cache_len:
+            raise RuntimeError("GraphedHFDecoder: static cache is full")
+        if self.graph is None:
+            self._capture()
+        self.graph.replay()
+        self._pos_h += 1
+        return self.ids
+
+    @torch.inference_mode()
+    def generate(self, input_ids: torch.Tensor, max_new_tokens: int) -> torch.Tensor:
+        self.prefill(input_ids)
+        out = [input_ids.to(self.device), self.ids.clone()]
+        for _ in range(max_new_tokens - 1):
+            out.append(self.step().clone())
+        return torch.cat(out, dim=1)

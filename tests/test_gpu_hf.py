@@ -120,3 +120,22 @@ def test_hf_decoder_with_swapped_modules_matches_reference_modules(amq, backend)
     assert _max_rel(logits, d["logits"]) <= 2e-2
     assert torch.equal(logits.argmax(-1), d["logits"].argmax(-1))
     assert torch.equal(gen, d["generated"])
+    # the same module path replayed from a CUDA graph over a static cache (amq_b200.hf.GraphedHFDecoder): same tokens
+    from amq_b200.hf import GraphedHFDecoder
+    # (compared with the SAME forward run eagerly over the same static cache: the static-cache attention call sees other
+    # shapes than generate()'s dynamic cache, and this random-init model's greedy choices sit on fp16 near-ties)
+    from transformers import StaticCache
+    with torch.inference_mode():
+        cache = StaticCache(config=model.config, max_cache_len=64)
+        T = ids.shape[1]
+        out = model(ids, past_key_values=cache, cache_position=torch.arange(T, device="cuda"), use_cache=True)
+        tok, pos, toks = out.logits[:, -1:].argmax(-1), torch.tensor([T], device="cuda"), []
+        for _ in range(8):
+            toks.append(tok.clone())
+            tok = model(tok, past_key_values=cache, cache_position=pos, use_cache=True).logits[:, -1:].argmax(-1)
+            pos = pos + 1
+        eager = torch.cat([ids] + toks, dim=1).cpu()
+    dec = GraphedHFDecoder(model, max_cache_len=64)
+    assert torch.equal(dec.generate(ids, 8).cpu(), eager)
+    assert torch.equal(dec.generate(ids, 8).cpu(), eager)                  # replay after a cache reset
+    assert torch.equal(eager[:, : T + 1], d["generated"][:, : T + 1])      # first generated token: same prompt pass

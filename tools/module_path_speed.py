@@ -42,6 +42,34 @@ for li, layer in enumerate(model.model.layers):
 torch.cuda.synchronize()
 ids = torch.randint(0, shape.vocab - 1, (1, 64), device=dev)
 steps = int(os.environ.get("STEPS", "64"))
+# torch 2.11's default SDPA choice on B200 (cuDNN) builds a plan per new (q_len, kv_len): 3.7 ms of HOST time per call when the
+# cache grows by one position per token (tools/profile_hf_step.py).  The reference's protocol does not pin a backend, so both
+# are reported: the default, and SDPA restricted to the flash / memory-efficient / math kernels.
+from torch.nn.attention import sdpa_kernel, SDPBackend
+res = {}
+def hf_tok_s():
+    with torch.inference_mode():
+        out = model(ids, use_cache=True)
+        past, tok = out.past_key_values, out.logits[:, -1:].argmax(-1)
+        for _ in range(8):
+            out = model(tok, past_key_values=past, use_cache=True); past, tok = out.past_key_values, out.logits[:, -1:].argmax(-1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = model(tok, past_key_values=past, use_cache=True); past, tok = out.past_key_values, out.logits[:, -1:].argmax(-1)
+        torch.cuda.synchronize()
+        return steps / (time.perf_counter() - t0)
+with sdpa_kernel([SDPBackend.FLASH_ATTENTION, SDPBackend.EFFICIENT_ATTENTION, SDPBackend.MATH]):
+    res["module_path_tok_s_sdpa_no_cudnn"] = hf_tok_s()
+from amq_b200.hf import GraphedHFDecoder
+dec = GraphedHFDecoder(model, max_cache_len=256)
+dec.prefill(ids)
+for _ in range(8): dec.step()
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(steps): dec.step()
+torch.cuda.synchronize()
+res["module_path_graphed_tok_s"] = steps / (time.perf_counter() - t0)
+del dec
 with torch.inference_mode():
     out = model(ids, use_cache=True)
     past, tok = out.past_key_values, out.logits[:, -1:].argmax(-1)
@@ -53,8 +81,8 @@ with torch.inference_mode():
         out = model(tok, past_key_values=past, use_cache=True); past, tok = out.past_key_values, out.logits[:, -1:].argmax(-1)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-res = {"module_path_tok_s": steps / dt, "ms_per_token": dt / steps * 1e3, "blocks": nb, "forward_calls_per_token": 7 * nb,
-       "how": "HF LlamaForCausalLM.forward with DynamicCache, eager, 7 quantized-linear module calls per block"}
+res.update({"module_path_tok_s": steps / dt, "ms_per_token": dt / steps * 1e3, "blocks": nb, "forward_calls_per_token": 7 * nb,
+       "how": "HF LlamaForCausalLM.forward with DynamicCache, eager, 7 quantized-linear module calls per block"})
 del model, past, out
 torch.cuda.empty_cache()
 from amq_b200.model import QuantDecoder
