@@ -245,6 +245,9 @@ struct TcArgs {
   const __half* bias;
   int bits, M, N, K;
   int nws;                 // W ring depth
+  int splits;              // K split over gridDim.z (few output tiles: short prompts, k / v projections); 1 = none
+  float* part;             // splits > 1: fp32 partial tiles [CTA][128 m][128 n]
+  int* tickets;            // splits > 1: one arrival counter per output tile (left at zero)
   int dbg;                 // AMQB_TC_DBG ablation mask (1: no dequant, 2: no MMA, 4: tiny X copies) — timing experiments only
 };
 
@@ -271,7 +274,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     if (A.dbg & 8) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); stamps[i] = t; }
   };
   if (tid == 0) stamp(0);
-  const int NG = A.K / kBlockK;
+  // K split: this CTA owns k blocks [kb0, kb0 + NG) of the NGA in the row (local index kb below)
+  const int NGA = A.K / kBlockK;
+  const int kb0 = (int)(((long long)NGA * blockIdx.z) / A.splits);
+  const int NG = (int)(((long long)NGA * (blockIdx.z + 1)) / A.splits) - kb0;
 
   if (tid == 0) {
     for (int i = 0; i < A.nws; ++i) { mbar_init(smem_u32(&bars[kBarWFull + i]), 1); mbar_init(smem_u32(&bars[kBarWEmpty + i]), 8); }
@@ -296,14 +302,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         mbar_expect_tx(smem_u32(&bars[kBarWFull + ws]), 4 * rbytes);
         for (int r = 0; r < 4; ++r)
           bulk_g2s(smem_u32(w_ring + (size_t)ws * w_stage + (size_t)r * rbytes),
-                   A.w + ((size_t)(n_tile * 4 + r) * NG + kb) * rbytes, rbytes, smem_u32(&bars[kBarWFull + ws]));
+                   A.w + ((size_t)(n_tile * 4 + r) * NGA + kb0 + kb) * rbytes, rbytes, smem_u32(&bars[kBarWFull + ws]));
         if (++ws == A.nws) { ws = 0; ph ^= 1; }
       }
     }
   } else if (warp == 3) {
     // ===== X producer: two pre-swizzled 64-k atoms of the m tile per k block
     if (lane == 0) {
-      const uint8_t* xsrc = A.xs + (size_t)m_tile * (A.K / 64) * kAtomBytes;
+      const uint8_t* xsrc = A.xs + ((size_t)m_tile * (A.K / 64) + 2 * (size_t)kb0) * kAtomBytes;
       const uint32_t xbytes = (A.dbg & 4) ? 16u * CL : (uint32_t)kXBytes;
       int st = 0; uint32_t ph = 0;
       pdl_wait();                          // the pre-swizzle pass (launched just before, overlapped via PDL) is complete
@@ -404,15 +410,51 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     {
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 32), r);
+      if (A.splits == 1) {
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const int m = m_tile * kTileM + cq * 32 + c;
-        if (m < A.M) A.y[(size_t)m * A.N + n] = __float2half_rn(__uint_as_float(r[c]) + bv);
+        for (int c = 0; c < 32; ++c) {
+          const int m = m_tile * kTileM + cq * 32 + c;
+          if (m < A.M) A.y[(size_t)m * A.N + n] = __float2half_rn(__uint_as_float(r[c]) + bv);
+        }
+      } else {
+        // K split: fp32 partial tile of this CTA, [m][n] so that a warp's store is one 128-byte line
+        float* pt = A.part + (((size_t)blockIdx.z * gridDim.y + m_tile) * gridDim.x + n_tile) * (kTileM * kTileN);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) __stcg(pt + (cq * 32 + c) * kTileN + q * 32 + lane, __uint_as_float(r[c]));
       }
     }
   }
   if (tid == 128) stamp(8);
   tc_fence_before();
+  if (A.splits > 1) {
+    // the last CTA of an output tile to arrive adds the partial tiles in split order (same bits whoever is last) and
+    // writes y; the counter is left at zero for the next launch / graph replay
+    volatile int& s_last = *reinterpret_cast<volatile int*>(smem + 520);      // header word (dynamic shared memory is at the CTA limit)
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      int* tk = A.tickets + m_tile * gridDim.x + n_tile;
+      const int t = atomicAdd(tk, 1);
+      s_last = (t == A.splits - 1);
+      if (s_last) *tk = 0;
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      const size_t zstride = (size_t)gridDim.y * gridDim.x * (kTileM * kTileN);
+      const float* p0 = A.part + ((size_t)m_tile * gridDim.x + n_tile) * (kTileM * kTileN);
+      for (int e = tid; e < kTileM * kTileN; e += kTcThreads) {
+        const int ml = e >> 7, nl = e & 127;
+        const int m = m_tile * kTileM + ml;
+        if (m >= A.M) continue;
+        float v = 0.f;
+        for (int z = 0; z < A.splits; ++z) v += __ldcg(p0 + (size_t)z * zstride + e);
+        const int nn = n_tile * kTileN + nl;
+        if (A.bias) v += __half2float(A.bias[nn]);
+        A.y[(size_t)m * A.N + nn] = __float2half_rn(v);
+      }
+    }
+  }
   __syncthreads();
   if (CL > 1) tc_cluster_sync();         // no CTA leaves while its peer may still multicast into it
   if ((A.dbg & 16) && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
@@ -435,13 +477,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
 
 using namespace amqb;
 
+// workspace: [pre-swizzled X | split-K partial tiles (at most one per SM: 148 x 64 KB) | tile tickets]
+static size_t tc_swizzled_bytes(int M, int K) { return (((size_t)((M + 127) / 128) * 128 * (size_t)K * 2 + 256) + 255) & ~size_t(255); }
+constexpr int kTcMaxCtas = 148;
+constexpr size_t kTcSplitBytes = (size_t)kTcMaxCtas * kTileM * kTileN * 4 + 1024;
+
 extern "C" {
 
 size_t amqb_gemm_workspace_bytes(int M, int K, int bits) {
   (void)bits;
   if (M <= 0 || K <= 0) return 0;
   // pre-swizzled activations for the tcgen05 kernel, or (fallback path) the decode kernel's M > 1 workspace
-  const size_t swz = (size_t)((M + 127) / 128) * 128 * (size_t)K * 2 + 256;
+  const size_t swz = tc_swizzled_bytes(M, K) + kTcSplitBytes;
   const size_t dec = amqb_workspace_bytes(1, K, 16);
   return swz > dec ? swz : dec;
 }
@@ -471,6 +518,25 @@ int amqb_gemm_tc(int bits, const void* w_native, const void* x, void* y, const v
   }
   const int m_tiles = (M + kTileM - 1) / kTileM;
   const long long chunks = (long long)m_tiles * 128 * (K / 8);
+  const int n_tiles = N / kTileN;
+  // K split when the output tiles leave most of the chip idle (a 63-row prompt is 32 tiles at N = 4096; k / v projections
+  // of a GQA model 8 per m tile): as many splits as fit one CTA per SM, at least 4 k blocks each
+  // Measured (profiles/r02_prefill_splitk.txt, 3-bit, M = 63): a call has ~20 us of fixed cost (pre-swizzle pass, TMEM /
+  // barrier set-up, ring fill, epilogue) around a k loop of 0.27 us per block, and the split adds ~8 us (counter reset,
+  // partial tiles, the last CTA's reduction): it pays for long rows only - 4096 x 11008: 44.4 -> 31.0 us, but
+  // 4096 x 4096: 20.8 -> 24.6 us.  Hence K >= 8192.
+  int splits = 1;
+  if (!getenv("AMQB_TC_NO_SPLITK") && K / kBlockK >= 64) {
+    splits = kTcMaxCtas / (n_tiles * m_tiles);
+    const int NGA = K / kBlockK;
+    if (splits > NGA / 4) splits = NGA / 4;
+    if (splits > 8) splits = 8;
+    if (splits < 1) splits = 1;
+  }
+  int* tickets = (int*)((uint8_t*)workspace + tc_swizzled_bytes(M, K) + (size_t)kTcMaxCtas * kTileM * kTileN * 4);
+  // the tile counters start at zero (a caller's workspace is uninitialised memory); issued before the pre-swizzle pass so
+  // that pass and the GEMM stay a programmatic-dependent-launch pair
+  if (splits > 1) cudaMemsetAsync(tickets, 0, 1024, st);
   swizzle_x_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>((const __half*)x, (uint8_t*)workspace, M, K, m_tiles);
   TcArgs A{};
   A.w = (const uint8_t*)w_native; A.xs = (const uint8_t*)workspace; A.y = (__half*)y; A.bias = (const __half*)bias;
@@ -486,12 +552,14 @@ int amqb_gemm_tc(int bits, const void* w_native, const void* x, void* y, const v
     cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax);
     cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax);
   }
-  const int n_tiles = N / kTileN;
+  A.splits = splits;
+  A.part = (float*)((uint8_t*)workspace + tc_swizzled_bytes(M, K));
+  A.tickets = tickets;
   // cluster pair + X multicast halves the activations' L2 traffic but measured ~5% slower (the X ring is bound by the
   // bulk-copy round trip, not by L2 bandwidth): opt-in, kept as the base for a cta_group::2 version
-  const bool pair = (n_tiles % 2 == 0) && getenv("AMQB_TC_CLUSTER") != nullptr;
+  const bool pair = (n_tiles % 2 == 0) && splits == 1 && getenv("AMQB_TC_CLUSTER") != nullptr;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(n_tiles, m_tiles);
+  cfg.gridDim = dim3(n_tiles, m_tiles, splits);
   cfg.blockDim = dim3(kTcThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
