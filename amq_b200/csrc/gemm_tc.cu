@@ -134,7 +134,7 @@ constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kTileM >> 3) << 17) | ((uint
 
 // ---- activations: pre-swizzled copy of X so that a plain bulk copy lands in the UMMA layout -------
 // Xs[m_tile][k_atom][128 rows][128 B], 16-byte chunk c of row r stored at chunk (c ^ (r & 7)); rows >= M are zero.
-__global__ void swizzle_x_kernel(const __half* __restrict__ X, uint8_t* __restrict__ Xs, int M, int K, int m_tiles) {
+__global__ void swizzle_x_kernel(const __half* X, uint8_t* Xs, int M, int K, int m_tiles) {
   pdl_launch_dependents();               // the GEMM's prologue, W ring and dequant may start; its X producer waits
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // one 16-byte chunk
   const int chunks_per_row = K / 8;
@@ -143,6 +143,7 @@ __global__ void swizzle_x_kernel(const __half* __restrict__ X, uint8_t* __restri
   const int m = (int)(idx / chunks_per_row), ck = (int)(idx - (long long)m * chunks_per_row);
   const int atom = ck >> 3, c = ck & 7, r = m & 127, mt = m >> 7;
   uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  pdl_wait();                            // X is the previous kernel's output (this pass is itself launched programmatically)
   if (m < M) v = *reinterpret_cast<const uint4*>(X + (size_t)m * K + 8 * ck);
   uint8_t* dst = Xs + ((size_t)mt * (K / 64) + atom) * kAtomBytes + (size_t)r * 128 + ((c ^ (r & 7)) << 4);
   *reinterpret_cast<uint4*>(dst) = v;
@@ -537,7 +538,22 @@ int amqb_gemm_tc(int bits, const void* w_native, const void* x, void* y, const v
   // the tile counters start at zero (a caller's workspace is uninitialised memory); issued before the pre-swizzle pass so
   // that pass and the GEMM stay a programmatic-dependent-launch pair
   if (splits > 1) cudaMemsetAsync(tickets, 0, 1024, st);
-  swizzle_x_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>((const __half*)x, (uint8_t*)workspace, M, K, m_tiles);
+  {
+    cudaLaunchConfig_t sc{};
+    sc.gridDim = dim3((unsigned)((chunks + 255) / 256));
+    sc.blockDim = dim3(256);
+    sc.stream = st;
+    cudaLaunchAttribute sa[1];
+    sa[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    sa[0].val.programmaticStreamSerializationAllowed = 1;
+    sc.attrs = sa;
+    sc.numAttrs = 1;
+    cudaError_t se = cudaLaunchKernelEx(&sc, swizzle_x_kernel, (const __half*)x, (uint8_t*)workspace, M, K, m_tiles);
+    if (se != cudaSuccess) {
+      set_error("gemm_tc pre-swizzle launch: %s", cudaGetErrorString(se));
+      return AMQB_ERR_LAUNCH;
+    }
+  }
   TcArgs A{};
   A.w = (const uint8_t*)w_native; A.xs = (const uint8_t*)workspace; A.y = (__half*)y; A.bias = (const __half*)bias;
   A.bits = bits; A.M = M; A.N = N; A.K = K;

@@ -16,12 +16,37 @@
 
 namespace amqb {
 
+// Every kernel of the prompt pass is launched with programmatic stream serialization and starts with
+// griddepcontrol.launch_dependents + griddepcontrol.wait: the next kernel's launch latency (~2 us between dependent
+// kernels, 16 kernels per layer) overlaps this one's execution, and nothing is read or written before the wait.
+// Inputs written by the previous kernel are NOT __restrict__ (no load may be moved above the wait).
+template <typename... KArgs, typename... Args>
+static int pf_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, const char* what, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args...);
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return AMQB_ERR_LAUNCH;
+  }
+  return AMQB_OK;
+}
+
 // ------------------------------------------------------------------ RMSNorm over rows
 // grid = rows, 256 threads; one pass over the row for the statistic (L1 / L2 serve the second)
 __global__ void __launch_bounds__(256)
-rmsnorm_rows_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma, float eps,
-                    __half* __restrict__ out, int H) {
+rmsnorm_rows_kernel(const __half* x, const __half* __restrict__ gamma, float eps,
+                    __half* out, int H) {
   __shared__ float part[8];
+  pdl_launch_dependents();
+  pdl_wait();
   const __half2* xr = reinterpret_cast<const __half2*>(x + (size_t)blockIdx.x * H);
   const __half2* gr = reinterpret_cast<const __half2*>(gamma);
   __half2* orow = reinterpret_cast<__half2*>(out + (size_t)blockIdx.x * H);
@@ -47,7 +72,9 @@ rmsnorm_rows_kernel(const __half* __restrict__ x, const __half* __restrict__ gam
 
 // ------------------------------------------------------------------ silu(gate) * up, h += y
 __global__ void __launch_bounds__(256)
-silu_mul_kernel(const __half2* __restrict__ gate, const __half2* __restrict__ up, __half2* __restrict__ out, size_t n2) {
+silu_mul_kernel(const __half2* gate, const __half2* up, __half2* out, size_t n2) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
     float2 g = __half22float2(gate[i]);
     g.x = __fdividef(g.x, 1.f + __expf(-g.x));
@@ -57,7 +84,9 @@ silu_mul_kernel(const __half2* __restrict__ gate, const __half2* __restrict__ up
 }
 
 __global__ void __launch_bounds__(256)
-add_rows_kernel(__half2* __restrict__ h, const __half2* __restrict__ y, size_t n2) {
+add_rows_kernel(__half2* h, const __half2* y, size_t n2) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
     const float2 a = __half22float2(h[i]), b = __half22float2(y[i]);
     h[i] = __float22half2_rn(make_float2(a.x + b.x, a.y + b.y));
@@ -67,9 +96,11 @@ add_rows_kernel(__half2* __restrict__ h, const __half2* __restrict__ y, size_t n
 // ------------------------------------------------------------------ RoPE + KV append for T prompt positions
 // grid (T, B), 256 threads.  q is rotated in place; rotated k and plain v go to the cache rows pos0 + t.
 __global__ void __launch_bounds__(256)
-rope_append_kernel(__half* __restrict__ q, const __half* __restrict__ k, const __half* __restrict__ v,
-                   __half* __restrict__ kc, __half* __restrict__ vc, const float2* __restrict__ rope_tab,
+rope_append_kernel(__half* q, const __half* k, const __half* v,
+                   __half* kc, __half* vc, const float2* __restrict__ rope_tab,
                    int pos0, int T, int Hq, int Hkv, int D, int max_seq) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = blockIdx.x, b = blockIdx.y;
   const size_t row = (size_t)b * T + t;
   const int pos = pos0 + t;
@@ -113,12 +144,14 @@ constexpr int kPfWarps = 8;
 constexpr int kPfTile = 32;
 template <int D>
 __global__ void __launch_bounds__(kPfWarps * 32)
-attn_prefill_kernel(const __half* __restrict__ q, const __half* __restrict__ kc, const __half* __restrict__ vc,
-                    __half* __restrict__ out, int pos0, int T, int Hq, int Hkv, int max_seq) {
+attn_prefill_kernel(const __half* q, const __half* kc, const __half* vc,
+                    __half* out, int pos0, int T, int Hq, int Hkv, int max_seq) {
   constexpr int EPL = D / 32;
   constexpr int UNR = 8;
   __shared__ __align__(16) __half sk[kPfTile][D];
   __shared__ __align__(16) __half sv[kPfTile][D];
+  pdl_launch_dependents();
+  pdl_wait();
   const int t0 = blockIdx.x * kPfWarps, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int hk = h / (Hq / Hkv);
@@ -202,24 +235,22 @@ extern "C" {
 
 int amqb_rmsnorm_rows(const void* x_f16, const void* gamma_f16, float eps, void* out_f16, int M, int H, void* stream) {
   if (!x_f16 || !gamma_f16 || !out_f16 || M < 1 || H < 2 || H % 2) return fail(AMQB_ERR_BAD_ARG, "rmsnorm_rows: bad argument");
-  rmsnorm_rows_kernel<<<M, 256, 0, (cudaStream_t)stream>>>((const __half*)x_f16, (const __half*)gamma_f16, eps,
-                                                            (__half*)out_f16, H);
-  return check_launch("rmsnorm_rows");
+  return pf_launch(rmsnorm_rows_kernel, dim3(M), dim3(256), (cudaStream_t)stream, "rmsnorm_rows", (const __half*)x_f16,
+                   (const __half*)gamma_f16, eps, (__half*)out_f16, H);
 }
 
 int amqb_silu_mul_rows(const void* gate_f16, const void* up_f16, void* out_f16, int M, int I, void* stream) {
   if (!gate_f16 || !up_f16 || !out_f16 || M < 1 || I < 2 || I % 2) return fail(AMQB_ERR_BAD_ARG, "silu_mul_rows: bad argument");
   const size_t n2 = (size_t)M * I / 2;
-  silu_mul_kernel<<<ew_grid(n2), 256, 0, (cudaStream_t)stream>>>((const __half2*)gate_f16, (const __half2*)up_f16,
-                                                                  (__half2*)out_f16, n2);
-  return check_launch("silu_mul_rows");
+  return pf_launch(silu_mul_kernel, dim3(ew_grid(n2)), dim3(256), (cudaStream_t)stream, "silu_mul_rows",
+                   (const __half2*)gate_f16, (const __half2*)up_f16, (__half2*)out_f16, n2);
 }
 
 int amqb_add_rows(void* h_f16, const void* y_f16, int M, int H, void* stream) {
   if (!h_f16 || !y_f16 || M < 1 || H < 2 || H % 2) return fail(AMQB_ERR_BAD_ARG, "add_rows: bad argument");
   const size_t n2 = (size_t)M * H / 2;
-  add_rows_kernel<<<ew_grid(n2), 256, 0, (cudaStream_t)stream>>>((__half2*)h_f16, (const __half2*)y_f16, n2);
-  return check_launch("add_rows");
+  return pf_launch(add_rows_kernel, dim3(ew_grid(n2)), dim3(256), (cudaStream_t)stream, "add_rows", (__half2*)h_f16,
+                   (const __half2*)y_f16, n2);
 }
 
 int amqb_attn_prefill(void* q_f16, const void* k_f16, const void* v_f16, void* k_cache, void* v_cache, void* out_f16,
@@ -230,19 +261,16 @@ int amqb_attn_prefill(void* q_f16, const void* k_f16, const void* v_f16, void* k
     return fail(AMQB_ERR_BAD_ARG, "attn_prefill: bad argument (pos0 + T <= max_seq, Hq % Hkv == 0, rope table required)");
   if (D != 64 && D != 128) return fail(AMQB_ERR_UNSUPPORTED_SHAPE, "attn_prefill: head_dim must be 64 or 128");
   cudaStream_t st = (cudaStream_t)stream;
-  rope_append_kernel<<<dim3(T, B), 256, 0, st>>>((__half*)q_f16, (const __half*)k_f16, (const __half*)v_f16,
-                                                 (__half*)k_cache, (__half*)v_cache, (const float2*)rope_cos_sin, pos0, T,
-                                                 Hq, Hkv, D, max_seq);
-  int rc = check_launch("attn_prefill (rope + append)");
+  int rc = pf_launch(rope_append_kernel, dim3(T, B), dim3(256), st, "attn_prefill (rope + append)", (__half*)q_f16,
+                     (const __half*)k_f16, (const __half*)v_f16, (__half*)k_cache, (__half*)v_cache,
+                     (const float2*)rope_cos_sin, pos0, T, Hq, Hkv, D, max_seq);
   if (rc) return rc;
   const dim3 grid((T + kPfWarps - 1) / kPfWarps, Hq, B);
   if (D == 128)
-    attn_prefill_kernel<128><<<grid, kPfWarps * 32, 0, st>>>((const __half*)q_f16, (const __half*)k_cache,
-                                                             (const __half*)v_cache, (__half*)out_f16, pos0, T, Hq, Hkv, max_seq);
-  else
-    attn_prefill_kernel<64><<<grid, kPfWarps * 32, 0, st>>>((const __half*)q_f16, (const __half*)k_cache,
-                                                            (const __half*)v_cache, (__half*)out_f16, pos0, T, Hq, Hkv, max_seq);
-  return check_launch("attn_prefill");
+    return pf_launch(attn_prefill_kernel<128>, grid, dim3(kPfWarps * 32), st, "attn_prefill", (const __half*)q_f16,
+                     (const __half*)k_cache, (const __half*)v_cache, (__half*)out_f16, pos0, T, Hq, Hkv, max_seq);
+  return pf_launch(attn_prefill_kernel<64>, grid, dim3(kPfWarps * 32), st, "attn_prefill", (const __half*)q_f16,
+                   (const __half*)k_cache, (const __half*)v_cache, (__half*)out_f16, pos0, T, Hq, Hkv, max_seq);
 }
 
 }  // extern "C"

@@ -35,6 +35,28 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
+# stdout carries EXACTLY one JSON line (the driver parses it): file descriptor 1 is pointed at stderr for the whole run, so
+# that nothing a library prints there (NCCL's version banner goes to stdout even with NCCL_DEBUG_FILE set) can precede it,
+# and the line itself is written to the saved descriptor.
+_REAL_STDOUT = None
+
+
+def _guard_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -139,7 +161,7 @@ def run_reference(args, shape, arch):
         "cpu_baseline": {"value": tok_s, "unit": "tok/s", "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": tok_s, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -211,7 +233,7 @@ def run_ours(args, shape, arch):
         # leave NCCL's own logging on (to a file: stdout carries exactly one JSON line) so that the communicator size
         # and transport it reports can be quoted next to the tensor-parallel numbers
         nccl_log = f"/tmp/amqb_nccl_{os.getpid()}_%h_%p.log"
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ["NCCL_DEBUG"] = "INFO"                 # the image presets NCCL_DEBUG=VERSION: override, the output goes to the file
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,GRAPH,ENV")
         os.environ.setdefault("NCCL_DEBUG_FILE", nccl_log)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -336,12 +358,13 @@ def run_ours(args, shape, arch):
             "cpu_baseline": {"value": cpu_tok_s, "unit": "tok/s", "cores": os.cpu_count(), "kind": "port", "sample": cpu_desc},
             "tp70b": tp_rec,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    _guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=128)
