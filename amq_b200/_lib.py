@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("AMQB_LIB") or os.path.join(_HERE, "lib", "libamqb.so"
 _lib: Optional[ctypes.CDLL] = None
 
 LAYOUT_HQQ, LAYOUT_GPTQ, LAYOUT_FT, LAYOUT_NATIVE = 0, 1, 2, 3
-PRO_NONE, PRO_RMSNORM, PRO_SILU_MUL = 0, 1, 2
+PRO_NONE, PRO_RMSNORM, PRO_SILU_MUL, PRO_MUL = 0, 1, 2, 3
 
 
 class ArCtx(ctypes.Structure):
@@ -31,7 +31,7 @@ class GemvProblem(ctypes.Structure):
         ("y", ctypes.c_void_p), ("ldy", ctypes.c_int),
         ("bias", ctypes.c_void_p), ("residual", ctypes.c_void_p),
         ("prologue", ctypes.c_int), ("gamma", ctypes.c_void_p), ("eps", ctypes.c_float),
-        ("allreduce", ctypes.POINTER(ArCtx)), ("ar_call", ctypes.c_int), ("after_gemv", ctypes.c_int),
+        ("allreduce", ctypes.POINTER(ArCtx)), ("ar_call", ctypes.c_int), ("act", ctypes.c_int), ("after_gemv", ctypes.c_int),
     ]
 
 

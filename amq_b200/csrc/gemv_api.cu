@@ -40,6 +40,9 @@ static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, 
     P.eps = q.eps; P.bits = q.bits; P.N = q.N; P.K = q.K; P.ldx = q.ldx; P.ldy = q.ldy; P.prologue = q.prologue;
     P.n_rb = q.N / 32; P.n_g = q.K / kGroup;
     P.ar = 0;
+    P.act = q.act;
+    if (q.act != 0 && q.act != 1) return fail(AMQB_ERR_BAD_ARG, "gemv: act must be 0 or 1 (silu)");
+    if (q.act && q.allreduce && q.allreduce->world > 1) return fail(AMQB_ERR_BAD_ARG, "gemv: act cannot follow a fused all-reduce");
     if (q.allreduce && q.allreduce->world > 1) {
       const amqb_ar_ctx& C = *q.allreduce;
       if (C.world > kArFuseMaxWorld || C.rank < 0 || C.rank >= C.world || !C.pos_dev || !C.gen_dev || (long long)M * q.N > C.max_elems)
@@ -92,7 +95,8 @@ static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, 
       X.x = P.x; X.gamma = P.gamma; X.eps = P.eps; X.ldx = P.ldx; X.K = P.K; X.M = M; X.MB = MB; X.mask = P.build_mask;
       X.xsg = (float2*)base;
       for (int b = 2; b <= 4; ++b) X.xg[b - 2] = base + xs_b + xg_variant_offset(P.n_g, b, M);
-      int rc = pro == AMQB_PRO_NONE ? launch_xg0(X, pdl, st) : (pro == AMQB_PRO_RMSNORM ? launch_xg1(X, pdl, st) : launch_xg2(X, pdl, st));
+      int rc = pro == AMQB_PRO_NONE ? launch_xg0(X, pdl, st) : (pro == AMQB_PRO_RMSNORM ? launch_xg1(X, pdl, st) :
+               (pro == AMQB_PRO_SILU_MUL ? launch_xg2(X, pdl, st) : launch_xg3(X, pdl, st)));
       if (rc) return rc;
       P.xsg = X.xsg;
       P.xg = X.xg[P.bits - 2];
@@ -189,6 +193,7 @@ static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, 
   if (M == 1 && kCoresident && grid < B) grid = (B / S) * S;          // place holders: every SM holds a CTA of this launch
   if (pro == AMQB_PRO_NONE) return launch_pro0(L, grid, smem, pdl, st);
   if (pro == AMQB_PRO_RMSNORM) return launch_pro1(L, grid, smem, pdl, st);
+  if (pro == AMQB_PRO_MUL) return launch_pro3(L, grid, smem, pdl, st);
   return launch_pro2(L, grid, smem, pdl, st);
 }
 
@@ -255,7 +260,7 @@ int amqb_gemv_grouped(const amqb_gemv_problem* pr, int count, void* workspace, s
       return fail(AMQB_ERR_UNSUPPORTED_SHAPE, "gemv: needs N % 32 == 0 and K % 128 == 0");
     if ((q.ldx % 4) || ((uintptr_t)q.x & 7) || ((uintptr_t)q.w_native & 15))
       return fail(AMQB_ERR_BAD_ARG, "gemv: x must be 8-byte aligned with ldx % 4 == 0, w 16-byte aligned");
-    if (q.prologue < AMQB_PRO_NONE || q.prologue > AMQB_PRO_SILU_MUL) return fail(AMQB_ERR_BAD_ARG, "gemv: bad prologue");
+    if (q.prologue < AMQB_PRO_NONE || q.prologue > AMQB_PRO_MUL) return fail(AMQB_ERR_BAD_ARG, "gemv: bad prologue");
     if (q.prologue == AMQB_PRO_RMSNORM && !q.gamma) return fail(AMQB_ERR_BAD_ARG, "gemv: rmsnorm prologue needs gamma");
     if (q.prologue == AMQB_PRO_RMSNORM && ((uintptr_t)q.x & 15)) return fail(AMQB_ERR_BAD_ARG, "gemv: rmsnorm prologue needs 16-byte aligned x");
   }

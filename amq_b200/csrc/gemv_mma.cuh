@@ -101,6 +101,7 @@ struct DevProblem {
                          // consecutive problems over different CTAs
   int build_mask;        // bit b set: build the x' variant of bit width b when this problem starts (0: reuse)
   int ar;                // 1: row-parallel problem of a tensor-parallel model: the epilogue all-reduces across L.ar ranks
+  int act;               // 1: y <- silu(y) on the fp16-rounded output (amqb_gemv_problem.act)
 };
 
 // Tensor-parallel all-reduce fused into the epilogue (amqb_ar_ctx, include/amqb.h).  "LL" exchange: every partial sum
@@ -248,6 +249,9 @@ __device__ __forceinline__ void finish_item(uint2 a, uint2 b, float rs, float (&
     const float2 lo = __half22float2(__hmul2(__float22half2_rn(g0), bh[0]));
     const float2 hi = __half22float2(__hmul2(__float22half2_rn(g1), bh[1]));
     xf[0] = lo.x; xf[1] = hi.x; xf[2] = lo.y; xf[3] = hi.y;
+  } else if (pro == AMQB_PRO_MUL) {
+    const float2 lo = __half22float2(__hmul2(ah[0], bh[0])), hi = __half22float2(__hmul2(ah[1], bh[1]));
+    xf[0] = lo.x; xf[1] = hi.x; xf[2] = lo.y; xf[3] = hi.y;
   } else if (pro == AMQB_PRO_RMSNORM) {
     const float2 x0 = __half22float2(ah[0]), x1 = __half22float2(ah[1]);
     const float2 w0 = __half22float2(bh[0]), w1 = __half22float2(bh[1]);
@@ -326,7 +330,7 @@ __device__ __forceinline__ void emit_item(const float (&xf)[4], const XLane (&xl
 #ifndef AMQB_KPRE_SILU
 #define AMQB_KPRE_SILU AMQB_KPRE
 #endif
-template <int PRO> struct PreItems { static constexpr int value = PRO == AMQB_PRO_SILU_MUL ? AMQB_KPRE_SILU : AMQB_KPRE; };
+template <int PRO> struct PreItems { static constexpr int value = (PRO == AMQB_PRO_SILU_MUL || PRO == AMQB_PRO_MUL) ? AMQB_KPRE_SILU : AMQB_KPRE; };
 template <int PRO>
 __device__ __forceinline__ void build_xprime(const DevProblem& P, int g_lo, int len, uint8_t* xp, float2* xsd, int cw,
                                              int lane, int mask, int variants, int var_stride, const XLane (&xl)[3],
@@ -364,7 +368,7 @@ __device__ __forceinline__ void build_xprime(const DevProblem& P, int g_lo, int 
         const __half* xr = P.x + (g_lo + cw + (base + i) * kCW) * kGroup + koff;
         a[i].x = __ldcg(reinterpret_cast<const uint32_t*>(xr));
         a[i].y = __ldcg(reinterpret_cast<const uint32_t*>(xr + 8));
-        if (PRO == AMQB_PRO_SILU_MUL) {
+        if (PRO == AMQB_PRO_SILU_MUL || PRO == AMQB_PRO_MUL) {
           b[i].x = __ldcg(reinterpret_cast<const uint32_t*>(xr + P.K));
           b[i].y = __ldcg(reinterpret_cast<const uint32_t*>(xr + P.K + 8));
         }
@@ -445,7 +449,7 @@ __global__ void __launch_bounds__(kXgWarps * 32) xprime_global_kernel(const XgAr
     uint2 a, b = make_uint2(0u, 0u);
     a.x = *reinterpret_cast<const uint32_t*>(xr);
     a.y = *reinterpret_cast<const uint32_t*>(xr + 8);
-    if (PRO == AMQB_PRO_SILU_MUL) {
+    if (PRO == AMQB_PRO_SILU_MUL || PRO == AMQB_PRO_MUL) {
       b.x = *reinterpret_cast<const uint32_t*>(xr + A.K);
       b.y = *reinterpret_cast<const uint32_t*>(xr + A.K + 8);
     } else if (PRO == AMQB_PRO_RMSNORM) {
@@ -724,11 +728,18 @@ __device__ __forceinline__ int first_rb(int cid, int rot, int ncl) {
   return r < 0 ? r + ncl : r;
 }
 
+// output activation on the rounded fp16 value (HF: act_fn(gate_proj(x)) on an fp16 tensor = fp32 math, fp16 result; the same
+// arithmetic the SILU_MUL prologue applies on the consuming side)
+__device__ __forceinline__ __half act_out(const DevProblem& P, __half h) {
+  if (!P.act) return h;
+  const float g = __half2float(h);
+  return __float2half_rn(__fdividef(g, 1.f + __expf(-g)));
+}
 __device__ __forceinline__ void store_out(const DevProblem& P, int n, int col, float v, float rs = 1.f) {
   v *= rs;
   if (P.bias) v += __half2float(P.bias[n]);
   if (P.residual) v += __half2float(__ushort_as_half(__ldcg(reinterpret_cast<const unsigned short*>(P.residual) + (size_t)col * P.ldy + n)));
-  P.y[(size_t)col * P.ldy + n] = __float2half_rn(v);
+  P.y[(size_t)col * P.ldy + n] = act_out(P, __float2half_rn(v));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -910,7 +921,7 @@ __global__ void __launch_bounds__(kThreads, kCoresident ? 2 : 1) gemv_mma_kernel
               }
               if (last_chunk) {
                 if (S == 1) {
-                  if (pre) P.y[rb * 32 + row] = __float2half_rn(fmaf(v, rs_ep, addend));
+                  if (pre) P.y[rb * 32 + row] = act_out(P, __float2half_rn(fmaf(v, rs_ep, addend)));
                   else if (col < M) {
                     if (fuse) ar_push(L.ar, epoch, col * P.N + rb * 32 + row, v * rs_ep);
                     else store_out(P, rb * 32 + row, col, v, rs_ep);
@@ -1202,5 +1213,7 @@ int launch_xg1(const XgArgs& A, int pdl, cudaStream_t st);
 int launch_xg2(const XgArgs& A, int pdl, cudaStream_t st);
 int launch_pro1(const GemvLaunch& L, int grid, size_t smem, int pdl, cudaStream_t st);
 int launch_pro2(const GemvLaunch& L, int grid, size_t smem, int pdl, cudaStream_t st);
+int launch_pro3(const GemvLaunch& L, int grid, size_t smem, int pdl, cudaStream_t st);
+int launch_xg3(const XgArgs& A, int pdl, cudaStream_t st);
 
 }  // namespace amqb

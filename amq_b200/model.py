@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import ops
-from ._lib import PRO_NONE, PRO_RMSNORM, PRO_SILU_MUL, check, cur_stream, lib, ptr
+from ._lib import PRO_MUL, PRO_NONE, PRO_RMSNORM, PRO_SILU_MUL, check, cur_stream, lib, ptr
 from .arch import LINEARS, ModelShape
 
 GROUP = 128
@@ -116,6 +116,7 @@ class QuantDecoder:
         # Two captured steps: the short-context one launches one CTA per head (the extra CTAs of the split grid, although
         # they leave at once below the threshold, were measured to cost ~0.75 us per layer); step() picks by a host-side
         # mirror of the position.  Either graph is correct at any position — the mirror only selects the faster one.
+        self.silu_in_consumer = os.environ.get("AMQB_SILU_IN_CONSUMER") == "1"      # A/B: round-1 placement of the activation
         self._cur_splits = 1
         self._pos_h = 0
         self.graph_long: Optional[torch.cuda.CUDAGraph] = None
@@ -230,7 +231,9 @@ class QuantDecoder:
                        L["norm2"])]
             db, dw, dn, dk = L["mlp.down_proj"]
             down = [fuse(prob(db, dw, self.gu, (self.part if tp else self.h).data_ptr(), dn, dk, gu_ld, self.H, None,
-                              None if tp else self.h, PRO_SILU_MUL), 2 * li + 1)]
+                              None if tp else self.h, PRO_SILU_MUL if self.silu_in_consumer else PRO_MUL), 2 * li + 1)]
+            # SiLU once per element, in gate_proj's epilogue (act), not once per element in each of down_proj's ~128 CTAs
+            gu[0].act = 0 if self.silu_in_consumer else 1
             # scheduling hint (include/amqb.h, after_gemv): which launches directly follow another batch-1 GEMV launch on the
             # stream.  q|k|v follows the previous layer's down_proj, gate|up follows o_proj, down_proj follows gate|up;
             # o_proj follows the attention kernel, and a separate all-reduce kernel breaks the chain as well.

@@ -47,7 +47,10 @@ typedef enum {
 typedef enum {
   AMQB_PRO_NONE = 0,      /* x used as is */
   AMQB_PRO_RMSNORM = 1,   /* x <- x * rsqrt(mean(x^2)+eps) * gamma   (fp32 math, fp16 result) */
-  AMQB_PRO_SILU_MUL = 2   /* x <- silu(x[:, :K]) * x[:, K:2K]  (x is the [M, 2K] gate|up buffer) */
+  AMQB_PRO_SILU_MUL = 2,  /* x <- silu(x[:, :K]) * x[:, K:2K]  (x is the [M, 2K] gate|up buffer) */
+  AMQB_PRO_MUL = 3        /* x <- x[:, :K] * x[:, K:2K]: the gate half already holds silu(gate) (amqb_gemv_problem.act of the
+                           * launch that wrote it): the activation is then computed once per element by its producer
+                           * instead of once per element in every CTA of the consuming launch */
 } amqb_prologue;
 
 const char* amqb_last_error_string(void);
@@ -122,6 +125,8 @@ typedef struct {
   float eps;
   const amqb_ar_ctx* allreduce; /* host pointer or NULL: fuse the tensor-parallel all-reduce into the epilogue */
   int ar_call;              /* index of this all-reduce inside the step (0 .. 255; consecutive calls alternate parity) */
+  int act;                  /* 0: none; 1: y <- silu(y), applied to the fp16-rounded output (fp32 math, fp16 result: HF's
+                             * act_fn on an fp16 tensor) */
   int after_gemv;           /* scheduling hint, batch 1 (first problem of a launch counts): nonzero = the kernel launched on
                              * this stream right before this one is an amqb batch-1 GEMV launch.  Such a launch is sized to
                              * sit NEXT TO its predecessor on every SM and stream its weights while the predecessor still
