@@ -180,7 +180,7 @@ static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, 
   L.n_stages = ns;
   {
     const char* e = getenv("AMQB_WINDOW_KB");              // 0: no window (the whole ring is requested at once)
-    const int wkb = e ? atoi(e) : 64;
+    const int wkb = e ? atoi(e) : 96;
     int w = wkb > 0 ? (wkb * 1024 + L.stage_bytes / 2) / L.stage_bytes : ns;
     if (w < 1) w = 1;
     if (w > ns) w = ns;
