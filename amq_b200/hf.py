@@ -226,6 +226,7 @@ class GraphedHFDecoder:
         self.pos = torch.zeros(1, dtype=torch.long, device=self.device)
         self.graph = None
         self.logits = None
+        self._pos_h = None             # host mirror of the position; None until a prompt has been consumed
 
     def _forward_step(self):
         out = self.model(self.ids, past_key_values=self.cache, cache_position=self.pos, use_cache=True)
@@ -281,6 +282,8 @@ class GraphedHFDecoder:
     @torch.inference_mode()
     def step(self) -> torch.Tensor:
         """One token: replays the captured forward; returns the device buffer holding the NEW token ids [B, 1]."""
+        if self._pos_h is None:
+            raise RuntimeError("GraphedHFDecoder.step: call prefill(input_ids) first")
         if self._pos_h + 1 > self.max_cache_len:
             raise RuntimeError("GraphedHFDecoder: static cache is full")
         if self.graph is None:

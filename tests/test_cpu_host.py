@@ -202,3 +202,21 @@ def test_speed_benchmark_cli_mirrors_reference_flags():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="CUDA"):
             cli.main(["--tps"])
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """The driver parses bench.py's stdout: exactly one JSON line, whatever libraries print (bench.py points file
+    descriptor 1 at stderr for the run and writes the line to the saved descriptor).  The reference arm is the CPU arm, so
+    it runs here."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "tok/s" and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["value"] > 0

@@ -158,6 +158,48 @@ def test_gemv_model_shapes(ops, N, K, bits):
     assert torch.equal(y1, y2)
 
 
+@pytest.mark.parametrize("M", [1, 2, 4])
+def test_output_activation_and_mul_prologue(ops, M):
+    """gate|up -> down as QuantDecoder launches it: `act = 1` on the gate problem stores silu(gate) and the down launch reads
+    x = a * b (AMQB_PRO_MUL) - bit for bit what the one-sided AMQB_PRO_SILU_MUL prologue computes from raw gate / up, and
+    within tolerance of the fp32 statement silu(g) * u."""
+    from amq_b200 import _lib
+    dev = "cuda"
+    H, I, bits = 512, 1024, 3
+    cg, sg, zg = [t if isinstance(t, torch.Tensor) else torch.from_numpy(t) for t in _synthetic(I, H, bits, seed=11)]
+    cu, su, zu = [t if isinstance(t, torch.Tensor) else torch.from_numpy(t) for t in _synthetic(I, H, bits, seed=12)]
+    cd, sd, zd = [t if isinstance(t, torch.Tensor) else torch.from_numpy(t) for t in _synthetic(H, I, bits, seed=13)]
+    wg = ops.pack_native(bits, cg.to(dev), sg.to(dev), zg.to(dev))
+    wu = ops.pack_native(bits, cu.to(dev), su.to(dev), zu.to(dev))
+    wd = ops.pack_native(bits, cd.to(dev), sd.to(dev), zd.to(dev))
+    torch.manual_seed(M)
+    x = torch.randn(M, H, device=dev).half()
+    ws = ops.workspace(x.device, 2 * I, max(H, I), M)
+    outs = []
+    for act_in_producer in (False, True):
+        gu = torch.zeros(M, 2 * I, device=dev, dtype=torch.float16)
+        y = torch.zeros(M, H, device=dev, dtype=torch.float16)
+        pg = ops.make_problem(bits, wg, x, gu, I, H, ldy=2 * I)
+        pu = ops.make_problem(bits, wu, x, gu, I, H, ldy=2 * I)
+        pu.y = gu.data_ptr() + 2 * I
+        pg.act = int(act_in_producer)
+        ops.gemv_grouped([pg, pu], ws)
+        pd = ops.make_problem(bits, wd, gu, y, H, I, ldx=2 * I,
+                              prologue=_lib.PRO_MUL if act_in_producer else _lib.PRO_SILU_MUL)
+        ops.gemv_grouped([pd], ws)
+        torch.cuda.synchronize()
+        outs.append((gu.clone(), y.clone()))
+    (gu0, y0), (gu1, y1) = outs
+    assert torch.equal(gu0[:, I:], gu1[:, I:])                                    # up half untouched by the activation
+    g = gu0[:, :I].float()
+    assert torch.equal(gu1[:, :I], (g / (1 + torch.exp(-g))).half()) or \
+        O.max_rel(gu1[:, :I].cpu(), (g / (1 + torch.exp(-g))).cpu()) <= 1e-3      # __expf / __fdividef vs torch
+    assert torch.equal(y0, y1)                                                    # same arithmetic on either side
+    Wd = (cd.float().reshape(H, I // G, G) * sd.float()[..., None] - (zd * sd).float()[..., None]).reshape(H, I).to(dev)
+    h = (torch.nn.functional.silu(gu0[:, :I].float()).half() * gu0[:, I:]).float()
+    assert O.max_rel(y1.cpu(), (h @ Wd.t()).cpu()) <= TOL
+
+
 @pytest.mark.parametrize("bits", [2, 3, 4])
 def test_gemv_group_count_sweep(ops, bits, monkeypatch):
     """Every k-group count around the pipeline-stage boundaries (a stage is 16 records; the batch-1 / batch-2 consumers
@@ -235,6 +277,31 @@ def test_prefill_gemm(ops, N, K, M, bits):
     # the same rows through the decode kernel (M <= 16): both paths see the same weights
     y16 = ops.gemv(bits, nat, x[:16].contiguous(), N, K)
     assert O.max_rel(y16.cpu(), ref[:16].cpu()) <= TOL
+
+
+def test_prefill_gemm_k_split_is_deterministic(ops, monkeypatch):
+    """Long rows with few output tiles run K-split over gridDim.z (K >= 8192): the last CTA of a tile adds the partial tiles
+    in split order, so reruns are bit-identical, the tile counters are left at zero (third run), and the result sits
+    within tolerance of fp32 like the unsplit kernel's."""
+    dev = "cuda"
+    N, K, M, bits = 256, 8192, 40, 3
+    codes, scale, zero = _synthetic(N, K, bits, seed=5)
+    cg, sg, zg = torch.from_numpy(codes).to(dev), scale.to(dev), zero.to(dev)
+    nat = ops.pack_native(bits, cg, sg, zg)
+    W = (cg.float().reshape(N, K // G, G) * sg.float()[..., None] - (zg * sg).float()[..., None]).reshape(N, K)
+    torch.manual_seed(3)
+    x = torch.randn(M, K, device=dev).half()
+    bias = torch.randn(N, device=dev).half()
+    ref = (x.float() @ W.t() + bias.float()).cpu()
+    ws = ops.gemm_workspace(M, K, bits, dev)
+    ws.fill_(0xA5)                                             # a caller's workspace is uninitialised memory
+    ys = [ops.gemm_tc(bits, nat, x, N, K, bias, workspace=ws).clone() for _ in range(3)]
+    assert torch.equal(ys[0], ys[1]) and torch.equal(ys[1], ys[2])
+    assert O.max_rel(ys[0].cpu(), ref) <= TOL
+    monkeypatch.setenv("AMQB_TC_NO_SPLITK", "1")
+    y1 = ops.gemm_tc(bits, nat, x, N, K, bias, workspace=ws)
+    assert O.max_rel(y1.cpu(), ref) <= TOL
+    assert O.max_rel(ys[0].cpu(), y1.float().cpu()) <= 1e-3
 
 
 def test_prefill_cluster_variant(ops, monkeypatch):
