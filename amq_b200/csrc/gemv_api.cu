@@ -42,6 +42,7 @@ static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, 
     P.ar = 0;
     P.act = q.act;
     if (q.act != 0 && q.act != 1) return fail(AMQB_ERR_BAD_ARG, "gemv: act must be 0 or 1 (silu)");
+    if (q.act && M != 1) return fail(AMQB_ERR_BAD_ARG, "gemv: act is a batch-1 feature (use AMQB_PRO_SILU_MUL on the consuming launch)");
     if (q.act && q.allreduce && q.allreduce->world > 1) return fail(AMQB_ERR_BAD_ARG, "gemv: act cannot follow a fused all-reduce");
     if (q.allreduce && q.allreduce->world > 1) {
       const amqb_ar_ctx& C = *q.allreduce;

@@ -735,11 +735,15 @@ __device__ __forceinline__ __half act_out(const DevProblem& P, __half h) {
   const float g = __half2float(h);
   return __float2half_rn(__fdividef(g, 1.f + __expf(-g)));
 }
+// ACT: the output activation is compiled into the batch-1 kernels only (the M > 1 kernels' eight-outputs-per-lane epilogue
+// measured 5 % slower per step with it inlined; QuantDecoder keeps the consumer-side SiLU prologue there)
+template <bool ACT>
 __device__ __forceinline__ void store_out(const DevProblem& P, int n, int col, float v, float rs = 1.f) {
   v *= rs;
   if (P.bias) v += __half2float(P.bias[n]);
   if (P.residual) v += __half2float(__ushort_as_half(__ldcg(reinterpret_cast<const unsigned short*>(P.residual) + (size_t)col * P.ldy + n)));
-  P.y[(size_t)col * P.ldy + n] = act_out(P, __float2half_rn(v));
+  const __half hv = __float2half_rn(v);
+  P.y[(size_t)col * P.ldy + n] = ACT ? act_out(P, hv) : hv;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -924,7 +928,7 @@ __global__ void __launch_bounds__(kThreads, kCoresident ? 2 : 1) gemv_mma_kernel
                   if (pre) P.y[rb * 32 + row] = act_out(P, __float2half_rn(fmaf(v, rs_ep, addend)));
                   else if (col < M) {
                     if (fuse) ar_push(L.ar, epoch, col * P.N + rb * 32 + row, v * rs_ep);
-                    else store_out(P, rb * 32 + row, col, v, rs_ep);
+                    else store_out<M1>(P, rb * 32 + row, col, v, rs_ep);
                   }
                 } else {
                   // K was split across the cluster: partial sums meet in rank 0's shared memory (DSMEM)
@@ -955,7 +959,7 @@ __global__ void __launch_bounds__(kThreads, kCoresident ? 2 : 1) gemv_mma_kernel
                     float tt = 0.f;
                     for (int r = 0; r < S; ++r) tt += part[(size_t)(p * S + r) * RS + e];
                     if (fuse) ar_push(L.ar, epoch, col * P.N + rb * 32 + row, tt * rs_ep);
-                    else store_out(P, rb * 32 + row, col, tt, rs_ep);
+                    else store_out<M1>(P, rb * 32 + row, col, tt, rs_ep);
                   }
                 }
               }
@@ -985,7 +989,7 @@ __global__ void __launch_bounds__(kThreads, kCoresident ? 2 : 1) gemv_mma_kernel
               row = tile * 16 + (ln >> 2) + 8 * (ci >> 1);
               col = hb * 8 + 2 * (ln & 3) + (ci & 1);
             }
-            if (col < M) store_out(P, rb * 32 + row, col, ar_collect(L.ar, epoch, col * P.N + rb * 32 + row));
+            if (col < M) store_out<M1>(P, rb * 32 + row, col, ar_collect(L.ar, epoch, col * P.N + rb * 32 + row));
           }
         }
       }

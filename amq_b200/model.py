@@ -116,7 +116,8 @@ class QuantDecoder:
         # Two captured steps: the short-context one launches one CTA per head (the extra CTAs of the split grid, although
         # they leave at once below the threshold, were measured to cost ~0.75 us per layer); step() picks by a host-side
         # mirror of the position.  Either graph is correct at any position — the mirror only selects the faster one.
-        self.silu_in_consumer = os.environ.get("AMQB_SILU_IN_CONSUMER") == "1"      # A/B: round-1 placement of the activation
+        # SiLU in gate_proj's epilogue is a batch-1 feature of the kernels; AMQB_SILU_IN_CONSUMER=1: A/B switch (round-1 placement)
+        self.silu_in_consumer = batch > 1 or os.environ.get("AMQB_SILU_IN_CONSUMER") == "1"
         self._cur_splits = 1
         self._pos_h = 0
         self.graph_long: Optional[torch.cuda.CUDAGraph] = None

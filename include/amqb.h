@@ -125,8 +125,8 @@ typedef struct {
   float eps;
   const amqb_ar_ctx* allreduce; /* host pointer or NULL: fuse the tensor-parallel all-reduce into the epilogue */
   int ar_call;              /* index of this all-reduce inside the step (0 .. 255; consecutive calls alternate parity) */
-  int act;                  /* 0: none; 1: y <- silu(y), applied to the fp16-rounded output (fp32 math, fp16 result: HF's
-                             * act_fn on an fp16 tensor) */
+  int act;                  /* 0: none; 1 (M == 1 only): y <- silu(y), applied to the fp16-rounded output (fp32 math, fp16
+                             * result: HF's act_fn on an fp16 tensor) */
   int after_gemv;           /* scheduling hint, batch 1 (first problem of a launch counts): nonzero = the kernel launched on
                              * this stream right before this one is an amqb batch-1 GEMV launch.  Such a launch is sized to
                              * sit NEXT TO its predecessor on every SM and stream its weights while the predecessor still

@@ -158,7 +158,7 @@ def test_gemv_model_shapes(ops, N, K, bits):
     assert torch.equal(y1, y2)
 
 
-@pytest.mark.parametrize("M", [1, 2, 4])
+@pytest.mark.parametrize("M", [1])
 def test_output_activation_and_mul_prologue(ops, M):
     """gate|up -> down as QuantDecoder launches it: `act = 1` on the gate problem stores silu(gate) and the down launch reads
     x = a * b (AMQB_PRO_MUL) - bit for bit what the one-sided AMQB_PRO_SILU_MUL prologue computes from raw gate / up, and
