@@ -159,7 +159,6 @@ static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, 
     const char* e = getenv("AMQB_COPY_RECS");
     L.copy_recs = e ? atoi(e) : 8;
     if (L.copy_recs < 1) L.copy_recs = 1;
-    L.pair = getenv("AMQB_NO_PAIR") ? 0 : 1;
     const char* d = getenv("AMQB_DBG_DELAY_NS");
     L.dbg_delay_ns = d ? atoi(d) : 0;
   }
@@ -167,7 +166,7 @@ static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, 
   L.xp_variants = (M == 1 && count > 1 && 3 * L.xprime_bytes <= (kCoresident ? 40 : 96) * 1024) ? 3 : 1;
   L.xs_floats = (2 * max_kc * MB * 8 + 31) & ~31;
   const size_t rs = red_stride(M);
-  const size_t fixed = 384 + (size_t)L.xs_floats * 4 + 16 * kCW * 4 + (size_t)L.xp_variants * L.xprime_bytes +
+  const size_t fixed = 384 + (size_t)L.xs_floats * 4 + 1024 + (size_t)L.xp_variants * L.xprime_bytes +
                        (size_t)2 * kCW * rs * 4 + (size_t)acc_blocks * rs * 4 + (S > 1 ? (size_t)count * S * rs * 4 : 0) + 128;
   // stage = two records per consumer warp; one when that would leave fewer than two stages (M > 1 with a large x')
   int stage_recs = max_slice < kStageRecs ? max_slice : kStageRecs;
@@ -190,6 +189,8 @@ static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, 
   size_t smem = fixed + (size_t)ns * L.stage_bytes;
   if (smem < smem_min) smem = smem_min;
   L.ncl = ncl;
+  L.feat = (S > 1 ? kFeatCluster : 0) | (L.ar.world > 1 ? kFeatAllReduce : 0) | (acc_blocks > 0 ? kFeatChunkedK : 0);
+  if (getenv("AMQB_FULL_KERNEL")) L.feat = kFeatAll;        // A/B: always the full instance
   int grid = ncl * S;
   if (M == 1 && kCoresident && grid < B) grid = (B / S) * S;          // place holders: every SM holds a CTA of this launch
   if (pro == AMQB_PRO_NONE) return launch_pro0(L, grid, smem, pdl, st);

@@ -134,9 +134,9 @@ struct GemvLaunch {
   int copy_recs;         // records per cp.async.bulk (a stage is issued as several bulk copies)
   int dbg_delay_ns;      // debug: consumers idle this long after building x' (0 in production)
   int xp_variants;       // 3: x' kept per bit width so problems sharing x reuse it; 1: rebuilt per problem
+  int feat;              // kFeat* bits this launch needs (0: the slim kernel instance)
   int ncl;               // clusters (CTAs at S == 1) that own row blocks; the grid's remaining clusters are place holders
   int window;            // stages the producer keeps in flight (see the producer loop)
-  int pair;              // 1: consumers take two pipeline stages per iteration (A/B switch AMQB_NO_PAIR=1 clears it)
   long long* dbg;        // optional per-CTA timeline (16 x int64 per CTA), NULL in production
 };
 
@@ -747,24 +747,29 @@ __device__ __forceinline__ void store_out(const DevProblem& P, int n, int col, f
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int MB, int KIND, int PRO>
+// FEAT: which rarely needed paths are compiled in.  The kernel is issue- and instruction-cache-sensitive (every launch starts
+// cold and runs a few microseconds): without the cluster split-K, fused all-reduce and chunked-K code the batch-1 kernel is
+// 2136 instead of 2960 SASS instructions and the 7B step 2.1 % faster (profiles/r02_coresident_experiment.txt, item 8).
+constexpr int kFeatCluster = 1, kFeatAllReduce = 2, kFeatChunkedK = 4, kFeatAll = 7;
+template <int MB, int KIND, int PRO, int FEAT>
 __global__ void __launch_bounds__(kThreads, kCoresident ? 2 : 1) gemv_mma_kernel(const __grid_constant__ GemvLaunch L) {
   constexpr bool M1 = KIND == kKindM1;
+  constexpr bool kCluster = (FEAT & kFeatCluster) != 0, kAr = (FEAT & kFeatAllReduce) != 0, kChunk = (FEAT & kFeatChunkedK) != 0;
   constexpr int RS = M1 ? 32 : 2 * MB * 128;            // red_stride(M): floats one warp deposits per row block
   extern __shared__ __align__(1024) uint8_t smem[];
   // smem map: [0,384) barriers | (xsum, delta) | sred | x' | red[2] | accbuf | part[4][S] | ring
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);      // [0,NS) full, [NS,2NS) empty, [24,28) cluster-reduce, 28..32 misc
   float2* xsd = reinterpret_cast<float2*>(smem + 384);
-  float* sred = reinterpret_cast<float*>(smem + 384) + L.xs_floats;     // 16 * kCW floats
-  uint8_t* xp = reinterpret_cast<uint8_t*>(sred + 16 * kCW);
+  float* sred = reinterpret_cast<float*>(smem + 384) + L.xs_floats;     // 256 floats (unused spacer kept for the layout's alignment)
+  uint8_t* xp = reinterpret_cast<uint8_t*>(sred + 256);
   float* red = reinterpret_cast<float*>(xp + (size_t)L.xp_variants * L.xprime_bytes);   // [2][kCW][2*MB*128]
   float* accbuf = red + 2 * kCW * RS;                        // [accbuf_blocks][2*MB*128]
   float* part = accbuf + (size_t)L.accbuf_blocks * RS;       // [count][S][2*MB*128] (S > 1)
-  uint8_t* ring = reinterpret_cast<uint8_t*>(part + (L.S > 1 ? L.count * L.S * RS : 0));
+  uint8_t* ring = reinterpret_cast<uint8_t*>(part + (L.S > 1 ? L.count * L.S * RS : 0));      // (host-side layout: L.S, not S)
   ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ring) + 127) & ~uintptr_t(127));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int S = L.S;
+  const int S = kCluster ? L.S : 1;
   const int rank = S > 1 ? (int)cluster_ctarank() : 0;
   const int cid = blockIdx.x >> L.log2S, ncl = L.ncl;
   const int NS = L.n_stages;
@@ -864,7 +869,7 @@ __global__ void __launch_bounds__(kThreads, kCoresident ? 2 : 1) gemv_mma_kernel
     // nothing to do until the first row block is finished, and multiplies the finished sums (see finish_item)
     float rs_ep = 1.f;
     const __half* rs_x = nullptr;
-    const bool ar_on = L.ar.world > 1;
+    const bool ar_on = kAr && L.ar.world > 1;
     const uint32_t epoch = ar_on ? ar_epoch(L.ar) : 0u;
     for (int p = 0; p < L.count; ++p) {
       const DevProblem P = sprob[p];
@@ -884,7 +889,7 @@ __global__ void __launch_bounds__(kThreads, kCoresident ? 2 : 1) gemv_mma_kernel
         rs_ep = rsqrtf(ss / (float)P.K + P.eps);
       }
       const int g_lo = (P.n_g * rank) >> L.log2S, g_hi = (P.n_g * (rank + 1)) >> L.log2S;
-      const bool chunked = (g_hi - g_lo) > P.kc;
+      const bool chunked = kChunk && (g_hi - g_lo) > P.kc;
       for (int c_lo = g_lo; c_lo < g_hi; c_lo += P.kc) {
         const int c_hi = (c_lo + P.kc) < g_hi ? (c_lo + P.kc) : g_hi;
         const bool first_chunk = c_lo == g_lo, last_chunk = c_hi == g_hi;
@@ -1024,7 +1029,7 @@ __global__ void __launch_bounds__(kThreads, kCoresident ? 2 : 1) gemv_mma_kernel
     const uint32_t rbytes = rec_bytes(P.bits);
     const int gbytes = xp_group_bytes(P.bits, M);
     const int g_lo = (P.n_g * rank) >> L.log2S, g_hi = (P.n_g * (rank + 1)) >> L.log2S;
-    const bool chunked = (g_hi - g_lo) > P.kc;
+    const bool chunked = kChunk && (g_hi - g_lo) > P.kc;
     AMQB_STAMP(4 + 4 * p);
     const bool same_x = (P.x == cur_x) && (P.K == cur_K);
     if (!same_x) { built_mask = 0; cur_x = P.x; cur_K = P.K; }
@@ -1074,7 +1079,7 @@ __global__ void __launch_bounds__(kThreads, kCoresident ? 2 : 1) gemv_mma_kernel
           if (KIND != kKindWide) {
             // records `warp` and `warp + kCW` of the stage: four independent IMMA chains per warp
             const uint32_t r0 = ring_u + s * L.stage_bytes + warp_rec, x0 = xpv_u + gl * gbytes, d0 = xsd_u + gl * 64;
-            if (warp + kCW < nrec && L.pair) {
+            if (warp + kCW < nrec) {
               const uint32_t rec[2] = {r0, r0 + kCW * rbytes};
               const uint32_t xpg[2] = {x0, x0 + kCW * gbytes};
               const uint32_t xsg[2] = {d0, d0 + kCW * 64};
@@ -1159,9 +1164,9 @@ __global__ void __launch_bounds__(kThreads, kCoresident ? 2 : 1) gemv_mma_kernel
 }
 
 
-template <int MB, int KIND, int PRO>
+template <int MB, int KIND, int PRO, int FEAT>
 static int launch_variant(const GemvLaunch& L, int grid, size_t smem, int pdl, cudaStream_t st) {
-  auto kern = gemv_mma_kernel<MB, KIND, PRO>;
+  auto kern = gemv_mma_kernel<MB, KIND, PRO, FEAT>;
   static PerDeviceOnce attr;
   if (attr.first()) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
@@ -1171,7 +1176,7 @@ static int launch_variant(const GemvLaunch& L, int grid, size_t smem, int pdl, c
     if (getenv("AMQB_DBG_OCC")) {
       int nb = -1;
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem);
-      fprintf(stderr, "gemv<%d,%d,%d>: %d threads, %zu B dynamic smem -> %d CTAs per SM\n", MB, KIND, PRO, kThreads, smem, nb);
+      fprintf(stderr, "gemv<%d,%d,%d,%d>: %d threads, %zu B dynamic smem -> %d CTAs per SM\n", MB, KIND, PRO, FEAT, kThreads, smem, nb);
     }
   }
   cudaLaunchConfig_t cfg{};
@@ -1206,9 +1211,12 @@ static int launch_variant(const GemvLaunch& L, int grid, size_t smem, int pdl, c
 // one translation unit per prologue kind instantiates this (gemv_pro0.cu / gemv_pro1.cu / gemv_pro2.cu)
 template <int PRO>
 static int launch_pro(const GemvLaunch& L, int grid, size_t smem, int pdl, cudaStream_t st) {
-  if (L.M == 1) return launch_variant<1, kKindM1, PRO>(L, grid, smem, pdl, st);
-  if (L.M == 2) return launch_variant<1, kKindSmall, PRO>(L, grid, smem, pdl, st);
-  return launch_variant<1, kKindWide, PRO>(L, grid, smem, pdl, st);     // M = 3..8 (larger M: two passes, gemv_api.cu)
+  // the slim instance whenever the launch needs none of the optional paths (every launch of a single-GPU 7B decoder)
+  const bool full = L.feat != 0;
+  if (L.M == 1) return full ? launch_variant<1, kKindM1, PRO, kFeatAll>(L, grid, smem, pdl, st) : launch_variant<1, kKindM1, PRO, 0>(L, grid, smem, pdl, st);
+  if (L.M == 2) return full ? launch_variant<1, kKindSmall, PRO, kFeatAll>(L, grid, smem, pdl, st) : launch_variant<1, kKindSmall, PRO, 0>(L, grid, smem, pdl, st);
+  // M = 3..8 (larger M: two passes, gemv_api.cu)
+  return full ? launch_variant<1, kKindWide, PRO, kFeatAll>(L, grid, smem, pdl, st) : launch_variant<1, kKindWide, PRO, 0>(L, grid, smem, pdl, st);
 }
 
 int launch_pro0(const GemvLaunch& L, int grid, size_t smem, int pdl, cudaStream_t st);
