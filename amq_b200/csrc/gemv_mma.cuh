@@ -135,6 +135,7 @@ struct GemvLaunch {
   int dbg_delay_ns;      // debug: consumers idle this long after building x' (0 in production)
   int xp_variants;       // 3: x' kept per bit width so problems sharing x reuse it; 1: rebuilt per problem
   int feat;              // kFeat* bits this launch needs (0: the slim kernel instance)
+  int bsel;              // the bit width every problem of the launch shares, or 0
   int ncl;               // clusters (CTAs at S == 1) that own row blocks; the grid's remaining clusters are place holders
   int window;            // stages the producer keeps in flight (see the producer loop)
   long long* dbg;        // optional per-CTA timeline (16 x int64 per CTA), NULL in production
@@ -302,7 +303,7 @@ __device__ __forceinline__ void store_xsd(float2* xsd_g, int M, int MB, int mm, 
 }
 
 // everything one item writes: all requested bit-width variants + its (xsum, delta) entries
-template <int KIND>
+template <int KIND, int BSEL = 0>
 __device__ __forceinline__ void emit_item(const float (&xf)[4], const XLane (&xl)[3], int mask, uint8_t* const (&vbase)[3],
                                           const int (&gbytes)[3], int gl, int dstride, float2* xsd_g, int M, int MB, int mm,
                                           int lane, bool valid) {
@@ -310,7 +311,7 @@ __device__ __forceinline__ void emit_item(const float (&xf)[4], const XLane (&xl
   const float2 sd = item_stats(xf, e);
 #pragma unroll
   for (int v = 0; v < 3; ++v)
-    if (mask & (4 << v)) {                               // warp-uniform
+    if ((BSEL == 0 || v == BSEL - 2) && (mask & (4 << v))) {      // warp-uniform; BSEL: the launch's only bit width
       uint8_t* g = vbase[v] + (size_t)gl * gbytes[v];
       emit_reg(g + xl[v].off0, dstride, xf, xl[v].fexp0, e, valid);
       if (v == 1) emit_reg(g + (xl[v].off1 < 0 ? 0 : xl[v].off1), dstride, xf, xl[v].fexp1, e, valid && xl[v].off1 >= 0);
@@ -331,7 +332,7 @@ __device__ __forceinline__ void emit_item(const float (&xf)[4], const XLane (&xl
 #define AMQB_KPRE_SILU AMQB_KPRE
 #endif
 template <int PRO> struct PreItems { static constexpr int value = (PRO == AMQB_PRO_SILU_MUL || PRO == AMQB_PRO_MUL) ? AMQB_KPRE_SILU : AMQB_KPRE; };
-template <int PRO>
+template <int PRO, int BSEL>
 __device__ __forceinline__ void build_xprime(const DevProblem& P, int g_lo, int len, uint8_t* xp, float2* xsd, int cw,
                                              int lane, int mask, int variants, int var_stride, const XLane (&xl)[3],
                                              bool& waited, long long* dbgp = nullptr) {
@@ -383,8 +384,8 @@ __device__ __forceinline__ void build_xprime(const DevProblem& P, int g_lo, int 
         finish_item<PRO>(a[i], b[i], 1.f, x0);
         finish_item<PRO>(v1 ? a[i + 1] : a[i], v1 ? b[i + 1] : b[i], 1.f, x1);
         AMQB_DBG(if (dbgp && base + i == 0) dbgp[14] = clock64() + (x0[0] == 1.2345e-30f);)
-        emit_item<kKindM1>(x0, xl, mask, vbase, gbytes, gl0, 32, xsd + (size_t)gl0 * 8, 1, 1, 0, lane, true);
-        emit_item<kKindM1>(x1, xl, mask, vbase, gbytes, gl1, 32, xsd + (size_t)gl1 * 8, 1, 1, 0, lane, v1);
+        emit_item<kKindM1, BSEL>(x0, xl, mask, vbase, gbytes, gl0, 32, xsd + (size_t)gl0 * 8, 1, 1, 0, lane, true);
+        emit_item<kKindM1, BSEL>(x1, xl, mask, vbase, gbytes, gl1, 32, xsd + (size_t)gl1 * 8, 1, 1, 0, lane, v1);
       }
     }
   }
@@ -751,7 +752,9 @@ __device__ __forceinline__ void store_out(const DevProblem& P, int n, int col, f
 // cold and runs a few microseconds): without the cluster split-K, fused all-reduce and chunked-K code the batch-1 kernel is
 // 2136 instead of 2960 SASS instructions and the 7B step 2.1 % faster (profiles/r02_coresident_experiment.txt, item 8).
 constexpr int kFeatCluster = 1, kFeatAllReduce = 2, kFeatChunkedK = 4, kFeatAll = 7;
-template <int MB, int KIND, int PRO, int FEAT>
+// BSEL: 0 = any mix of bit widths; 2 / 3 / 4 = every problem of the launch has this width (o_proj, down_proj, uniform
+// groups): the other widths' record code and x' variants are not compiled in.
+template <int MB, int KIND, int PRO, int FEAT, int BSEL>
 __global__ void __launch_bounds__(kThreads, kCoresident ? 2 : 1) gemv_mma_kernel(const __grid_constant__ GemvLaunch L) {
   constexpr bool M1 = KIND == kKindM1;
   constexpr bool kCluster = (FEAT & kFeatCluster) != 0, kAr = (FEAT & kFeatAllReduce) != 0, kChunk = (FEAT & kFeatChunkedK) != 0;
@@ -1026,8 +1029,9 @@ __global__ void __launch_bounds__(kThreads, kCoresident ? 2 : 1) gemv_mma_kernel
   uint32_t xphase = 0;
   for (int p = 0; p < L.count; ++p) {
     const DevProblem P = sprob[p];
-    const uint32_t rbytes = rec_bytes(P.bits);
-    const int gbytes = xp_group_bytes(P.bits, M);
+    const int bits = BSEL ? BSEL : P.bits;
+    const uint32_t rbytes = rec_bytes(bits);
+    const int gbytes = xp_group_bytes(bits, M);
     const int g_lo = (P.n_g * rank) >> L.log2S, g_hi = (P.n_g * (rank + 1)) >> L.log2S;
     const bool chunked = kChunk && (g_hi - g_lo) > P.kc;
     AMQB_STAMP(4 + 4 * p);
@@ -1035,7 +1039,7 @@ __global__ void __launch_bounds__(kThreads, kCoresident ? 2 : 1) gemv_mma_kernel
     if (!same_x) { built_mask = 0; cur_x = P.x; cur_K = P.K; }
     if (P.build_mask) run_mask = P.build_mask;
     if (first_rb(cid, P.rot, ncl) >= P.n_rb) continue;          // (after the bookkeeping: a later problem may rely on this run's mask)
-    uint8_t* xpv = xp + (L.xp_variants == 3 ? (size_t)(P.bits - 2) * L.xprime_bytes : 0);
+    uint8_t* xpv = xp + (L.xp_variants == 3 ? (size_t)(bits - 2) * L.xprime_bytes : 0);
     const uint32_t ring_u = smem_u32(ring), xpv_u = smem_u32(xpv), xsd_u = smem_u32(xsd), warp_rec = warp * rbytes;
     for (int c_lo = g_lo; c_lo < g_hi; c_lo += P.kc) {
       const int c_hi = (c_lo + P.kc) < g_hi ? (c_lo + P.kc) : g_hi;
@@ -1055,11 +1059,11 @@ __global__ void __launch_bounds__(kThreads, kCoresident ? 2 : 1) gemv_mma_kernel
         mbar_wait(xb, xphase);
         xphase ^= 1;
       } else {
-        const int want = (chunked || L.xp_variants != 3) ? (1 << P.bits) : ((run_mask | (1 << P.bits)) & ~built_mask);
+        const int want = (BSEL || chunked || L.xp_variants != 3) ? (1 << bits) : ((run_mask | (1 << bits)) & ~built_mask);
         if (want && M1)
-          build_xprime<PRO>(P, c_lo, c_hi - c_lo, xp, xsd, warp, lane, want, L.xp_variants, L.xprime_bytes, xl, waited
+          build_xprime<PRO, BSEL>(P, c_lo, c_hi - c_lo, xp, xsd, warp, lane, want, L.xp_variants, L.xprime_bytes, xl, waited
                             AMQB_DBG(, (L.dbg && tid == 0) ? L.dbg + blockIdx.x * 16 : nullptr));
-        built_mask |= want | (1 << P.bits);
+        built_mask |= want | (1 << bits);
       }
       AMQB_DBG(if (L.dbg_delay_ns > 0) { const long long t_end = gtime() + L.dbg_delay_ns; while (gtime() < t_end) {} })
       AMQB_STAMP(5 + 4 * p);
@@ -1083,8 +1087,8 @@ __global__ void __launch_bounds__(kThreads, kCoresident ? 2 : 1) gemv_mma_kernel
               const uint32_t rec[2] = {r0, r0 + kCW * rbytes};
               const uint32_t xpg[2] = {x0, x0 + kCW * gbytes};
               const uint32_t xsg[2] = {d0, d0 + kCW * 64};
-              if (P.bits == 3) process_records<3, KIND, 2>(rec, xpg, xsg, M, lane, acc);
-              else if (P.bits == 4) process_records<4, KIND, 2>(rec, xpg, xsg, M, lane, acc);
+              if (BSEL ? BSEL == 3 : bits == 3) process_records<3, KIND, 2>(rec, xpg, xsg, M, lane, acc);
+              else if (BSEL ? BSEL == 4 : bits == 4) process_records<4, KIND, 2>(rec, xpg, xsg, M, lane, acc);
               else process_records<2, KIND, 2>(rec, xpg, xsg, M, lane, acc);
             } else {
 #pragma unroll 1
@@ -1093,8 +1097,8 @@ __global__ void __launch_bounds__(kThreads, kCoresident ? 2 : 1) gemv_mma_kernel
                 const uint32_t rec[1] = {r0 + h * kCW * rbytes};
                 const uint32_t xpg[1] = {x0 + h * kCW * gbytes};
                 const uint32_t xsg[1] = {d0 + h * kCW * 64};
-                if (P.bits == 3) process_records<3, KIND, 1>(rec, xpg, xsg, M, lane, acc);
-                else if (P.bits == 4) process_records<4, KIND, 1>(rec, xpg, xsg, M, lane, acc);
+                if (BSEL ? BSEL == 3 : bits == 3) process_records<3, KIND, 1>(rec, xpg, xsg, M, lane, acc);
+                else if (BSEL ? BSEL == 4 : bits == 4) process_records<4, KIND, 1>(rec, xpg, xsg, M, lane, acc);
                 else process_records<2, KIND, 1>(rec, xpg, xsg, M, lane, acc);
               }
             }
@@ -1164,9 +1168,9 @@ __global__ void __launch_bounds__(kThreads, kCoresident ? 2 : 1) gemv_mma_kernel
 }
 
 
-template <int MB, int KIND, int PRO, int FEAT>
+template <int MB, int KIND, int PRO, int FEAT, int BSEL = 0>
 static int launch_variant(const GemvLaunch& L, int grid, size_t smem, int pdl, cudaStream_t st) {
-  auto kern = gemv_mma_kernel<MB, KIND, PRO, FEAT>;
+  auto kern = gemv_mma_kernel<MB, KIND, PRO, FEAT, BSEL>;
   static PerDeviceOnce attr;
   if (attr.first()) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
@@ -1213,7 +1217,13 @@ template <int PRO>
 static int launch_pro(const GemvLaunch& L, int grid, size_t smem, int pdl, cudaStream_t st) {
   // the slim instance whenever the launch needs none of the optional paths (every launch of a single-GPU 7B decoder)
   const bool full = L.feat != 0;
-  if (L.M == 1) return full ? launch_variant<1, kKindM1, PRO, kFeatAll>(L, grid, smem, pdl, st) : launch_variant<1, kKindM1, PRO, 0>(L, grid, smem, pdl, st);
+  if (L.M == 1) {
+    if (full) return launch_variant<1, kKindM1, PRO, kFeatAll>(L, grid, smem, pdl, st);
+    if (L.bsel == 2) return launch_variant<1, kKindM1, PRO, 0, 2>(L, grid, smem, pdl, st);
+    if (L.bsel == 3) return launch_variant<1, kKindM1, PRO, 0, 3>(L, grid, smem, pdl, st);
+    if (L.bsel == 4) return launch_variant<1, kKindM1, PRO, 0, 4>(L, grid, smem, pdl, st);
+    return launch_variant<1, kKindM1, PRO, 0>(L, grid, smem, pdl, st);
+  }
   if (L.M == 2) return full ? launch_variant<1, kKindSmall, PRO, kFeatAll>(L, grid, smem, pdl, st) : launch_variant<1, kKindSmall, PRO, 0>(L, grid, smem, pdl, st);
   // M = 3..8 (larger M: two passes, gemv_api.cu)
   return full ? launch_variant<1, kKindWide, PRO, kFeatAll>(L, grid, smem, pdl, st) : launch_variant<1, kKindWide, PRO, 0>(L, grid, smem, pdl, st);
