@@ -191,10 +191,9 @@ static int launch_group(const amqb_gemv_problem* const* pr, int count, int pdl, 
   L.ncl = ncl;
   L.feat = (S > 1 ? kFeatCluster : 0) | (L.ar.world > 1 ? kFeatAllReduce : 0) | (acc_blocks > 0 ? kFeatChunkedK : 0);
   if (getenv("AMQB_FULL_KERNEL")) L.feat = kFeatAll;        // A/B: always the full instance
-  L.bsel = L.prob[0].bits;
-  for (int i = 1; i < count; ++i)
-    if (L.prob[i].bits != L.bsel) L.bsel = 0;
-  if (getenv("AMQB_NO_BSEL")) L.bsel = 0;                   // A/B: never the single-width instances
+  L.bsel = 0;
+  for (int i = 0; i < count; ++i) L.bsel |= 1 << L.prob[i].bits;
+  if (L.bsel == 28 || getenv("AMQB_NO_BSEL")) L.bsel = 0;   // all three widths / A/B: the any-width instance
   int grid = ncl * S;
   if (M == 1 && kCoresident && grid < B) grid = (B / S) * S;          // place holders: every SM holds a CTA of this launch
   if (pro == AMQB_PRO_NONE) return launch_pro0(L, grid, smem, pdl, st);

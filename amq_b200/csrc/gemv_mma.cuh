@@ -135,7 +135,7 @@ struct GemvLaunch {
   int dbg_delay_ns;      // debug: consumers idle this long after building x' (0 in production)
   int xp_variants;       // 3: x' kept per bit width so problems sharing x reuse it; 1: rebuilt per problem
   int feat;              // kFeat* bits this launch needs (0: the slim kernel instance)
-  int bsel;              // the bit width every problem of the launch shares, or 0
+  int bsel;              // mask of the bit widths of the launch's problems (bit b: width b), or 0 = the any-width instance
   int ncl;               // clusters (CTAs at S == 1) that own row blocks; the grid's remaining clusters are place holders
   int window;            // stages the producer keeps in flight (see the producer loop)
   long long* dbg;        // optional per-CTA timeline (16 x int64 per CTA), NULL in production
@@ -311,7 +311,7 @@ __device__ __forceinline__ void emit_item(const float (&xf)[4], const XLane (&xl
   const float2 sd = item_stats(xf, e);
 #pragma unroll
   for (int v = 0; v < 3; ++v)
-    if ((BSEL == 0 || v == BSEL - 2) && (mask & (4 << v))) {      // warp-uniform; BSEL: the launch's only bit width
+    if ((BSEL == 0 || ((BSEL >> (v + 2)) & 1)) && (mask & (4 << v))) {      // warp-uniform; BSEL: the launch's bit widths
       uint8_t* g = vbase[v] + (size_t)gl * gbytes[v];
       emit_reg(g + xl[v].off0, dstride, xf, xl[v].fexp0, e, valid);
       if (v == 1) emit_reg(g + (xl[v].off1 < 0 ? 0 : xl[v].off1), dstride, xf, xl[v].fexp1, e, valid && xl[v].off1 >= 0);
@@ -752,8 +752,10 @@ __device__ __forceinline__ void store_out(const DevProblem& P, int n, int col, f
 // cold and runs a few microseconds): without the cluster split-K, fused all-reduce and chunked-K code the batch-1 kernel is
 // 2136 instead of 2960 SASS instructions and the 7B step 2.1 % faster (profiles/r02_coresident_experiment.txt, item 8).
 constexpr int kFeatCluster = 1, kFeatAllReduce = 2, kFeatChunkedK = 4, kFeatAll = 7;
-// BSEL: 0 = any mix of bit widths; 2 / 3 / 4 = every problem of the launch has this width (o_proj, down_proj, uniform
-// groups): the other widths' record code and x' variants are not compiled in.
+// BSEL: mask of the bit widths the launch's problems have (bit b set: width b; 0 = any): the other widths' record code and
+// x' variants are not compiled in.  One width: o_proj, down_proj, uniform groups; two: most q|k|v and gate|up launches.
+constexpr bool bsel_single(int m) { return m == 4 || m == 8 || m == 16; }
+constexpr int bsel_width(int m) { return m == 4 ? 2 : (m == 8 ? 3 : 4); }
 template <int MB, int KIND, int PRO, int FEAT, int BSEL>
 __global__ void __launch_bounds__(kThreads, kCoresident ? 2 : 1) gemv_mma_kernel(const __grid_constant__ GemvLaunch L) {
   constexpr bool M1 = KIND == kKindM1;
@@ -1029,7 +1031,8 @@ __global__ void __launch_bounds__(kThreads, kCoresident ? 2 : 1) gemv_mma_kernel
   uint32_t xphase = 0;
   for (int p = 0; p < L.count; ++p) {
     const DevProblem P = sprob[p];
-    const int bits = BSEL ? BSEL : P.bits;
+    constexpr bool has2 = BSEL == 0 || (BSEL & 4), has3 = BSEL == 0 || (BSEL & 8), has4 = BSEL == 0 || (BSEL & 16);
+    const int bits = bsel_single(BSEL) ? bsel_width(BSEL) : P.bits;
     const uint32_t rbytes = rec_bytes(bits);
     const int gbytes = xp_group_bytes(bits, M);
     const int g_lo = (P.n_g * rank) >> L.log2S, g_hi = (P.n_g * (rank + 1)) >> L.log2S;
@@ -1059,7 +1062,7 @@ __global__ void __launch_bounds__(kThreads, kCoresident ? 2 : 1) gemv_mma_kernel
         mbar_wait(xb, xphase);
         xphase ^= 1;
       } else {
-        const int want = (BSEL || chunked || L.xp_variants != 3) ? (1 << bits) : ((run_mask | (1 << bits)) & ~built_mask);
+        const int want = (bsel_single(BSEL) || chunked || L.xp_variants != 3) ? (1 << bits) : ((run_mask | (1 << bits)) & ~built_mask);
         if (want && M1)
           build_xprime<PRO, BSEL>(P, c_lo, c_hi - c_lo, xp, xsd, warp, lane, want, L.xp_variants, L.xprime_bytes, xl, waited
                             AMQB_DBG(, (L.dbg && tid == 0) ? L.dbg + blockIdx.x * 16 : nullptr));
@@ -1087,9 +1090,9 @@ __global__ void __launch_bounds__(kThreads, kCoresident ? 2 : 1) gemv_mma_kernel
               const uint32_t rec[2] = {r0, r0 + kCW * rbytes};
               const uint32_t xpg[2] = {x0, x0 + kCW * gbytes};
               const uint32_t xsg[2] = {d0, d0 + kCW * 64};
-              if (BSEL ? BSEL == 3 : bits == 3) process_records<3, KIND, 2>(rec, xpg, xsg, M, lane, acc);
-              else if (BSEL ? BSEL == 4 : bits == 4) process_records<4, KIND, 2>(rec, xpg, xsg, M, lane, acc);
-              else process_records<2, KIND, 2>(rec, xpg, xsg, M, lane, acc);
+              if (has3 && (bits == 3 || (!has2 && !has4))) process_records<3, KIND, 2>(rec, xpg, xsg, M, lane, acc);
+              else if (has4 && (bits == 4 || !has2)) process_records<4, KIND, 2>(rec, xpg, xsg, M, lane, acc);
+              else if (has2) process_records<2, KIND, 2>(rec, xpg, xsg, M, lane, acc);
             } else {
 #pragma unroll 1
               for (int h = 0; h < 2; ++h) {
@@ -1097,9 +1100,9 @@ __global__ void __launch_bounds__(kThreads, kCoresident ? 2 : 1) gemv_mma_kernel
                 const uint32_t rec[1] = {r0 + h * kCW * rbytes};
                 const uint32_t xpg[1] = {x0 + h * kCW * gbytes};
                 const uint32_t xsg[1] = {d0 + h * kCW * 64};
-                if (BSEL ? BSEL == 3 : bits == 3) process_records<3, KIND, 1>(rec, xpg, xsg, M, lane, acc);
-                else if (BSEL ? BSEL == 4 : bits == 4) process_records<4, KIND, 1>(rec, xpg, xsg, M, lane, acc);
-                else process_records<2, KIND, 1>(rec, xpg, xsg, M, lane, acc);
+                if (has3 && (bits == 3 || (!has2 && !has4))) process_records<3, KIND, 1>(rec, xpg, xsg, M, lane, acc);
+                else if (has4 && (bits == 4 || !has2)) process_records<4, KIND, 1>(rec, xpg, xsg, M, lane, acc);
+                else if (has2) process_records<2, KIND, 1>(rec, xpg, xsg, M, lane, acc);
               }
             }
           } else {
@@ -1219,10 +1222,15 @@ static int launch_pro(const GemvLaunch& L, int grid, size_t smem, int pdl, cudaS
   const bool full = L.feat != 0;
   if (L.M == 1) {
     if (full) return launch_variant<1, kKindM1, PRO, kFeatAll>(L, grid, smem, pdl, st);
-    if (L.bsel == 2) return launch_variant<1, kKindM1, PRO, 0, 2>(L, grid, smem, pdl, st);
-    if (L.bsel == 3) return launch_variant<1, kKindM1, PRO, 0, 3>(L, grid, smem, pdl, st);
-    if (L.bsel == 4) return launch_variant<1, kKindM1, PRO, 0, 4>(L, grid, smem, pdl, st);
-    return launch_variant<1, kKindM1, PRO, 0>(L, grid, smem, pdl, st);
+    switch (L.bsel) {
+      case 4: return launch_variant<1, kKindM1, PRO, 0, 4>(L, grid, smem, pdl, st);
+      case 8: return launch_variant<1, kKindM1, PRO, 0, 8>(L, grid, smem, pdl, st);
+      case 16: return launch_variant<1, kKindM1, PRO, 0, 16>(L, grid, smem, pdl, st);
+      case 12: return launch_variant<1, kKindM1, PRO, 0, 12>(L, grid, smem, pdl, st);
+      case 20: return launch_variant<1, kKindM1, PRO, 0, 20>(L, grid, smem, pdl, st);
+      case 24: return launch_variant<1, kKindM1, PRO, 0, 24>(L, grid, smem, pdl, st);
+      default: return launch_variant<1, kKindM1, PRO, 0>(L, grid, smem, pdl, st);
+    }
   }
   if (L.M == 2) return full ? launch_variant<1, kKindSmall, PRO, kFeatAll>(L, grid, smem, pdl, st) : launch_variant<1, kKindSmall, PRO, 0>(L, grid, smem, pdl, st);
   // M = 3..8 (larger M: two passes, gemv_api.cu)
