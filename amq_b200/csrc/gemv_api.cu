@@ -208,6 +208,19 @@ using namespace amqb;
 
 extern "C" {
 
+/* Loads and configures every kernel instance of the decode path on the current device (see prep_variant). */
+int amqb_preload(void) {
+  preload_pro0(); preload_pro1(); preload_pro2(); preload_pro3();
+  preload_glue();
+  preload_allreduce();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("preload: %s", cudaGetErrorString(e));
+    return AMQB_ERR_LAUNCH;
+  }
+  return AMQB_OK;
+}
+
 /* debug: per-CTA globaltimer stamps (8 x int64 per CTA) written by the next decode launches */
 int amqb_debug_set_timeline(void* buf) {
   g_dbg = (long long*)buf;

@@ -1171,8 +1171,12 @@ __global__ void __launch_bounds__(kThreads, kCoresident ? 2 : 1) gemv_mma_kernel
 }
 
 
+// One-time set-up of a kernel instance on the current device (function attributes; with CUDA's lazy module loading this is
+// also what loads the instance).  amqb_preload() runs it for EVERY instance up front: a first use in the middle of a decode
+// step can synchronise the context, and a tensor-parallel rank whose peer spins on its partial sums must never do that
+// (measured: emulated tp = 4 ranks on one GPU ran into the all-reduce's time-out on the first step of a process).
 template <int MB, int KIND, int PRO, int FEAT, int BSEL = 0>
-static int launch_variant(const GemvLaunch& L, int grid, size_t smem, int pdl, cudaStream_t st) {
+static void prep_variant() {
   auto kern = gemv_mma_kernel<MB, KIND, PRO, FEAT, BSEL>;
   static PerDeviceOnce attr;
   if (attr.first()) {
@@ -1180,11 +1184,17 @@ static int launch_variant(const GemvLaunch& L, int grid, size_t smem, int pdl, c
     // the shared-memory / L1 split is per kernel: without this the driver may pick a carve-out that holds ONE of these
     // CTAs even when two would fit the SM's other limits
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (getenv("AMQB_DBG_OCC")) {
-      int nb = -1;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem);
-      fprintf(stderr, "gemv<%d,%d,%d,%d>: %d threads, %zu B dynamic smem -> %d CTAs per SM\n", MB, KIND, PRO, FEAT, kThreads, smem, nb);
-    }
+  }
+}
+
+template <int MB, int KIND, int PRO, int FEAT, int BSEL = 0>
+static int launch_variant(const GemvLaunch& L, int grid, size_t smem, int pdl, cudaStream_t st) {
+  auto kern = gemv_mma_kernel<MB, KIND, PRO, FEAT, BSEL>;
+  prep_variant<MB, KIND, PRO, FEAT, BSEL>();
+  if (getenv("AMQB_DBG_OCC")) {
+    int nb = -1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem);
+    fprintf(stderr, "gemv<%d,%d,%d,%d,%d>: %d threads, %zu B dynamic smem -> %d CTAs per SM\n", MB, KIND, PRO, FEAT, BSEL, kThreads, smem, nb);
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
@@ -1236,6 +1246,21 @@ static int launch_pro(const GemvLaunch& L, int grid, size_t smem, int pdl, cudaS
   // M = 3..8 (larger M: two passes, gemv_api.cu)
   return full ? launch_variant<1, kKindWide, PRO, kFeatAll>(L, grid, smem, pdl, st) : launch_variant<1, kKindWide, PRO, 0>(L, grid, smem, pdl, st);
 }
+
+// every instance launch_pro<PRO> can dispatch to, and the pre-pass kernel of that prologue
+template <int PRO>
+static void preload_pro() {
+  prep_variant<1, kKindM1, PRO, kFeatAll>();
+  prep_variant<1, kKindM1, PRO, 0>();
+  prep_variant<1, kKindM1, PRO, 0, 4>(); prep_variant<1, kKindM1, PRO, 0, 8>(); prep_variant<1, kKindM1, PRO, 0, 16>();
+  prep_variant<1, kKindM1, PRO, 0, 12>(); prep_variant<1, kKindM1, PRO, 0, 20>(); prep_variant<1, kKindM1, PRO, 0, 24>();
+  prep_variant<1, kKindSmall, PRO, kFeatAll>(); prep_variant<1, kKindSmall, PRO, 0>();
+  prep_variant<1, kKindWide, PRO, kFeatAll>(); prep_variant<1, kKindWide, PRO, 0>();
+  cudaFuncAttributes fa;
+  cudaFuncGetAttributes(&fa, xprime_global_kernel<PRO>);
+}
+void preload_pro0(); void preload_pro1(); void preload_pro2(); void preload_pro3();
+void preload_glue(); void preload_allreduce();
 
 int launch_pro0(const GemvLaunch& L, int grid, size_t smem, int pdl, cudaStream_t st);
 int launch_xg0(const XgArgs& A, int pdl, cudaStream_t st);

@@ -6,4 +6,5 @@ int launch_pro0(const GemvLaunch& L, int grid, size_t smem, int pdl, cudaStream_
   return launch_pro<AMQB_PRO_NONE>(L, grid, smem, pdl, st);
 }
 int launch_xg0(const XgArgs& A, int pdl, cudaStream_t st) { return launch_xprime_global<AMQB_PRO_NONE>(A, pdl, st); }
+void preload_pro0() { preload_pro<AMQB_PRO_NONE>(); }
 }  // namespace amqb

@@ -663,6 +663,21 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const float* logits, int64
 
 }  // namespace amqb
 
+namespace amqb {
+void preload_glue() {
+  cudaFuncAttributes fa;
+  cudaFuncGetAttributes(&fa, embed_kernel);
+  cudaFuncGetAttributes(&fa, attn_decode_kernel<64>); cudaFuncGetAttributes(&fa, attn_decode_kernel<128>);
+  cudaFuncGetAttributes(&fa, attn_decode_split_kernel<64>); cudaFuncGetAttributes(&fa, attn_decode_split_kernel<128>);
+  cudaFuncSetAttribute(lm_head_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(lm_head_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(lm_head_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(lm_head_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(lm_head_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncGetAttributes(&fa, argmax_kernel);
+}
+}  // namespace amqb
+
 using namespace amqb;
 
 extern "C" {

@@ -68,6 +68,7 @@ class QuantDecoder:
         self.I_loc = shape.inter // tp
         self.q_dim, self.kv_dim = self.Hq * self.D, self.Hkv * self.D
         torch.cuda.set_device(self.dev)
+        check(lib().amqb_preload(), "preload")          # no first-use kernel loads (context synchronisation) inside a decode step
         gen = torch.Generator(device=self.dev).manual_seed(seed)
         H, B = self.H, batch
         self.embed = (torch.randn(shape.vocab, H, device=self.dev, generator=gen) * 0.02).half()

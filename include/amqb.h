@@ -136,6 +136,11 @@ typedef struct {
 /* One launch over `count` independent problems sharing M (q/k/v or gate/up, mixed bit-widths
  * allowed).  workspace: amqb_workspace_bytes() bytes.  pdl != 0 launches with
  * programmatic stream serialization (weights prefetch overlaps the previous kernel's tail). */
+/* Loads and configures every decode-path kernel instance on the current device.  Call once per device before the first
+ * decode step of a process whose steps must not synchronise the context (tensor-parallel ranks waiting on each other,
+ * ranks emulated as streams of one GPU): a kernel's first use otherwise can.  QuantDecoder calls it. */
+int amqb_preload(void);
+
 int amqb_gemv_grouped(const amqb_gemv_problem* problems_host, int count,
                       void* workspace, size_t workspace_bytes, int pdl, void* stream);
 /* Single-problem convenience wrappers, one per bit width (the three specialisations). */
