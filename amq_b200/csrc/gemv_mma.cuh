@@ -847,6 +847,7 @@ __global__ void __launch_bounds__(kThreads, kCoresident ? 2 : 1) gemv_mma_kernel
                 const int j = it - L.window;
                 mbar_wait(smem_u32(&bars[j % NS]), (j / NS) & 1);
               }
+              AMQB_DBG(if (L.dbg && it < 3) L.dbg[148 * 16 + blockIdx.x * 32 + 24 + it] = clock64();)
               ++it;
               const uint32_t bytes = nrec * rbytes;
               mbar_expect_tx(smem_u32(&bars[s]), bytes);
@@ -861,6 +862,16 @@ __global__ void __launch_bounds__(kThreads, kCoresident ? 2 : 1) gemv_mma_kernel
           }
         }
       }
+      AMQB_DBG(if (L.dbg) {
+      // landing time of the first three fills (single-problem launches with <= NS stages: fills 0..2 are slots 0..2, phase 0)
+      if (it <= NS)                         // nothing was refilled: fill k is slot k, phase 0 (bounded polls: a debug aid must not hang)
+        for (int k = 0; k < 3 && k < it; ++k) {
+          uint32_t ok = 0;
+          for (int spin = 0; spin < 200000 && !ok; ++spin)
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(&bars[k])), "r"(0u) : "memory");
+          L.dbg[148 * 16 + blockIdx.x * 32 + 27 + k] = ok ? clock64() : 0;
+        }
+      })
     }
     return;
   }

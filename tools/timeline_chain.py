@@ -69,6 +69,11 @@ for i, (name, n, b) in enumerate(bufs):
     cnt = torch.bincount(smid[smid >= 0], minlength=148)
     endt = ent + (d[:, 3] - d[:, 0]).clamp(min=0) / 1965.0
     print(f"      SMs with 0/1/2+ CTAs of this launch: {(cnt == 0).sum().item()}/{(cnt == 1).sum().item()}/{(cnt >= 2).sum().item()} | reducer done(abs) {endt.min():7.2f} {endt.median():7.2f} {endt.max():7.2f}")
+    if os.environ.get("PRODUCER") == "1":
+        ent0 = d[:, 0]
+        iss = rbs[:, 24:30]
+        print("      producer: issue of stage 0..2, then landing of fill 0..2 (us since entry, median): " + " ".join(
+            f"{((iss[:, k][iss[:, k] > 0] - ent0[iss[:, k] > 0]) / 1965.0).median():5.2f}" if (iss[:, k] > 0).any() else "    -" for k in range(6)))
     if os.environ.get("ROWBLOCKS") == "1" and name in ("gu", "qkv"):
         ent0 = d[:, 0]
         line = []
