@@ -624,7 +624,8 @@ lm_head_mma_kernel(const __half* __restrict__ W, const __half* x, const __half* 
 
 // ------------------------------------------------------------------ argmax (lowest index among maxima)
 __global__ void __launch_bounds__(1024) argmax_kernel(const float* logits, int64_t* __restrict__ out, int V,
-                                                      int64_t* __restrict__ feed, int* __restrict__ pos) {
+                                                      int64_t* __restrict__ feed, int* __restrict__ pos,
+                                                      int64_t* __restrict__ log, int log_rows, int* __restrict__ log_pos) {
   pdl_launch_dependents();
   pdl_wait();
   const int m = blockIdx.x;
@@ -656,6 +657,11 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const float* logits, int64
     if (threadIdx.x == 0) {
       out[m] = bi;
       if (feed) feed[m] = bi;              // the generated id is the next step's input
+      if (log) {                           // token log [log_rows][M]; every sequence has its own row counter (no cross-block order needed)
+        const int r = log_pos[m];
+        if (r < log_rows) log[(size_t)r * gridDim.x + m] = bi;
+        log_pos[m] = r + 1;
+      }
       if (pos && m == 0) pos[0] += 1;      // nothing later in this step reads the position
     }
   }
@@ -795,13 +801,22 @@ int amqb_lm_head(const void* W_f16, const void* x, const void* gamma, float eps,
 int amqb_argmax(const float* logits, int64_t* out_ids, int M, int V, void* stream) {
   if (!logits || !out_ids || M < 1 || V < 1) return fail(AMQB_ERR_BAD_ARG, "argmax: bad argument");
   return launch(argmax_kernel, dim3(M), dim3(1024), 0, (cudaStream_t)stream, "argmax", logits, out_ids, V, (int64_t*)nullptr,
-                (int*)nullptr);
+                (int*)nullptr, (int64_t*)nullptr, 0, (int*)nullptr);
 }
 
 int amqb_argmax_advance(const float* logits, int64_t* out_ids, int64_t* next_input_ids, int* pos_dev, int M, int V,
                         void* stream) {
   if (!logits || !out_ids || M < 1 || V < 1) return fail(AMQB_ERR_BAD_ARG, "argmax_advance: bad argument");
-  return launch(argmax_kernel, dim3(M), dim3(1024), 0, (cudaStream_t)stream, "argmax", logits, out_ids, V, next_input_ids, pos_dev);
+  return launch(argmax_kernel, dim3(M), dim3(1024), 0, (cudaStream_t)stream, "argmax", logits, out_ids, V, next_input_ids, pos_dev,
+                (int64_t*)nullptr, 0, (int*)nullptr);
+}
+
+int amqb_argmax_advance_log(const float* logits, int64_t* out_ids, int64_t* next_input_ids, int* pos_dev, int64_t* token_log,
+                            int log_rows, int* log_pos, int M, int V, void* stream) {
+  if (!logits || !out_ids || M < 1 || V < 1 || (token_log && (!log_pos || log_rows < 1)))
+    return fail(AMQB_ERR_BAD_ARG, "argmax_advance_log: bad argument");
+  return launch(argmax_kernel, dim3(M), dim3(1024), 0, (cudaStream_t)stream, "argmax", logits, out_ids, V, next_input_ids, pos_dev,
+                token_log, log_rows, log_pos);
 }
 
 }  // extern "C"

@@ -104,6 +104,9 @@ class QuantDecoder:
         self.logits = torch.zeros(B, shape.vocab, device=self.dev, dtype=torch.float32)
         self.next_tokens = torch.zeros(B, dtype=torch.int64, device=self.dev)
         self.pos = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        # generated ids of every step since the last generate() / reset(): [steps][B], filled by the step's last launch
+        self.token_log = torch.zeros(max_seq, B, dtype=torch.int64, device=self.dev)
+        self.log_pos = torch.zeros(B, dtype=torch.int32, device=self.dev)
         self.rope = torch.empty(max_seq, self.D // 2, 2, dtype=torch.float32, device=self.dev)
         check(lib().amqb_rope_table(ptr(self.rope), max_seq, self.D, ctypes.c_float(shape.rope_theta), cur_stream()), "rope_table")
         self.ws = ops.workspace(self.dev, 4 * shape.inter, max(shape.inter, shape.hidden), batch)
@@ -279,7 +282,8 @@ class QuantDecoder:
         check(Lb.amqb_lm_head(ptr(self.lm_head), ptr(self.h), ptr(self.final_norm), ctypes.c_float(S.rms_eps),
                               ptr(self.logits), self.B, S.vocab, self.H, st), "lm_head")
         # greedy token, fed back as the next input, position advanced: all in the step's last launch
-        check(Lb.amqb_argmax_advance(ptr(self.logits), ptr(self.next_tokens), ptr(self.tokens), ptr(self.pos), self.B, S.vocab, st),
+        check(Lb.amqb_argmax_advance_log(ptr(self.logits), ptr(self.next_tokens), ptr(self.tokens), ptr(self.pos),
+                                         ptr(self.token_log), self.token_log.shape[0], ptr(self.log_pos), self.B, S.vocab, st),
               "argmax_advance")
         self.launches_per_step += 2
 
@@ -303,11 +307,12 @@ class QuantDecoder:
         s.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(s):
             if warm:
-                saved_pos, saved_tok = self.pos.clone(), self.tokens.clone()
+                saved_pos, saved_tok, saved_log = self.pos.clone(), self.tokens.clone(), self.log_pos.clone()
                 for _ in range(2):                  # warm-up outside capture (lazy module loads, attributes)
                     self._step_launches()
                 self.pos.copy_(saved_pos)           # the step advances position and input ids itself: undo the warm-up's
                 self.tokens.copy_(saved_tok)
+                self.log_pos.copy_(saved_log)
                 self.bump_generation()
             s.synchronize()
             g = torch.cuda.CUDAGraph()
@@ -370,6 +375,7 @@ class QuantDecoder:
 
     def reset(self) -> None:
         self.pos.zero_()
+        self.log_pos.zero_()
         self._pos_h = 0
         self.bump_generation()
 
@@ -472,7 +478,6 @@ class QuantDecoder:
         fn = self.step if use_graph else self.step_eager
         if use_graph and self.graph is None:
             self.capture()
-        out = torch.empty(self.B, max_new_tokens, dtype=torch.int64, device=self.dev)
         if prefill is None:
             prefill = self.tp_world == 1
         first = 0
@@ -481,12 +486,14 @@ class QuantDecoder:
             first = prompt - 1
         for t in range(first, prompt):
             self.tokens.copy_(ids[:, t])
+            if t == prompt - 1:
+                self.log_pos.zero_()                 # the step fed with the last prompt token logs generated id 0
             fn()
-        out[:, 0] = self.tokens
+        # the generated ids are logged on the device by each step's last launch (amqb_argmax_advance_log): the loop is
+        # graph replays back to back, with no per-token copy kernel between them
         for t in range(1, max_new_tokens):
             fn()
-            out[:, t] = self.tokens
-        return out
+        return self.token_log[:max_new_tokens].t().contiguous()
 
     # ---------------------------------------------------------------- accounting
     def algorithmic_bytes_per_token(self) -> Dict[str, int]:

@@ -221,6 +221,11 @@ int amqb_argmax(const float* logits, int64_t* out_ids, int M, int V, void* strea
  * (may be NULL) and *pos_dev (may be NULL) is incremented, so a captured step needs no extra copy / add nodes. */
 int amqb_argmax_advance(const float* logits, int64_t* out_ids, int64_t* next_input_ids, int* pos_dev,
                         int M, int V, void* stream);
+/* Same, and appends the generated ids to a device-side log: token_log[log_pos[m] * M + m] = id, log_pos[m] += 1 (rows
+ * >= log_rows are dropped).  A generation loop is then captured steps replayed back to back and ONE read of the log at
+ * its end (the reference's benchmark_tps times exactly that loop, amq/utils/speed.py:23-46); token_log may be NULL. */
+int amqb_argmax_advance_log(const float* logits, int64_t* out_ids, int64_t* next_input_ids, int* pos_dev, int64_t* token_log,
+                            int log_rows, int* log_pos, int M, int V, void* stream);
 
 /* ---- prompt-prefill glue (csrc/prefill_glue.cu) --------------------------
  * The row kernels between the tensor-core linears (amqb_gemm_tc) when a whole prompt is consumed at once, as the
