@@ -158,6 +158,42 @@ def test_gemv_model_shapes(ops, N, K, bits):
     assert torch.equal(y1, y2)
 
 
+@pytest.mark.parametrize("widths", [(2,), (3,), (4,), (2, 3), (2, 4), (3, 4), (2, 3, 4), (4, 2, 4), (3, 3, 2)])
+@pytest.mark.parametrize("pro", ["none", "rmsnorm"])
+def test_grouped_launch_every_bit_width_set(ops, widths, pro):
+    """Batch-1 grouped launches are served by a kernel instance per SET of bit widths present (one width, two widths, all
+    three): every set, with and without the RMSNorm prologue, against the fp32 statement of the same problems."""
+    from amq_b200 import _lib
+    dev = torch.device("cuda")
+    H, N = 1024, 512
+    torch.manual_seed(sum(widths))
+    x = torch.randn(1, H, device=dev).half()
+    gamma = (1.0 + 0.1 * torch.randn(H, device=dev)).half()
+    eps = 1e-5
+    xin = x.float()
+    if pro == "rmsnorm":
+        xin = (gamma.float() * (xin * torch.rsqrt(xin.pow(2).mean(-1, keepdim=True) + eps)).half().float())
+    y = torch.zeros(1, N * len(widths), device=dev, dtype=torch.float16)
+    ws = ops.workspace(dev, N * len(widths), H, 1)
+    probs, refs = [], []
+    for i, b in enumerate(widths):
+        codes, scale, zero = _synthetic(N, H, b, seed=100 + 7 * i + b)
+        cg, sg, zg = torch.from_numpy(codes).to(dev), scale.to(dev), zero.to(dev)
+        nat = ops.pack_native(b, cg, sg, zg)
+        W = (cg.float().reshape(N, H // G, G) * sg.float()[..., None] - (zg * sg).float()[..., None]).reshape(N, H)
+        refs.append(xin @ W.t())
+        p = ops.make_problem(b, nat, x, y, N, H, ldy=N * len(widths),
+                             prologue=_lib.PRO_RMSNORM if pro == "rmsnorm" else _lib.PRO_NONE,
+                             gamma=gamma if pro == "rmsnorm" else None, eps=eps)
+        p.y = y.data_ptr() + 2 * N * i
+        probs.append((p, nat))
+    ops.gemv_grouped([p for p, _ in probs], ws)
+    torch.cuda.synchronize()
+    ref = torch.cat(refs, dim=1)
+    tol = TOL if pro == "none" else 2e-3                      # the prologue rounds x * rs to fp16 before gamma (HF's RMSNorm)
+    assert O.max_rel(y.cpu(), ref.cpu()) <= tol, (widths, pro, O.max_rel(y.cpu(), ref.cpu()))
+
+
 @pytest.mark.parametrize("M", [1])
 def test_output_activation_and_mul_prologue(ops, M):
     """gate|up -> down as QuantDecoder launches it: `act = 1` on the gate problem stores silu(gate) and the down launch reads
