@@ -165,7 +165,7 @@ def test_grouped_launch_every_bit_width_set(ops, widths, pro):
     three): every set, with and without the RMSNorm prologue, against the fp32 statement of the same problems."""
     from amq_b200 import _lib
     dev = torch.device("cuda")
-    H, N = 1024, 512
+    H, N = 1024, 2560            # 80 row blocks: too many for a cluster K split, so these are the slim per-width-set instances
     torch.manual_seed(sum(widths))
     x = torch.randn(1, H, device=dev).half()
     gamma = (1.0 + 0.1 * torch.randn(H, device=dev)).half()
