@@ -2,7 +2,7 @@
 // (axis=1, group-wise, optimize=True) — /root/reference/amq/kernel/hqq/hqq/core/quantize.py:75-180
 // and the half-quadratic solver optimize_weights_proximal_legacy, core/optimize.py:96-108, 201-255.
 //
-// Three launches per layer (round 1: 42).  One warp owns one group (a row of the [R, G=128] view, 4 elements per
+// Three launches per layer (round 1: 42; the stop-rule kernel is twenty blocks, one per iteration).  One warp owns one group (a row of the [R, G=128] view, 4 elements per
 // lane) and runs ALL 20 solver iterations with the row in registers; the only thing that crosses groups is the
 // tensor-wide mean error that decides where the reference's loop stops (optimize.py:242-247), so every iteration's
 // zero-point is kept in a history [20][R] and every iteration's error as a per-block partial sum; a one-block kernel
@@ -26,6 +26,7 @@ struct HqqCtl { float best; int stop_iter; int iters; int pad; };
 
 constexpr int kRowsPerBlock = 8;
 constexpr int kHqqIters = 20;          // opt_params: lp_norm 0.7, beta 10, iters 20 (optimize.py:216)
+constexpr int kHqqHeader = 256;        // workspace header: HqqCtl | ticket (offset 32) | per-iteration errors (offset 64, 20 floats)
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -253,35 +254,41 @@ hqq_solve_kernel(const __half* __restrict__ W, float* __restrict__ scale, float*
   }
 }
 
-// Sum every iteration's partials in fixed order and replay the reference's stop rule (optimize.py:240-247).
+// Sum every iteration's partials in fixed order (one block per iteration; the order inside a block does not depend on the
+// grid) and replay the reference's stop rule (optimize.py:240-247) in the last block to finish (ticket left at zero).
 template <bool FP16>
-__global__ void __launch_bounds__(1024) hqq_pick_kernel(const float* __restrict__ partial, int nblocks, double numel, HqqCtl* ctl) {
+__global__ void __launch_bounds__(1024) hqq_pick_kernel(const float* __restrict__ partial, int nblocks, double numel, HqqCtl* ctl,
+                                                        float* __restrict__ errs, unsigned* __restrict__ ticket) {
   __shared__ double sh[1024];
-  __shared__ float errs[kHqqIters];
-  for (int it = 0; it < kHqqIters; ++it) {
-    double t = 0.0;
-    for (int i = threadIdx.x; i < nblocks; i += 1024) t += (double)partial[(long long)i * kHqqIters + it];
-    sh[threadIdx.x] = t;
-    __syncthreads();
-    for (int o = 512; o; o >>= 1) {
-      if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-      float e = (float)(sh[0] / numel);
-      if (FP16) e = rh(e);                       // torch.abs(..).mean() of an fp16 tensor is an fp16 value (then .float())
-      errs[it] = e;
-    }
+  __shared__ int s_last;
+  const int it = blockIdx.x;
+  double t = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += 1024) t += (double)partial[(long long)i * kHqqIters + it];
+  sh[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = 512; o; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    float best = INFINITY;
-    int last = kHqqIters - 1;
-    for (int it = 0; it < kHqqIters; ++it) {
-      if (errs[it] < best) best = errs[it];
-      else { last = it; break; }                 // the breaking iteration's zero update is kept
+    float e = (float)(sh[0] / numel);
+    if (FP16) e = rh(e);                         // torch.abs(..).mean() of an fp16 tensor is an fp16 value (then .float())
+    errs[it] = e;
+    __threadfence();
+    const unsigned tk = atomicAdd(ticket, 1u);
+    s_last = tk == (unsigned)kHqqIters - 1;
+    if (s_last) {
+      *ticket = 0u;
+      __threadfence();
+      float best = INFINITY;
+      int last = kHqqIters - 1;
+      for (int i = 0; i < kHqqIters; ++i) {
+        const float ei = *reinterpret_cast<volatile float*>(errs + i);
+        if (ei < best) best = ei;
+        else { last = i; break; }                // the breaking iteration's zero update is kept
+      }
+      ctl->best = best; ctl->stop_iter = last; ctl->iters = last + 1;
     }
-    ctl->best = best; ctl->stop_iter = last; ctl->iters = last + 1;
   }
 }
 
@@ -338,7 +345,7 @@ size_t amqb_hqq_quantize_workspace_bytes(int N, int K, int G) {
   if (N <= 0 || K <= 0 || G != 128) return 0;
   const long long R = (long long)N * K / G;
   const long long nblocks = (R + kRowsPerBlock - 1) / kRowsPerBlock;
-  return 64 + (size_t)nblocks * kHqqIters * sizeof(float) + (size_t)R * kHqqIters * sizeof(float);
+  return kHqqHeader + (size_t)nblocks * kHqqIters * sizeof(float) + (size_t)R * kHqqIters * sizeof(float);
 }
 
 static int hqq_quantize_impl(int bits, const void* W_f16, uint8_t* codes, void* Wq, float* scale, float* zero, int round_zero,
@@ -356,7 +363,10 @@ static int hqq_quantize_impl(int bits, const void* W_f16, uint8_t* codes, void* 
   const long long step = bits == 3 ? (R + 9) / 10 : R / p;
   const int nblocks = (int)((R + kRowsPerBlock - 1) / kRowsPerBlock);
   HqqCtl* ctl = reinterpret_cast<HqqCtl*>(workspace);
-  float* partial = reinterpret_cast<float*>((uint8_t*)workspace + 64);
+  float* partial = reinterpret_cast<float*>((uint8_t*)workspace + kHqqHeader);
+  unsigned* ticket = reinterpret_cast<unsigned*>((uint8_t*)workspace + 32);
+  float* errs = reinterpret_cast<float*>((uint8_t*)workspace + 64);
+  cudaMemsetAsync(ticket, 0, sizeof(unsigned), st);          // a caller's workspace is uninitialised memory
   float* zhist = partial + (size_t)nblocks * kHqqIters;
   const float maxv = (float)((1 << bits) - 1);
   const __half* W = (const __half*)W_f16;
@@ -364,11 +374,11 @@ static int hqq_quantize_impl(int bits, const void* W_f16, uint8_t* codes, void* 
   const int cblocks = (int)((crow + kRowsPerBlock - 1) / kRowsPerBlock);
   if (solver_fp16) {
     hqq_solve_kernel<true><<<nblocks, kRowsPerBlock * 32, 0, st>>>(W, scale, zhist, partial, R, maxv, round_zero);
-    hqq_pick_kernel<true><<<1, 1024, 0, st>>>(partial, nblocks, (double)N * (double)K, ctl);
+    hqq_pick_kernel<true><<<kHqqIters, 1024, 0, st>>>(partial, nblocks, (double)N * (double)K, ctl, errs, ticket);
     hqq_codes_kernel<true><<<cblocks, kRowsPerBlock * 32, 0, st>>>(W, scale, zero, zhist, ctl, codes, Wq, bits, R, step, maxv);
   } else {
     hqq_solve_kernel<false><<<nblocks, kRowsPerBlock * 32, 0, st>>>(W, scale, zhist, partial, R, maxv, round_zero);
-    hqq_pick_kernel<false><<<1, 1024, 0, st>>>(partial, nblocks, (double)N * (double)K, ctl);
+    hqq_pick_kernel<false><<<kHqqIters, 1024, 0, st>>>(partial, nblocks, (double)N * (double)K, ctl, errs, ticket);
     hqq_codes_kernel<false><<<cblocks, kRowsPerBlock * 32, 0, st>>>(W, scale, zero, zhist, ctl, codes, Wq, bits, R, step, maxv);
   }
   if (iters_run_out) cudaMemcpyAsync(iters_run_out, &ctl->iters, sizeof(int), cudaMemcpyDeviceToDevice, st);
