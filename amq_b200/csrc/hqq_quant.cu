@@ -196,6 +196,57 @@ hqq_solve_kernel(const __half* __restrict__ W, float* __restrict__ scale, float*
     init_scale_zero(w, maxv, round_zero, s, z);
     if (lane == 0) scale[row] = s;                       // fp32 scale as computed (the codes kernel inverts it)
     if (FP16) rh2(s, z);                                 // scale.to(fp16), zero.to(fp16)
+#ifndef AMQB_HQQ_F32PATH
+    if (FP16) {
+      // fp16 solver in PACKED fp16 arithmetic.  Every torch op of this mode is "fp32 op, one rounding to fp16" on fp16
+      // operands; for +, -, * that is exactly the IEEE fp16 operation (fp32 carries >= 2 * 11 + 2 significand bits, so the
+      // second rounding is innocuous), hence HADD2 / HMUL2 on element pairs (the _rn intrinsics: never contracted into an
+      // HFMA2, which would round once where torch rounds twice) give the same bits as the float + round sequence below at
+      // less than half the instructions.  What stays in fp32: the pow (MUFU), the product with the
+      // fp32 scalar 1 / beta, the group mean and the error sum (torch accumulates those in fp32).
+      const __half2 w01 = __floats2half2_rn(w[0], w[1]), w23 = __floats2half2_rn(w[2], w[3]);     // exact: W is fp16
+      const __half2 s2 = __float2half2_rn(s), maxv2 = __float2half2_rn(maxv), zero2 = __float2half2_rn(0.f);
+      for (int it = 0; it < kHqqIters; ++it) {
+        float tnum = __fsub_rn((float)lane, z), tdum = 0.f;
+        rh2(tnum, tdum);
+        float tab = __fdiv_rn(tnum, s);
+        rh2(tab, tdum);
+        const uint32_t tabh = __half_as_ushort(__float2half_rn(tab));          // exact: already an fp16 value
+        const __half2 z2 = __float2half2_rn(z);
+        float tsum = 0.f, err = 0.f;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const __half2 wv = i ? w23 : w01;
+          __half2 q = __hadd2_rn(__hmul2_rn(wv, s2), z2);
+          q = __hmax2(__hmin2(h2rint(q), maxv2), zero2);
+          const uint32_t r0 = __shfl_sync(0xffffffffu, tabh, __half2int_rn(__low2half(q)));
+          const uint32_t r1 = __shfl_sync(0xffffffffu, tabh, __half2int_rn(__high2half(q)));
+          const uint32_t wrb = r0 | (r1 << 16);
+          const __half2 e = __hsub2_rn(wv, *reinterpret_cast<const __half2*>(&wrb));
+          const __half2 a = __habs2(e);
+          const float2 af = __half22float2(a);
+          float p0 = exp2f(__fmul_rn(pm1, log2f(af.x))), p1 = exp2f(__fmul_rn(pm1, log2f(af.y)));
+          rh2(p0, p1);
+          const __half2 c = __floats2half2_rn(__fmul_rn(inv_beta, p0), __fmul_rn(inv_beta, p1));
+          const __half2 m = __hmax2(__hsub2_rn(a, c), zero2);
+          // sign(e) * m: m >= 0, so OR-ing e's sign bit in is the select (e == 0 gives m == 0: |e|^(p-1) is inf there)
+          const uint32_t web = *reinterpret_cast<const uint32_t*>(&m) | (*reinterpret_cast<const uint32_t*>(&e) & 0x80008000u);
+          const __half2 d = __hmul2_rn(__hsub2_rn(wv, *reinterpret_cast<const __half2*>(&web)), s2);
+          const float2 tf = __half22float2(__hsub2_rn(q, d));
+          tsum += (tf.x + tf.y) * 1.f;                    // (t0 + t1), then + (t2 + t3): the order of the float path
+          err += af.x; err += af.y;
+        }
+        float zn = __fmul_rn(warp_sum(tsum), 1.0f / 128.0f), zd = 0.f;
+        rh2(zn, zd);
+        z = zn;
+        err = warp_sum(err);
+        if (lane == 0) {
+          zhist[(long long)it * R + row] = z;
+          s_err[wid][it] = err;
+        }
+      }
+    } else
+#endif
     for (int it = 0; it < kHqqIters; ++it) {
       // W_r takes at most maxv + 1 values per group: lane q holds (q - zero) / scale, elements fetch theirs by shuffle
       float tnum = __fsub_rn((float)lane, z), tdum = 0.f;
