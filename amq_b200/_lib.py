@@ -35,6 +35,12 @@ class GemvProblem(ctypes.Structure):
     ]
 
 
+class GemmProblem(ctypes.Structure):
+    """amqb_gemm_problem (include/amqb.h)."""
+    _fields_ = [("bits", ctypes.c_int), ("N", ctypes.c_int), ("w_native", ctypes.c_void_p), ("y", ctypes.c_void_p),
+                ("bias", ctypes.c_void_p)]
+
+
 def lib() -> ctypes.CDLL:
     global _lib
     if _lib is None:

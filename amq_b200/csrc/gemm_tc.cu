@@ -239,12 +239,22 @@ __device__ __forceinline__ void dequant_tile(const uint8_t* rec, int tile, uint3
   tmem_wait_st();
 }
 
-struct TcArgs {
+// Up to kTcMaxProblems linears that share the activations (q|k|v, gate|up) run as ONE launch: their n tiles are
+// concatenated along blockIdx.x, the activations are pre-swizzled once, and the small members (k / v projections: 8 n
+// tiles each) fill SMs the large one leaves idle instead of paying a launch of their own.
+constexpr int kTcMaxProblems = 3;
+struct TcProblem {
   const uint8_t* w;        // native layout
-  const uint8_t* xs;       // pre-swizzled activations
-  __half* y;
+  __half* y;               // [M, N]
   const __half* bias;
-  int bits, M, N, K;
+  int bits, N;
+  int tile0;               // first global n tile of this problem
+};
+struct TcArgs {
+  TcProblem prob[kTcMaxProblems];
+  int count;
+  const uint8_t* xs;       // pre-swizzled activations
+  int M, K;
   int nws;                 // W ring depth
   int splits;              // K split over gridDim.z (few output tiles: short prompts, k / v projections); 1 = none
   float* part;             // splits > 1: fp32 partial tiles [CTA][128 m][128 n]
@@ -262,12 +272,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 512);
   uint8_t* x_ring = smem + kTcHeader;
   uint8_t* w_ring = x_ring + kXStages * kXBytes;
-  const int rbytes = rec_bytes(A.bits);
-  const int w_stage = 4 * rbytes;
+  // this CTA's problem (the launch's n tiles are the problems' tiles back to back)
+  int pi = 0;
+#pragma unroll
+  for (int i = 1; i < kTcMaxProblems; ++i)
+    if (i < A.count && (int)blockIdx.x >= A.prob[i].tile0) pi = i;
+  const TcProblem P = A.prob[pi];
+  const int rbytes = rec_bytes(P.bits);
+  const int w_stage = 4 * rec_bytes(4);                        // ring slots sized for the largest record (host: nws)
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform for the compiler
-  const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+  const int n_tile = (int)blockIdx.x - P.tile0, m_tile = blockIdx.y;
   long long (*trace)[40] = reinterpret_cast<long long (*)[40]>(smem + 1024);   // AMQB_TC_DBG & 16: clock64 of [role][kb]
   auto tr = [&](int role, int kb) { if ((A.dbg & 16) && kb < 40) trace[role][kb] = clock64(); };
   unsigned long long* stamps = reinterpret_cast<unsigned long long*>(smem + 640);   // AMQB_TC_DBG & 8: timeline of CTA (0,0)
@@ -303,7 +319,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         mbar_expect_tx(smem_u32(&bars[kBarWFull + ws]), 4 * rbytes);
         for (int r = 0; r < 4; ++r)
           bulk_g2s(smem_u32(w_ring + (size_t)ws * w_stage + (size_t)r * rbytes),
-                   A.w + ((size_t)(n_tile * 4 + r) * NGA + kb0 + kb) * rbytes, rbytes, smem_u32(&bars[kBarWFull + ws]));
+                   P.w + ((size_t)(n_tile * 4 + r) * NGA + kb0 + kb) * rbytes, rbytes, smem_u32(&bars[kBarWFull + ws]));
         if (++ws == A.nws) { ws = 0; ph ^= 1; }
       }
     }
@@ -386,8 +402,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
       const uint8_t* rec = w_ring + (size_t)ws * w_stage + (size_t)q * rbytes;
       const uint32_t taddr = lane_base + st * kTmemAStage;
       if (A.dbg & 1) {}
-      else if (A.bits == 3) dequant_tile<3>(rec, tile, taddr, lane);
-      else if (A.bits == 4) dequant_tile<4>(rec, tile, taddr, lane);
+      else if (P.bits == 3) dequant_tile<3>(rec, tile, taddr, lane);
+      else if (P.bits == 4) dequant_tile<4>(rec, tile, taddr, lane);
       else dequant_tile<2>(rec, tile, taddr, lane);
       tc_fence_before();
       __syncwarp();
@@ -407,7 +423,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     if (tid == 128) stamp(7);
     const int cq = (warp - 4) >> 2;                 // columns [32 cq, 32 cq + 32)
     const int n = n_tile * kTileN + q * 32 + lane;
-    const float bv = A.bias ? __half2float(A.bias[n]) : 0.f;
+    const float bv = P.bias ? __half2float(P.bias[n]) : 0.f;
     {
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 32), r);
@@ -415,11 +431,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
           const int m = m_tile * kTileM + cq * 32 + c;
-          if (m < A.M) A.y[(size_t)m * A.N + n] = __float2half_rn(__uint_as_float(r[c]) + bv);
+          if (m < A.M) P.y[(size_t)m * P.N + n] = __float2half_rn(__uint_as_float(r[c]) + bv);
         }
       } else {
         // K split: fp32 partial tile of this CTA, [m][n] so that a warp's store is one 128-byte line
-        float* pt = A.part + (((size_t)blockIdx.z * gridDim.y + m_tile) * gridDim.x + n_tile) * (kTileM * kTileN);
+        float* pt = A.part + (((size_t)blockIdx.z * gridDim.y + m_tile) * gridDim.x + blockIdx.x) * (kTileM * kTileN);
 #pragma unroll
         for (int c = 0; c < 32; ++c) __stcg(pt + (cq * 32 + c) * kTileN + q * 32 + lane, __uint_as_float(r[c]));
       }
@@ -434,7 +450,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     __threadfence();
     __syncthreads();
     if (tid == 0) {
-      int* tk = A.tickets + m_tile * gridDim.x + n_tile;
+      int* tk = A.tickets + m_tile * gridDim.x + blockIdx.x;
       const int t = atomicAdd(tk, 1);
       s_last = (t == A.splits - 1);
       if (s_last) *tk = 0;
@@ -443,7 +459,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     if (s_last) {
       __threadfence();
       const size_t zstride = (size_t)gridDim.y * gridDim.x * (kTileM * kTileN);
-      const float* p0 = A.part + ((size_t)m_tile * gridDim.x + n_tile) * (kTileM * kTileN);
+      const float* p0 = A.part + ((size_t)m_tile * gridDim.x + blockIdx.x) * (kTileM * kTileN);
       for (int e = tid; e < kTileM * kTileN; e += kTcThreads) {
         const int ml = e >> 7, nl = e & 127;
         const int m = m_tile * kTileM + ml;
@@ -451,8 +467,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         float v = 0.f;
         for (int z = 0; z < A.splits; ++z) v += __ldcg(p0 + (size_t)z * zstride + e);
         const int nn = n_tile * kTileN + nl;
-        if (A.bias) v += __half2float(A.bias[nn]);
-        A.y[(size_t)m * A.N + nn] = __float2half_rn(v);
+        if (P.bias) v += __half2float(P.bias[nn]);
+        P.y[(size_t)m * P.N + nn] = __float2half_rn(v);
       }
     }
   }
@@ -494,36 +510,24 @@ size_t amqb_gemm_workspace_bytes(int M, int K, int bits) {
   return swz > dec ? swz : dec;
 }
 
-int amqb_gemm_tc(int bits, const void* w_native, const void* x, void* y, const void* bias, int M, int N, int K,
-                 void* workspace, size_t workspace_bytes, void* stream) {
-  if (!w_native || !x || !y || M < 1) return fail(AMQB_ERR_BAD_ARG, "gemm_tc: bad argument");
-  if (!(bits == 2 || bits == 3 || bits == 4)) return fail(AMQB_ERR_BAD_ARG, "gemm_tc: bits must be 2, 3 or 4");
-  if (N <= 0 || K <= 0 || N % 32 || K % kGroup) return fail(AMQB_ERR_UNSUPPORTED_SHAPE, "gemm_tc: needs N % 32 == 0 and K % 128 == 0");
-  cudaStream_t st = (cudaStream_t)stream;
-  const bool tc_ok = (N % kTileN == 0) && workspace && workspace_bytes >= amqb_gemm_workspace_bytes(M, K, bits) &&
-                     (((uintptr_t)workspace & 255) == 0) && (((uintptr_t)x & 15) == 0) && getenv("AMQB_NO_TCGEN05") == nullptr;
-  if (!tc_ok) {
-    // 16-row slabs through the HMMA decode kernel (exact, but the weights stream once per slab)
-    const __half* xp = (const __half*)x;
-    __half* yp = (__half*)y;
-    for (int m0 = 0; m0 < M; m0 += 16) {
-      const int mm = (M - m0) < 16 ? (M - m0) : 16;
-      amqb_gemv_problem p{};
-      p.bits = bits; p.M = mm; p.N = N; p.K = K; p.w_native = w_native;
-      p.x = xp + (size_t)m0 * K; p.ldx = K; p.y = yp + (size_t)m0 * N; p.ldy = N; p.bias = bias;
-      p.prologue = AMQB_PRO_NONE;
-      const int rc = amqb_gemv_grouped(&p, 1, workspace, workspace_bytes, 0, stream);
-      if (rc) return rc;
-    }
-    return AMQB_OK;
-  }
+// One launch over `count` problems sharing x (tcgen05 path; every N % 128 == 0).
+static int gemm_tc_launch(const amqb_gemm_problem* pr, int count, const void* x, int M, int K, void* workspace,
+                          size_t workspace_bytes, cudaStream_t st) {
+  (void)workspace_bytes;
   const int m_tiles = (M + kTileM - 1) / kTileM;
   const long long chunks = (long long)m_tiles * 128 * (K / 8);
-  const int n_tiles = N / kTileN;
+  TcArgs A{};
+  int n_tiles = 0;
+  for (int i = 0; i < count; ++i) {
+    A.prob[i].w = (const uint8_t*)pr[i].w_native; A.prob[i].y = (__half*)pr[i].y; A.prob[i].bias = (const __half*)pr[i].bias;
+    A.prob[i].bits = pr[i].bits; A.prob[i].N = pr[i].N; A.prob[i].tile0 = n_tiles;
+    n_tiles += pr[i].N / kTileN;
+  }
+  A.count = count;
   // K split when the output tiles leave most of the chip idle (a 63-row prompt is 32 tiles at N = 4096; k / v projections
   // of a GQA model 8 per m tile): as many splits as fit one CTA per SM, at least 4 k blocks each
   // Measured (profiles/r02_prefill_splitk.txt, 3-bit, M = 63): a call has ~20 us of fixed cost (pre-swizzle pass, TMEM /
-  // barrier set-up, ring fill, epilogue) around a k loop of 0.27 us per block, and the split adds ~8 us (counter reset,
+  // barrier set-up, ring fill, epilogue) around a k loop of 0.43 us per block, and the split adds ~8 us (counter reset,
   // partial tiles, the last CTA's reduction): it pays for long rows only - 4096 x 11008: 44.4 -> 31.0 us, but
   // 4096 x 4096: 20.8 -> 24.6 us.  Hence K >= 8192.
   int splits = 1;
@@ -554,11 +558,9 @@ int amqb_gemm_tc(int bits, const void* w_native, const void* x, void* y, const v
       return AMQB_ERR_LAUNCH;
     }
   }
-  TcArgs A{};
-  A.w = (const uint8_t*)w_native; A.xs = (const uint8_t*)workspace; A.y = (__half*)y; A.bias = (const __half*)bias;
-  A.bits = bits; A.M = M; A.N = N; A.K = K;
+  A.xs = (const uint8_t*)workspace; A.M = M; A.K = K;
   { const char* e = getenv("AMQB_TC_DBG"); A.dbg = e ? atoi(e) : 0; }
-  const size_t w_stage = 4 * (size_t)rec_bytes(bits);
+  const size_t w_stage = 4 * (size_t)rec_bytes(4);          // ring slots hold the largest record whatever the problem's width
   size_t nws = (kTcSmemMax - kTcHeader - (size_t)kXStages * kXBytes) / w_stage;
   if (nws > (size_t)kWStagesMax) nws = kWStagesMax;
   A.nws = (int)nws;
@@ -573,7 +575,7 @@ int amqb_gemm_tc(int bits, const void* w_native, const void* x, void* y, const v
   A.tickets = tickets;
   // cluster pair + X multicast halves the activations' L2 traffic but measured ~5% slower (the X ring is bound by the
   // bulk-copy round trip, not by L2 bandwidth): opt-in, kept as the base for a cta_group::2 version
-  const bool pair = (n_tiles % 2 == 0) && splits == 1 && getenv("AMQB_TC_CLUSTER") != nullptr;
+  const bool pair = count == 1 && (n_tiles % 2 == 0) && splits == 1 && getenv("AMQB_TC_CLUSTER") != nullptr;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(n_tiles, m_tiles, splits);
   cfg.blockDim = dim3(kTcThreads);
@@ -592,6 +594,58 @@ int amqb_gemm_tc(int bits, const void* w_native, const void* x, void* y, const v
     return AMQB_ERR_LAUNCH;
   }
   return check_launch("gemm_tc");
+}
+
+static bool tc_usable(int N, int M, int K, int bits, const void* x, void* workspace, size_t workspace_bytes) {
+  return (N % kTileN == 0) && workspace && workspace_bytes >= amqb_gemm_workspace_bytes(M, K, bits) &&
+         (((uintptr_t)workspace & 255) == 0) && (((uintptr_t)x & 15) == 0) && getenv("AMQB_NO_TCGEN05") == nullptr;
+}
+
+int amqb_gemm_tc(int bits, const void* w_native, const void* x, void* y, const void* bias, int M, int N, int K,
+                 void* workspace, size_t workspace_bytes, void* stream) {
+  if (!w_native || !x || !y || M < 1) return fail(AMQB_ERR_BAD_ARG, "gemm_tc: bad argument");
+  if (!(bits == 2 || bits == 3 || bits == 4)) return fail(AMQB_ERR_BAD_ARG, "gemm_tc: bits must be 2, 3 or 4");
+  if (N <= 0 || K <= 0 || N % 32 || K % kGroup) return fail(AMQB_ERR_UNSUPPORTED_SHAPE, "gemm_tc: needs N % 32 == 0 and K % 128 == 0");
+  if (!tc_usable(N, M, K, bits, x, workspace, workspace_bytes)) {
+    // 16-row slabs through the HMMA decode kernel (exact, but the weights stream once per slab)
+    const __half* xp = (const __half*)x;
+    __half* yp = (__half*)y;
+    for (int m0 = 0; m0 < M; m0 += 16) {
+      const int mm = (M - m0) < 16 ? (M - m0) : 16;
+      amqb_gemv_problem p{};
+      p.bits = bits; p.M = mm; p.N = N; p.K = K; p.w_native = w_native;
+      p.x = xp + (size_t)m0 * K; p.ldx = K; p.y = yp + (size_t)m0 * N; p.ldy = N; p.bias = bias;
+      p.prologue = AMQB_PRO_NONE;
+      const int rc = amqb_gemv_grouped(&p, 1, workspace, workspace_bytes, 0, stream);
+      if (rc) return rc;
+    }
+    return AMQB_OK;
+  }
+  amqb_gemm_problem p{};
+  p.bits = bits; p.N = N; p.w_native = w_native; p.y = y; p.bias = bias;
+  return gemm_tc_launch(&p, 1, x, M, K, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int amqb_gemm_tc_grouped(const amqb_gemm_problem* problems, int count, const void* x, int M, int K, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  if (!problems || count < 1 || count > kTcMaxProblems || !x || M < 1 || K <= 0 || K % kGroup)
+    return fail(AMQB_ERR_BAD_ARG, "gemm_tc_grouped: bad argument (1..3 problems, K % 128 == 0)");
+  bool all_tc = true;
+  for (int i = 0; i < count; ++i) {
+    const amqb_gemm_problem& q = problems[i];
+    if (!(q.bits == 2 || q.bits == 3 || q.bits == 4) || !q.w_native || !q.y || q.N <= 0 || q.N % 32)
+      return fail(AMQB_ERR_BAD_ARG, "gemm_tc_grouped: bad problem");
+    all_tc = all_tc && tc_usable(q.N, M, K, q.bits, x, workspace, workspace_bytes);
+  }
+  if (!all_tc) {                                           // a member the tcgen05 kernel does not take: one by one
+    for (int i = 0; i < count; ++i) {
+      const int rc = amqb_gemm_tc(problems[i].bits, problems[i].w_native, x, problems[i].y, problems[i].bias, M, problems[i].N, K,
+                                  workspace, workspace_bytes, stream);
+      if (rc) return rc;
+    }
+    return AMQB_OK;
+  }
+  return gemm_tc_launch(problems, count, x, M, K, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -447,9 +447,10 @@ class QuantDecoder:
             bq = bk = bv = None
             if bias is not None:
                 bq, bk, bv = bias[: self.q_dim], bias[self.q_dim: self.q_dim + self.kv_dim], bias[self.q_dim + self.kv_dim:]
-            q = linear(L, "self_attn.q_proj", x, bq)
-            k = linear(L, "self_attn.k_proj", x, bk)
-            v = linear(L, "self_attn.v_proj", x, bv)
+            # q|k|v (and gate|up below) share their activations: one grouped launch each
+            q, k, v = ops.linear_forward_grouped(
+                [(L[n][0], L[n][1], L[n][2], b_) for n, b_ in (("self_attn.q_proj", bq), ("self_attn.k_proj", bk), ("self_attn.v_proj", bv))],
+                x, H)
             check(Lb.amqb_attn_prefill(ptr(q), ptr(k), ptr(v), ptr(L["k_cache"]), ptr(L["v_cache"]), ptr(attn), pos0, T, B,
                                        self.Hq, self.Hkv, self.D, self.max_seq, ptr(self.rope), st), "attn_prefill")
             if li == len(self.layers) - 1:
@@ -457,8 +458,7 @@ class QuantDecoder:
             o = linear(L, "self_attn.o_proj", attn)
             check(Lb.amqb_add_rows(ptr(h), ptr(o), M, H, st), "add_rows")
             check(Lb.amqb_rmsnorm_rows(ptr(h), ptr(L["norm2"]), ctypes.c_float(S.rms_eps), ptr(x), M, H, st), "rmsnorm_rows")
-            g = linear(L, "mlp.gate_proj", x)
-            u = linear(L, "mlp.up_proj", x)
+            g, u = ops.linear_forward_grouped([(L[n][0], L[n][1], L[n][2], None) for n in ("mlp.gate_proj", "mlp.up_proj")], x, H)
             check(Lb.amqb_silu_mul_rows(ptr(g), ptr(u), ptr(act), M, self.I_loc, st), "silu_mul_rows")
             d = linear(L, "mlp.down_proj", act)
             check(Lb.amqb_add_rows(ptr(h), ptr(d), M, H, st), "add_rows")

@@ -224,6 +224,35 @@ def gemm_tc(bits: int, w_native: torch.Tensor, x: torch.Tensor, N: int, K: int,
     return y
 
 
+@_on_device
+def linear_forward_grouped(members, x: torch.Tensor, K: int, workspace: Optional[torch.Tensor] = None):
+    """Several linears over the same activations x [M, K] (q|k|v, gate|up): members = [(bits, w_native, N, bias or None)].
+    More than 16 rows: ONE tcgen05 launch (amqb_gemm_tc_grouped); up to 16: the decode kernel's grouped launch.  Returns
+    the list of outputs [M, N_i]."""
+    from ._lib import GemmProblem
+    x = x.contiguous()
+    M = x.shape[0]
+    outs = [torch.empty((M, N), dtype=torch.float16, device=x.device) for (_, _, N, _) in members]
+    if M <= 16:
+        ws = workspace if workspace is not None else globals()["workspace"](x.device, sum(m[2] for m in members), K, M)
+        probs = [make_problem(b, w, x, y, N, K, bias=bias) for (b, w, N, bias), y in zip(members, outs)]
+        gemv_grouped(probs, ws)
+        return outs
+    bits_max = max(m[0] for m in members)
+    wsb = workspace if workspace is not None else gemm_workspace(M, K, bits_max, x.device)
+    arr = (GemmProblem * len(members))()
+    keep = []
+    for i, ((b, w, N, bias), y) in enumerate(zip(members, outs)):
+        _req_cuda(w)
+        arr[i].bits, arr[i].N = b, N
+        arr[i].w_native, arr[i].y = w.data_ptr(), y.data_ptr()
+        arr[i].bias = bias.data_ptr() if bias is not None else None
+        keep.append((w, bias))
+    check(lib().amqb_gemm_tc_grouped(arr, len(members), ptr(x), M, K, ptr(wsb), ctypes.c_size_t(wsb.numel()), cur_stream()),
+          "gemm_tc_grouped")
+    return outs
+
+
 # ------------------------------------------------------------------ HQQ proxy ops
 @_on_device
 def hqq_dequant(bits: int, W_q: torch.Tensor, scale: torch.Tensor, zero: torch.Tensor, N: int, K: int,

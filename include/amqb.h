@@ -162,6 +162,17 @@ int amqb_gemv_gptq_layout(int bits, const int32_t* qweight, const float* scales,
 /* ---- prefill: dequant-fused tensor-core GEMM (tcgen05 / TMEM), M >= 17 -- */
 /* workspace: amqb_gemm_workspace_bytes(M, K) bytes (permuted copy of x). */
 size_t amqb_gemm_workspace_bytes(int M, int K, int bits);
+/* Several linears over the SAME activations (q|k|v, gate|up) as one launch: their output tiles share the grid, x is
+ * permuted once.  Replaces the three / two back-to-back module forwards of the reference's prompt pass. */
+typedef struct {
+  int bits;                 /* 2, 3 or 4 */
+  int N;                    /* out features */
+  const void* w_native;
+  void* y;                  /* fp16 [M, N] */
+  const void* bias;         /* fp16 [N] or NULL */
+} amqb_gemm_problem;
+int amqb_gemm_tc_grouped(const amqb_gemm_problem* problems_host, int count, const void* x, int M, int K, void* workspace,
+                         size_t workspace_bytes, void* stream);
 int amqb_gemm_tc(int bits, const void* w_native, const void* x, void* y, const void* bias,
                  int M, int N, int K, void* workspace, size_t workspace_bytes, void* stream);
 

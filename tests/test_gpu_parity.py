@@ -315,6 +315,27 @@ def test_prefill_gemm(ops, N, K, M, bits):
     assert O.max_rel(y16.cpu(), ref[:16].cpu()) <= TOL
 
 
+@pytest.mark.parametrize("M", [40, 300])
+def test_prefill_gemm_grouped_matches_single_calls(ops, M):
+    """q|k|v-style grouped tcgen05 launch (three problems of different width and size over the same activations, with and
+    without bias) against the same problems through amqb_gemm_tc one by one: bit-identical (same tiles, same arithmetic)."""
+    dev = torch.device("cuda")
+    K = 1024
+    torch.manual_seed(M)
+    x = torch.randn(M, K, device=dev).half()
+    members, singles = [], []
+    for i, (bits, N) in enumerate(((3, 512), (2, 128), (4, 256))):
+        codes, scale, zero = _synthetic(N, K, bits, seed=40 + i)
+        nat = ops.pack_native(bits, torch.from_numpy(codes).to(dev), scale.to(dev), zero.to(dev))
+        bias = torch.randn(N, device=dev).half() if i != 1 else None
+        members.append((bits, nat, N, bias))
+        singles.append(ops.gemm_tc(bits, nat, x, N, K, bias))
+    outs = ops.linear_forward_grouped(members, x, K)
+    torch.cuda.synchronize()
+    for y, ref in zip(outs, singles):
+        assert torch.equal(y, ref)
+
+
 def test_prefill_gemm_k_split_is_deterministic(ops, monkeypatch):
     """Long rows with few output tiles run K-split over gridDim.z (K >= 8192): the last CTA of a tile adds the partial tiles
     in split order, so reruns are bit-identical, the tile counters are left at zero (third run), and the result sits
