@@ -59,6 +59,38 @@ for name, (N, K) in shape.linear_shape.items():
 c3["prefill512_linears"] = {"ms_all_224_linears": tot_ms, "tflops": tot_flop / tot_ms / 1e9, "frac_of_bf16_peak": tot_flop / tot_ms / 1e9 / PEAK_TF,
                             "tokens_per_s_linears_only": M * 1e3 / tot_ms, "per_shape": per_shape}
 print("config3 prefill", {k: v for k, v in c3["prefill512_linears"].items() if k != "per_shape"}, flush=True)
+# the same 224 linears as the prompt pass launches them: q|k|v and gate|up grouped (one launch each), o_proj and down_proj
+# single, layer by layer with the model's own bit widths, captured in one CUDA graph
+nat = {}
+def weight(name, bits):
+    if (name, bits) not in nat:
+        N, K = shape.linear_shape[name]
+        nat[(name, bits)] = synthetic_native(bits, N, K, dev, gen)
+    return nat[(name, bits)]
+H, I = shape.hidden, shape.inter
+xh = torch.randn(M, H, device=dev).half(); xa = torch.randn(M, shape.n_heads * shape.head_dim, device=dev).half(); xi = torch.randn(M, I, device=dev).half()
+def layer(li):
+    b = {n: int(arch[n][li % len(arch[n])]) for n in LINEARS}
+    ops.linear_forward_grouped([(b[n], weight(n, b[n]), shape.linear_shape[n][0], None) for n in ("self_attn.q_proj", "self_attn.k_proj", "self_attn.v_proj")], xh, H)
+    n = "self_attn.o_proj"; ops.gemm_tc(b[n], weight(n, b[n]), xa, *shape.linear_shape[n])
+    ops.linear_forward_grouped([(b[n], weight(n, b[n]), shape.linear_shape[n][0], None) for n in ("mlp.gate_proj", "mlp.up_proj")], xh, H)
+    n = "mlp.down_proj"; ops.gemm_tc(b[n], weight(n, b[n]), xi, *shape.linear_shape[n])
+for li in range(shape.n_block): layer(li)
+torch.cuda.synchronize()
+st_ = torch.cuda.Stream()
+with torch.cuda.stream(st_):
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr, stream=st_):
+        for li in range(shape.n_block): layer(li)
+    gr.replay(); st_.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st_)
+    for _ in range(5): gr.replay()
+    e1.record(st_); st_.synchronize()
+gms = e0.elapsed_time(e1) / 5
+c3["prefill512_grouped"] = {"ms_all_224_linears": gms, "tflops": tot_flop / gms / 1e9, "frac_of_bf16_peak": tot_flop / gms / 1e9 / PEAK_TF,
+                            "how": "q|k|v and gate|up as grouped launches, model order, one CUDA graph"}
+print("config3 prefill grouped", c3["prefill512_grouped"], flush=True)
 out["config3_mistral7b_2.5bit"] = c3
 
 # ---- config 4: Qwen2-7B proxy sweep: quantize -> pack -> dequantize for every linear shape at 2/3/4 bits
