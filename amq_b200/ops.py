@@ -225,7 +225,7 @@ def gemm_tc(bits: int, w_native: torch.Tensor, x: torch.Tensor, N: int, K: int,
 
 
 @_on_device
-def linear_forward_grouped(members, x: torch.Tensor, K: int, workspace: Optional[torch.Tensor] = None):
+def linear_forward_grouped(members, x: torch.Tensor, K: int, ws: Optional[torch.Tensor] = None):
     """Several linears over the same activations x [M, K] (q|k|v, gate|up): members = [(bits, w_native, N, bias or None)].
     More than 16 rows: ONE tcgen05 launch (amqb_gemm_tc_grouped); up to 16: the decode kernel's grouped launch.  Returns
     the list of outputs [M, N_i]."""
@@ -234,12 +234,12 @@ def linear_forward_grouped(members, x: torch.Tensor, K: int, workspace: Optional
     M = x.shape[0]
     outs = [torch.empty((M, N), dtype=torch.float16, device=x.device) for (_, _, N, _) in members]
     if M <= 16:
-        ws = workspace if workspace is not None else globals()["workspace"](x.device, sum(m[2] for m in members), K, M)
+        wsd = ws if ws is not None else workspace(x.device, sum(m[2] for m in members), K, M)
         probs = [make_problem(b, w, x, y, N, K, bias=bias) for (b, w, N, bias), y in zip(members, outs)]
-        gemv_grouped(probs, ws)
+        gemv_grouped(probs, wsd)
         return outs
     bits_max = max(m[0] for m in members)
-    wsb = workspace if workspace is not None else gemm_workspace(M, K, bits_max, x.device)
+    wsb = ws if ws is not None else gemm_workspace(M, K, bits_max, x.device)
     arr = (GemmProblem * len(members))()
     keep = []
     for i, ((b, w, N, bias), y) in enumerate(zip(members, outs)):
