@@ -51,7 +51,7 @@ def lib() -> ctypes.CDLL:
         L = ctypes.CDLL(LIB_PATH)
         L.amqb_last_error_string.restype = ctypes.c_char_p
         for name in ("amqb_native_bytes", "amqb_workspace_bytes", "amqb_gemm_workspace_bytes",
-                     "amqb_hqq_quantize_workspace_bytes", "amqb_ar_buffer_bytes",
+                     "amqb_hqq_quantize_workspace_bytes", "amqb_ar_buffer_bytes", "amqb_ar_rows_buffer_bytes",
                      "amqb_attn_split_workspace_bytes"):
             if hasattr(L, name):
                 getattr(L, name).restype = ctypes.c_size_t

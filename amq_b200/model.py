@@ -113,7 +113,7 @@ class QuantDecoder:
         # long contexts: the cached positions of a head are shared by several CTAs (amqb_attn_decode_split) when one CTA
         # per (head, sequence) would leave most of the chip idle; below ATTN_SPLIT_MIN_POS it is the single-CTA kernel
         sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
-        self.attn_splits = max(1, min(4, sms // max(1, self.Hq * batch))) if tp_world == 1 else 1   # TP: validated path only
+        self.attn_splits = max(1, min(4, sms // max(1, self.Hq * batch)))      # per rank: Hq is this rank's share of the heads
         self.attn_split_min_pos = int(os.environ.get("AMQB_ATTN_SPLIT_MIN_POS", "256"))
         self.attn_ws = torch.zeros(max(256, int(lib().amqb_attn_split_workspace_bytes(batch, self.Hq, self.D, self.attn_splits))),
                                    dtype=torch.uint8, device=self.dev)
@@ -390,12 +390,15 @@ class QuantDecoder:
         the LAST prompt token through step() to obtain the first logits.  What HF generate() does with the prompt in
         the reference's benchmark_tps (speed.py:23-46).  The ~16 launches per layer are captured in a CUDA graph per
         (T, start position) and replayed (a 64-token prompt is otherwise bound by the host's launch rate)."""
-        if self.tp_world != 1:
-            raise RuntimeError("prefill: single-GPU decoders only (tensor-parallel runs consume the prompt through step())")
+        if self.tp_world > 1 and not getattr(self.allreduce, "has_rows", False):
+            raise RuntimeError("prefill: a tensor-parallel decoder needs an all-reduce with a rows() method attached "
+                               "(tp.PeerAllReduce(..., rows_elems=B * max_seq * hidden), tp.NcclAllReduce)")
         ids = ids.to(self.dev).to(torch.int64).contiguous()
         B, T = ids.shape
         assert B == self.B and T >= 1
-        pos0 = int(self.pos.item())
+        # tensor parallel: the host mirror (reading the device word would wait for this rank's stream, which in the
+        # one-process emulation of tp.LocalTPGroup may hold launches that wait for a peer not yet launched)
+        pos0 = self._pos_h if self.tp_world > 1 else int(self.pos.item())
         assert pos0 + T <= self.max_seq
         self._pos_h = pos0 + T
         if not use_graph:
@@ -441,6 +444,14 @@ class QuantDecoder:
             bits, w, N, K = L[name]
             return ops.linear_forward(bits, w, inp, N, K, bias)
 
+        def add_rows(y):
+            """h += y; tensor parallel: y holds this rank's partial sums of a row-parallel linear (o_proj / down_proj over
+            its K shard), h += sum over ranks of y in rank order (bit-identical on every rank), SURVEY §8e."""
+            if self.tp_world > 1:
+                self.allreduce.rows(y, h)
+            else:
+                check(Lb.amqb_add_rows(ptr(h), ptr(y), M, H, st), "add_rows")
+
         for li, L in enumerate(self.layers):
             check(Lb.amqb_rmsnorm_rows(ptr(h), ptr(L["norm1"]), ctypes.c_float(S.rms_eps), ptr(x), M, H, st), "rmsnorm_rows")
             bias = L.get("qkv_bias")
@@ -456,12 +467,12 @@ class QuantDecoder:
             if li == len(self.layers) - 1:
                 break                                   # only the cache rows of the last layer are needed
             o = linear(L, "self_attn.o_proj", attn)
-            check(Lb.amqb_add_rows(ptr(h), ptr(o), M, H, st), "add_rows")
+            add_rows(o)
             check(Lb.amqb_rmsnorm_rows(ptr(h), ptr(L["norm2"]), ctypes.c_float(S.rms_eps), ptr(x), M, H, st), "rmsnorm_rows")
             g, u = ops.linear_forward_grouped([(L[n][0], L[n][1], L[n][2], None) for n in ("mlp.gate_proj", "mlp.up_proj")], x, H)
             check(Lb.amqb_silu_mul_rows(ptr(g), ptr(u), ptr(act), M, self.I_loc, st), "silu_mul_rows")
             d = linear(L, "mlp.down_proj", act)
-            check(Lb.amqb_add_rows(ptr(h), ptr(d), M, H, st), "add_rows")
+            add_rows(d)
 
     @torch.inference_mode()
     def generate(self, input_ids: torch.Tensor, max_new_tokens: int, use_graph: bool = True,
@@ -479,7 +490,7 @@ class QuantDecoder:
         if use_graph and self.graph is None:
             self.capture()
         if prefill is None:
-            prefill = self.tp_world == 1
+            prefill = self.tp_world == 1 or getattr(self.allreduce, "has_rows", False)
         first = 0
         if prefill and prompt > 1:
             self.prefill(ids[:, : prompt - 1])

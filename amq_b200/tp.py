@@ -68,29 +68,45 @@ class PeerAllReduce:
     """Owns this rank's exchange buffer and the mapped peer buffers; __call__(partial, h) does
     h <- h + sum_ranks(partial)."""
 
-    def __init__(self, rank: int, world: int, max_elems: int, pdl: bool = True):
-        from ._lib import check, lib
+    def __init__(self, rank: int, world: int, max_elems: int, pdl: bool = True, rows_elems: int = 0):
+        """COLLECTIVE (handles travel over torch.distributed).  rows_elems > 0 also creates the exchange buffers of the
+        prompt pass's [B*T, hidden] all-reduce (amqb_allreduce_rows_f16): rows_elems >= B * T_max * hidden."""
+        from ._lib import lib
         self.rank, self.world, self.max_elems, self.pdl = rank, world, max_elems, pdl
+        self.rows_elems = rows_elems
+        self.has_rows = rows_elems > 0
+        self._opened = []
+        self._mine, self._peers = self._exchange(int(lib().amqb_ar_buffer_bytes(max_elems, world)))
+        self._rows_mine = self._rows_peers = None
+        if rows_elems > 0:
+            self._rows_mine, self._rows_peers = self._exchange(int(lib().amqb_ar_rows_buffer_bytes(rows_elems, world)))
+        import torch.distributed as dist
+        dist.barrier()
+
+    def _exchange(self, nbytes: int):
+        from ._lib import check, lib
         L = lib()
-        nbytes = int(L.amqb_ar_buffer_bytes(max_elems, world))
         mine = ctypes.c_void_p()
         handle = (ctypes.c_ubyte * 64)()
         check(L.amqb_ar_alloc(ctypes.c_size_t(nbytes), ctypes.byref(mine), handle), "ar_alloc")
-        self._mine = mine
         handles = exchange_handles(bytes(handle))
-        self._peers = (ctypes.c_void_p * world)()
-        self._opened = []
+        peers = (ctypes.c_void_p * self.world)()
         for r, h in enumerate(handles):
-            if r == rank:
-                self._peers[r] = mine
+            if r == self.rank:
+                peers[r] = mine
             else:
                 p = ctypes.c_void_p()
                 buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
                 check(L.amqb_ar_open(buf, ctypes.byref(p)), "ar_open")
-                self._peers[r] = p
+                peers[r] = p
                 self._opened.append(p)
-        import torch.distributed as dist
-        dist.barrier()
+        return mine, peers
+
+    def rows(self, partial: torch.Tensor, h: torch.Tensor) -> None:
+        """h <- h + sum over ranks of partial for an [M, hidden] matrix (the prompt pass)."""
+        if self._rows_peers is None:
+            raise RuntimeError("PeerAllReduce: created without rows_elems (no exchange buffers for the prompt pass)")
+        _rows_call(self._rows_peers, self.rank, self.world, partial, h, self.rows_elems, self.pdl)
 
     def make_ctx(self, pos_dev: torch.Tensor, gen_dev: torch.Tensor):
         """amqb_ar_ctx for the all-reduce fused into the row-parallel GEMV's epilogue (amqb_gemv_problem.allreduce)."""
@@ -112,12 +128,22 @@ class PeerAllReduce:
         if dist.is_initialized():
             dist.barrier()
         L.amqb_ar_free(self._mine)
-        self._mine = None
+        if self._rows_mine is not None:
+            L.amqb_ar_free(self._rows_mine)
+        self._mine = self._rows_mine = self._rows_peers = None
 
     def __call__(self, partial: torch.Tensor, h: torch.Tensor) -> None:
         from ._lib import check, cur_stream, lib, ptr
         check(lib().amqb_allreduce_f16(self._peers, self.rank, self.world, ptr(partial), ptr(h), ptr(h), partial.numel(),
                                        self.max_elems, int(self.pdl), cur_stream()), "allreduce")
+
+
+def _rows_call(peers, rank: int, world: int, partial: torch.Tensor, h: torch.Tensor, max_elems: int, pdl: bool) -> None:
+    from ._lib import check, cur_stream, lib, ptr
+    if partial.dtype != torch.float16 or h.dtype != torch.float16 or partial.numel() != h.numel():
+        raise ValueError("all-reduce of rows: fp16 partial and residual of the same size")
+    check(lib().amqb_allreduce_rows_f16(peers, rank, world, ptr(partial), ptr(h), ptr(h), ctypes.c_longlong(partial.numel()),
+                                        ctypes.c_longlong(max_elems), int(pdl), cur_stream()), "allreduce_rows")
 
 
 def _make_ctx(peers, rank: int, world: int, max_elems: int, pos_dev: torch.Tensor, gen_dev: torch.Tensor):
@@ -134,10 +160,17 @@ class LocalAllReduce:
     """PeerAllReduce for emulated ranks that live in ONE process on ONE device (tp.LocalTPGroup): the exchange buffers
     are plain device tensors of this process, so the "peer" pointers need no IPC mapping.  Same kernel."""
 
-    def __init__(self, rank: int, world: int, max_elems: int, bufs: List[torch.Tensor], pdl: bool = True):
+    def __init__(self, rank: int, world: int, max_elems: int, bufs: List[torch.Tensor], pdl: bool = True,
+                 rows_elems: int = 0, rows_bufs: Optional[List[torch.Tensor]] = None):
         self.rank, self.world, self.max_elems, self.pdl = rank, world, max_elems, pdl
         self._bufs = bufs
         self._peers = (ctypes.c_void_p * world)(*[ctypes.c_void_p(b.data_ptr()) for b in bufs])
+        self.rows_elems, self._rows_bufs = rows_elems, rows_bufs
+        self.has_rows = bool(rows_bufs)
+        self._rows_peers = (ctypes.c_void_p * world)(*[ctypes.c_void_p(b.data_ptr()) for b in rows_bufs]) if rows_bufs else None
+
+    def rows(self, partial: torch.Tensor, h: torch.Tensor) -> None:
+        _rows_call(self._rows_peers, self.rank, self.world, partial, h, self.rows_elems, self.pdl)
 
     def make_ctx(self, pos_dev: torch.Tensor, gen_dev: torch.Tensor):
         return _make_ctx(self._peers, self.rank, self.world, self.max_elems, pos_dev, gen_dev)
@@ -166,6 +199,10 @@ class LocalTPGroup:
         shard_plan(full.shape, world)
         nbytes = int(lib().amqb_ar_buffer_bytes(full.shape.hidden * full.B, world))
         self._bufs = [torch.zeros(nbytes, dtype=torch.uint8, device=dev) for _ in range(world)]
+        # exchange buffers of the prompt pass's [B*T, hidden] all-reduce (amqb_allreduce_rows_f16)
+        rows_elems = full.shape.hidden * full.B * (max_seq or full.max_seq)
+        rbytes = int(lib().amqb_ar_rows_buffer_bytes(rows_elems, world))
+        self._rows_bufs = [torch.zeros(rbytes, dtype=torch.uint8, device=dev) for _ in range(world)]
         self.streams = [torch.cuda.Stream(device=dev) for _ in range(world)]
         self.ranks = []
         for r in range(world):
@@ -174,7 +211,8 @@ class LocalTPGroup:
             m.adopt_shard_of(full)
             # own workspace (the M > 1 pre-pass writes the integer activations there; ops.workspace is per stream)
             m.ws = torch.zeros_like(m.ws)
-            m.attach_allreduce(LocalAllReduce(r, world, full.shape.hidden * full.B, self._bufs, pdl=pdl), fused=fused)
+            m.attach_allreduce(LocalAllReduce(r, world, full.shape.hidden * full.B, self._bufs, pdl=pdl,
+                                              rows_elems=rows_elems, rows_bufs=self._rows_bufs), fused=fused)
             self.ranks.append(m)
         self._captured = False
         # a GEMV whose epilogue waits for the peers' partial sums (fused all-reduce) keeps its SMs: every emulated rank
@@ -192,6 +230,10 @@ class LocalTPGroup:
         for b in self._bufs:
             c = ctypes.c_int(0)
             check(lib().amqb_ar_timeouts(ctypes.c_void_p(b.data_ptr()), ctypes.byref(c)), "ar_timeouts")
+            n += c.value
+        for b in self._rows_bufs:
+            c = ctypes.c_int(0)
+            check(lib().amqb_ar_rows_timeouts(ctypes.c_void_p(b.data_ptr()), ctypes.byref(c)), "ar_rows_timeouts")
             n += c.value
         return n
 
@@ -233,6 +275,8 @@ class LocalTPGroup:
         self._limit(True)
         for s, m in zip(self.streams, self.ranks):
             m.graph = m._capture(stream=s, warm=False)
+            if m.attn_splits > 1 and m.max_seq > m.attn_split_min_pos:      # as QuantDecoder.capture
+                m.graph_long = m._capture(stream=s, warm=False, splits=m.attn_splits)
         self._limit(False)
         self._captured = True
 
@@ -242,8 +286,15 @@ class LocalTPGroup:
 
         def go(m):
             m._check_room()
-            m.graph.replay()
+            (m.graph_long if (m.graph_long is not None and m._long_context()) else m.graph).replay()
             m._pos_h += 1
+        self._each(go)
+
+    def prefill(self, ids: torch.Tensor) -> None:
+        """Every rank's prompt pass (QuantDecoder.prefill, plain launches: a per-rank graph capture would have to warm up
+        one rank alone, whose all-reduces wait for peers that have not been launched)."""
+        def go(m):
+            m.prefill(ids, use_graph=False)
         self._each(go)
 
 
@@ -257,6 +308,9 @@ class NcclAllReduce:
     def __call__(self, partial: torch.Tensor, h: torch.Tensor) -> None:
         self.dist.all_reduce(partial)
         h.add_(partial)
+
+    rows = __call__
+    has_rows = True
 
 
 def _peak_gbs() -> float:

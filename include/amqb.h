@@ -275,6 +275,15 @@ int amqb_ar_free(void* dev_ptr);
 int amqb_allreduce_f16(void* const* peer_bufs_host, int rank, int world, const void* partial_f16,
                        const void* residual_f16, void* out_f16, int n_elems, int max_elems, int pdl,
                        void* stream);
+/* The same for an [M, hidden] activation matrix (the tensor-parallel prompt pass: one all-reduce of the partial sums
+ * after each row-parallel linear of the [B*T, K] pass).  One-shot push over up to 64 CTAs; its exchange
+ * buffers have their own layout: amqb_ar_alloc(amqb_ar_rows_buffer_bytes(max_elems, world)), handles exchanged and
+ * mapped like the others.  out may alias residual.  Graph-capturable; every rank issues the same sequence of calls. */
+size_t amqb_ar_rows_buffer_bytes(int max_elems, int world);
+int amqb_ar_rows_timeouts(const void* own_buf_dev, int* count_out);
+int amqb_allreduce_rows_f16(void* const* peer_bufs_host, int rank, int world, const void* partial_f16,
+                            const void* residual_f16, void* out_f16, long long n_elems, long long max_elems, int pdl,
+                            void* stream);
 
 #ifdef __cplusplus
 }

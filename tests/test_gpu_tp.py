@@ -91,6 +91,51 @@ for kind in ("fused", "amqb", "nccl"):
     dist.barrier()
     if kind != "nccl":
         m.allreduce.close()                                      # collective: unmap, barrier, free
+# 4. all-reduce of an activation matrix (prompt pass) against NCCL, several sizes / rounds (per-launch parity)
+arr = tp.PeerAllReduce(rank, world, 8, pdl=False, rows_elems=1 << 20)
+for it, n in enumerate([8, 8200, 1 << 20, 512 * 40, 1 << 20, 8]):
+    torch.manual_seed(100 * it + rank)
+    part = torch.randn(n, device=dev).half()
+    torch.manual_seed(7 + it)
+    h = torch.randn(n, device=dev).half()
+    ref = part.float().clone()
+    dist.all_reduce(ref)
+    ref = ref + h.float()
+    out = h.clone()
+    arr.rows(part, out)
+    torch.cuda.synchronize()
+    assert (out.float() - ref).abs().max() <= 2e-3 * ref.abs().max(), ("rows", it)
+    gathered = [torch.empty_like(out) for _ in range(world)]
+    dist.all_gather(gathered, out)
+    assert all(torch.equal(g, gathered[0]) for g in gathered)
+arr.close()
+# 5. the sharded decoder's prompt pass (plain launches, then the captured graph) against the unsharded one
+S = 64
+full = QuantDecoder(shape, arch, batch=2, max_seq=S, device=f"cuda:{local}", seed=11)
+m = QuantDecoder(shape, arch, batch=2, max_seq=S, device=f"cuda:{local}", seed=0, tp_rank=rank, tp_world=world)
+m.adopt_shard_of(full)
+m.attach_allreduce(tp.PeerAllReduce(rank, world, shape.hidden * 2, rows_elems=shape.hidden * 2 * S), fused=True)
+torch.manual_seed(5)
+ids = torch.randint(0, shape.vocab, (2, 41), device=dev)
+hk = full.Hkv // world
+for use_graph in (False, True, True):
+    for mm in (full, m):
+        mm.reset()
+        for L in mm.layers:
+            L["k_cache"].zero_(); L["v_cache"].zero_()
+    full.prefill(ids[:, :40]); m.prefill(ids[:, :40], use_graph=use_graph)
+    torch.cuda.synchronize()
+    for Lf, Lm in zip(full.layers, m.layers):
+        for c in ("k_cache", "v_cache"):
+            want = Lf[c][:, rank * hk:(rank + 1) * hk, :40].float(); got = Lm[c][:, :, :40].float()
+            assert (want - got).abs().max() <= 1e-2 * want.abs().max(), (use_graph, c)
+    for mm in (full, m):
+        mm.tokens.copy_(ids[:, 40]); mm.step()
+    torch.cuda.synchronize()
+    rel = float((m.logits - full.logits).abs().max() / full.logits.abs().max())
+    assert rel <= 2e-2, ("prefill", use_graph, rel)
+dist.barrier()
+m.allreduce.close()
 dist.barrier()
 torch.cuda.synchronize()
 print("ok", rank, flush=True)
@@ -156,4 +201,142 @@ def test_tp_decoder_matches_unsharded_emulated(world, batch, fused):
             assert torch.equal(m.logits, grp.ranks[0].logits)
         rel = float((grp.ranks[0].logits - ref).abs().max() / ref.abs().max())
         assert rel <= 2e-2, (world, batch, pos, rel)
+    assert grp.timeouts() == 0
+
+
+def _emulated_ranks_allreduce_rows(world, sizes):
+    import ctypes
+    from amq_b200 import tp
+    from amq_b200._lib import lib
+    dev = torch.device("cuda", 0)
+    max_elems = max(sizes)
+    nbytes = int(lib().amqb_ar_rows_buffer_bytes(max_elems, world))
+    bufs = [torch.zeros(nbytes, dtype=torch.uint8, device=dev) for _ in range(world)]
+    ars = [tp.LocalAllReduce(r, world, 8, bufs, pdl=False, rows_elems=max_elems, rows_bufs=bufs) for r in range(world)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(world)]
+    g = torch.Generator(device=dev).manual_seed(world)
+    for it, n in enumerate(sizes):
+        parts = [torch.randn(n, device=dev, generator=g).half() for _ in range(world)]
+        h = torch.randn(n, device=dev, generator=g).half()
+        outs = [h.clone() for _ in range(world)]
+        torch.cuda.synchronize()
+        for r in range(world):                       # every rank's launch is issued before anything is waited for
+            with torch.cuda.stream(streams[r]):
+                ars[r].rows(parts[r], outs[r])
+        torch.cuda.synchronize()
+        acc = torch.zeros(n, device=dev)
+        for r in range(world):                       # rank order, fp32, residual last: what the kernel does
+            acc = acc + parts[r].float()
+        want = (acc + h.float()).half()
+        for r in range(world):
+            assert torch.equal(outs[r], want), (world, it, n, r)
+    for b in bufs:
+        c = ctypes.c_int(0)
+        assert lib().amqb_ar_rows_timeouts(ctypes.c_void_p(b.data_ptr()), ctypes.byref(c)) == 0 and c.value == 0
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_allreduce_rows_emulated(world):
+    """amqb_allreduce_rows_f16 (the prompt pass's [B*T, hidden] all-reduce: one-shot push spread over up to 64 CTAs, slot
+    parity per launch) with `world` emulated ranks on one device, one stream each: exact fp32 rank-order sum, identical on
+    every rank, over sizes that use one CTA, a ragged last CTA, all 64 CTAs, and back (stale slots of a larger launch)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    _emulated_ranks_allreduce_rows(world, [8, 8200, 1 << 20, 512 * 40, (1 << 20) - 8, 8, 1024 * 8 * 3 + 16])
+
+
+def test_allreduce_rows_rejects_bad_arguments():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import ctypes
+    from amq_b200._lib import cur_stream, lib, ptr
+    L = lib()
+    assert L.amqb_ar_rows_buffer_bytes(0, 2) == 0 and L.amqb_ar_rows_buffer_bytes(8, 17) == 0
+    buf = torch.zeros(int(L.amqb_ar_rows_buffer_bytes(64, 1)), dtype=torch.uint8, device="cuda")
+    peers = (ctypes.c_void_p * 1)(ctypes.c_void_p(buf.data_ptr()))
+    x = torch.zeros(64, dtype=torch.float16, device="cuda")
+    call = lambda n, mx: L.amqb_allreduce_rows_f16(peers, 0, 1, ptr(x), ptr(x), ptr(x), ctypes.c_longlong(n),
+                                                    ctypes.c_longlong(mx), 0, cur_stream())
+    assert call(12, 64) != 0 and call(128, 64) != 0 and call(0, 64) != 0
+    assert call(64, 64) == 0                         # world = 1: out = residual + partial
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("world,batch,prompt", [(2, 2, 6), (2, 1, 41), (4, 2, 30)])
+def test_tp_prefill_matches_unsharded_emulated(world, batch, prompt):
+    """The tensor-parallel prompt pass (QuantDecoder.prefill with tp_world > 1: column-parallel q|k|v / gate|up on this
+    rank's heads and columns, row-parallel o_proj / down_proj followed by the [B*T, hidden] all-reduce) with emulated
+    ranks against the unsharded prompt pass: every rank's K/V cache equals its heads of the unsharded cache (1e-2), the
+    next decode step's logits agree (2e-2) and are bit-identical across ranks.  10 rows take the skinny decode kernel,
+    40 / 58 rows the tcgen05 GEMM."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import numpy as np
+    from amq_b200 import tp
+    from amq_b200.arch import LINEARS, ModelShape
+    from amq_b200.model import QuantDecoder
+    shape = ModelShape("tiny-gqa", 512, 1024, 8, 4, 2, 512, head_dim=64, qkv_bias=(batch == 2))
+    rs = np.random.RandomState(world)
+    arch = {n: rs.choice([2, 3, 4], size=2).tolist() for n in LINEARS}
+    full = QuantDecoder(shape, arch, batch=batch, max_seq=64, seed=5)
+    grp = tp.LocalTPGroup(full, world, fused=True)
+    ids = torch.randint(0, shape.vocab, (batch, prompt), device=full.dev)
+    P = prompt - 1
+    full.reset()
+    grp.set_tokens(ids[:, 0])
+    full.prefill(ids[:, :P])
+    grp.prefill(ids[:, :P])
+    torch.cuda.synchronize()
+    hk = full.Hkv // world
+    for r, m in enumerate(grp.ranks):
+        assert int(m.pos.item()) == P and m._pos_h == P
+        for Lf, Lm in zip(full.layers, m.layers):
+            for c in ("k_cache", "v_cache"):
+                want, got = Lf[c][:, r * hk:(r + 1) * hk, :P].float(), Lm[c][:, :, :P].float()
+                assert (want - got).abs().max() <= 1e-2 * want.abs().max(), (world, r, c)
+    full.tokens.copy_(ids[:, P])
+    for m in grp.ranks:
+        m.tokens.copy_(ids[:, P])
+    torch.cuda.synchronize()
+    full.step_eager(); grp.step_eager()
+    torch.cuda.synchronize()
+    for m in grp.ranks:
+        assert torch.equal(m.logits, grp.ranks[0].logits)
+    rel = float((grp.ranks[0].logits - full.logits).abs().max() / full.logits.abs().max())
+    assert rel <= 2e-2, (world, batch, prompt, rel)
+    assert grp.timeouts() == 0
+
+
+def test_tp_decoder_split_attention_emulated(monkeypatch):
+    """Tensor-parallel decoders take the split-KV decode attention like the unsharded one (each rank over its own heads):
+    forced on from position 8, eager and graph-replayed across the threshold, against the unsharded decoder."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import numpy as np
+    from amq_b200 import tp
+    from amq_b200.arch import LINEARS, ModelShape
+    from amq_b200.model import QuantDecoder
+    monkeypatch.setenv("AMQB_ATTN_SPLIT_MIN_POS", "8")
+    shape = ModelShape("tiny-gqa", 512, 1024, 8, 4, 2, 512, head_dim=64)
+    rs = np.random.RandomState(9)
+    arch = {n: rs.choice([2, 3, 4], size=2).tolist() for n in LINEARS}
+    full = QuantDecoder(shape, arch, batch=1, max_seq=32, seed=5)
+    grp = tp.LocalTPGroup(full, 2, fused=True)
+    assert all(m.attn_splits == 4 and m.attn_split_min_pos == 8 for m in grp.ranks)
+    tok = torch.randint(0, shape.vocab, (1,), device=full.dev)
+    full.reset(); full.tokens.copy_(tok)
+    grp.set_tokens(tok)
+    for pos in range(16):
+        for m in grp.ranks:
+            m.tokens.copy_(full.tokens)
+        torch.cuda.synchronize()
+        if pos in (0, 1, 9):
+            full.step_eager(); grp.step_eager()
+        else:
+            full.step(); grp.step()
+        torch.cuda.synchronize()
+        assert all(m.graph_long is not None for m in grp.ranks) or pos < 2
+        rel = float((grp.ranks[0].logits - full.logits).abs().max() / full.logits.abs().max())
+        assert rel <= 2e-2, (pos, rel)
+        assert torch.equal(grp.ranks[0].logits, grp.ranks[1].logits)
     assert grp.timeouts() == 0
