@@ -313,6 +313,9 @@ class NcclAllReduce:
     has_rows = True
 
 
+PROMPT_ROWS = 63          # the reference's TTFT / TPS protocol feeds a 64-token prompt: 63 rows in one pass + one decode step
+
+
 def _peak_gbs() -> float:
     p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -343,7 +346,8 @@ def measure_tp70b(steps: int, warmup: int, world: int, rank: int, local: int, tp
             if ar_kind == "nccl":
                 model.attach_allreduce(NcclAllReduce(), fused=False)
             else:
-                model.attach_allreduce(PeerAllReduce(rank, tp, shape.hidden), fused=(ar_kind == "fused"))
+                model.attach_allreduce(PeerAllReduce(rank, tp, shape.hidden, rows_elems=shape.hidden * PROMPT_ROWS),
+                                       fused=(ar_kind == "fused"))
         model.capture()
         lps = model.launches_per_step
         by = model.algorithmic_bytes_per_token()
@@ -362,11 +366,36 @@ def measure_tp70b(steps: int, warmup: int, world: int, rank: int, local: int, tp
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
+    # the prompt pass of the reference's protocol (speed.py:23-46: 64 prompt tokens, the first 63 in ONE pass over this
+    # rank's weight shard, [63, hidden] all-reduce after o_proj / down_proj) and the decode step that yields the first token
+    pf_ms = ttft_ms = 0.0
+    pf_err = None
+    if rank < tp:
+        try:
+            ids = torch.randint(0, shape.vocab, (1, PROMPT_ROWS), device=f"cuda:{local}",
+                                generator=torch.Generator(device=f"cuda:{local}").manual_seed(1))
+            reps = 5
+            for it in range(2 + reps):             # the first call captures the pass, the second is a warm replay
+                model.reset()
+                model.tokens.fill_(1)
+                torch.cuda.synchronize()
+                a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                a.record()
+                model.prefill(ids)
+                b.record()
+                model.step()
+                c.record()
+                torch.cuda.synchronize()
+                if it >= 2:
+                    pf_ms += a.elapsed_time(b) / reps
+                    ttft_ms += a.elapsed_time(c) / reps
+        except Exception as e:                     # the decode record above must survive a failure of this extra
+            pf_err, pf_ms, ttft_ms = repr(e)[:200], 0.0, 0.0
     if world > 1:
         dist.barrier()
-        t = torch.tensor([ms], device=f"cuda:{local}", dtype=torch.float64)
+        t = torch.tensor([ms, pf_ms, ttft_ms], device=f"cuda:{local}", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t[0])
+        ms, pf_ms, ttft_ms = float(t[0]), float(t[1]), float(t[2])
     if rank < tp:
         if tp > 1 and ar_kind != "nccl":
             model.allreduce.close()             # collective over the tp ranks (tp == world here)
@@ -380,6 +409,8 @@ def measure_tp70b(steps: int, warmup: int, world: int, rank: int, local: int, tp
             "allreduce": ar_kind, "allreduces_per_step": 2 * n_block if tp > 1 else 0,
             "allreduce_algorithmic_bytes": 2 * shape.hidden, "launches_per_step": lps,
             "per_gpu_weight_bytes": by["total"],
+            "prompt_pass_ms": pf_ms, "ttft_ms": ttft_ms, "prompt_rows": PROMPT_ROWS, "prompt_pass_error": pf_err,
+            "prompt_allreduce_algorithmic_bytes": 2 * shape.hidden * PROMPT_ROWS if tp > 1 else 0,
             "frac_of_hbm_roofline_per_gpu": (by["total"] / (peak * 1e9)) / (ms / steps * 1e-3)}
 
 

@@ -316,6 +316,7 @@ def run_ours(args, shape, arch):
     if rank == 0 and tp_rec is not None:
         base = tp1_rec if tp1_rec is not None else tp_rec
         tp_rec["tp1_tok_s"] = base["tok_s"]
+        tp_rec["tp1_prompt_pass_ms"] = base["prompt_pass_ms"]
         tp_rec["strong_scaling_efficiency"] = tp_rec["tok_s"] / (world * base["tok_s"])
         if nccl_log is not None:
             tp_rec["nccl"] = tpmod.nccl_log_summary(f"/tmp/amqb_nccl_{os.getpid()}_*.log")

@@ -36,6 +36,12 @@ def test_library_exports_every_declared_symbol():
     assert lib.amqb_native_bytes(3, 4096, 4096) == 128 * 32 * 1664
     assert lib.amqb_native_bytes(2, 4096, 4096) * 8 == 4096 * 4096 * 9 // 4      # 2.25 bits / weight
     assert lib.amqb_native_bytes(3, 100, 4096) == 0 and lib.amqb_native_bytes(5, 64, 128) == 0
+    # exchange buffers of the tensor-parallel all-reduces: header + one flag line per (rank, CTA) + two generations of slots
+    lib.amqb_ar_rows_buffer_bytes.restype = ctypes.c_size_t
+    lib.amqb_ar_buffer_bytes.restype = ctypes.c_size_t
+    assert lib.amqb_ar_rows_buffer_bytes(63 * 8192, 8) == 1024 + 128 * 8 * 64 + 2 * 8 * 63 * 8192 * 2
+    assert lib.amqb_ar_rows_buffer_bytes(0, 8) == 0 and lib.amqb_ar_rows_buffer_bytes(8, 17) == 0
+    assert lib.amqb_ar_buffer_bytes(8192, 8) > 2 * 8 * 8192 * (2 + 8)
 
 
 def test_native_layout_index_math(tmp_path):
