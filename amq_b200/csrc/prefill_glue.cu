@@ -93,6 +93,42 @@ add_rows_kernel(__half2* h, const __half2* y, size_t n2) {
   }
 }
 
+// ------------------------------------------------------------------ h += y, then RMSNorm of the updated row
+// The residual add after a row-parallel linear and the RMSNorm in front of the next linears, one launch instead of two
+// (grid = rows, 256 threads).  Bit-identical to add_rows_kernel followed by rmsnorm_rows_kernel: the sum is rounded to
+// fp16 and stored first, the statistic and the scaled output are taken from the ROUNDED values.
+__global__ void __launch_bounds__(256)
+add_rmsnorm_rows_kernel(__half* h, const __half* y, const __half* __restrict__ gamma, float eps, __half* out, int H) {
+  __shared__ float part[8];
+  pdl_launch_dependents();
+  pdl_wait();
+  __half2* hr = reinterpret_cast<__half2*>(h + (size_t)blockIdx.x * H);
+  const __half2* yr = reinterpret_cast<const __half2*>(y + (size_t)blockIdx.x * H);
+  const __half2* gr = reinterpret_cast<const __half2*>(gamma);
+  __half2* orow = reinterpret_cast<__half2*>(out + (size_t)blockIdx.x * H);
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < H / 2; i += blockDim.x) {
+    const float2 a = __half22float2(hr[i]), b = __half22float2(yr[i]);
+    const __half2 s2 = __float22half2_rn(make_float2(a.x + b.x, a.y + b.y));
+    hr[i] = s2;                                      // re-read below by the same thread
+    const float2 v = __half22float2(s2);
+    ss += v.x * v.x + v.y * v.y;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tot += part[w];
+  const float rs = rsqrtf(tot / (float)H + eps);
+  for (int i = threadIdx.x; i < H / 2; i += blockDim.x) {
+    float2 v = __half22float2(hr[i]);
+    v.x *= rs; v.y *= rs;
+    orow[i] = __hmul2(gr[i], __float22half2_rn(v));
+  }
+}
+
 // ------------------------------------------------------------------ RoPE + KV append for T prompt positions
 // grid (T, B), 256 threads.  q is rotated in place; rotated k and plain v go to the cache rows pos0 + t.
 __global__ void __launch_bounds__(256)
@@ -251,6 +287,14 @@ int amqb_add_rows(void* h_f16, const void* y_f16, int M, int H, void* stream) {
   const size_t n2 = (size_t)M * H / 2;
   return pf_launch(add_rows_kernel, dim3(ew_grid(n2)), dim3(256), (cudaStream_t)stream, "add_rows", (__half2*)h_f16,
                    (const __half2*)y_f16, n2);
+}
+
+int amqb_add_rmsnorm_rows(void* h_f16, const void* y_f16, const void* gamma_f16, float eps, void* out_f16, int M, int H,
+                          void* stream) {
+  if (!h_f16 || !y_f16 || !gamma_f16 || !out_f16 || M < 1 || H < 2 || H % 2 || out_f16 == h_f16)
+    return fail(AMQB_ERR_BAD_ARG, "add_rmsnorm_rows: bad argument");
+  return pf_launch(add_rmsnorm_rows_kernel, dim3(M), dim3(256), (cudaStream_t)stream, "add_rmsnorm_rows", (__half*)h_f16,
+                   (const __half*)y_f16, (const __half*)gamma_f16, eps, (__half*)out_f16, H);
 }
 
 int amqb_attn_prefill(void* q_f16, const void* k_f16, const void* v_f16, void* k_cache, void* v_cache, void* out_f16,

@@ -444,16 +444,19 @@ class QuantDecoder:
             bits, w, N, K = L[name]
             return ops.linear_forward(bits, w, inp, N, K, bias)
 
-        def add_rows(y):
-            """h += y; tensor parallel: y holds this rank's partial sums of a row-parallel linear (o_proj / down_proj over
-            its K shard), h += sum over ranks of y in rank order (bit-identical on every rank), SURVEY §8e."""
+        def add_norm(y, gamma):
+            """h += y, x = RMSNorm(h) * gamma (what follows every o_proj / down_proj).  One GPU: one fused row kernel.
+            Tensor parallel: y holds this rank's partial sums of a row-parallel linear (its K shard), so the add is the
+            all-reduce h += sum over ranks of y, in rank order (bit-identical on every rank), SURVEY §8e."""
             if self.tp_world > 1:
                 self.allreduce.rows(y, h)
+                check(Lb.amqb_rmsnorm_rows(ptr(h), ptr(gamma), ctypes.c_float(S.rms_eps), ptr(x), M, H, st), "rmsnorm_rows")
             else:
-                check(Lb.amqb_add_rows(ptr(h), ptr(y), M, H, st), "add_rows")
+                check(Lb.amqb_add_rmsnorm_rows(ptr(h), ptr(y), ptr(gamma), ctypes.c_float(S.rms_eps), ptr(x), M, H, st),
+                      "add_rmsnorm_rows")
 
+        check(Lb.amqb_rmsnorm_rows(ptr(h), ptr(self.layers[0]["norm1"]), ctypes.c_float(S.rms_eps), ptr(x), M, H, st), "rmsnorm_rows")
         for li, L in enumerate(self.layers):
-            check(Lb.amqb_rmsnorm_rows(ptr(h), ptr(L["norm1"]), ctypes.c_float(S.rms_eps), ptr(x), M, H, st), "rmsnorm_rows")
             bias = L.get("qkv_bias")
             bq = bk = bv = None
             if bias is not None:
@@ -467,12 +470,11 @@ class QuantDecoder:
             if li == len(self.layers) - 1:
                 break                                   # only the cache rows of the last layer are needed
             o = linear(L, "self_attn.o_proj", attn)
-            add_rows(o)
-            check(Lb.amqb_rmsnorm_rows(ptr(h), ptr(L["norm2"]), ctypes.c_float(S.rms_eps), ptr(x), M, H, st), "rmsnorm_rows")
+            add_norm(o, L["norm2"])
             g, u = ops.linear_forward_grouped([(L[n][0], L[n][1], L[n][2], None) for n in ("mlp.gate_proj", "mlp.up_proj")], x, H)
             check(Lb.amqb_silu_mul_rows(ptr(g), ptr(u), ptr(act), M, self.I_loc, st), "silu_mul_rows")
             d = linear(L, "mlp.down_proj", act)
-            add_rows(d)
+            add_norm(d, self.layers[li + 1]["norm1"])   # the next layer's input norm
 
     @torch.inference_mode()
     def generate(self, input_ids: torch.Tensor, max_new_tokens: int, use_graph: bool = True,

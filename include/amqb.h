@@ -249,6 +249,10 @@ int amqb_rmsnorm_rows(const void* x_f16, const void* gamma_f16, float eps, void*
 int amqb_silu_mul_rows(const void* gate_f16, const void* up_f16, void* out_f16, int M, int I, void* stream);
 /* h += y (fp32 add, one rounding), [M, H] */
 int amqb_add_rows(void* h_f16, const void* y_f16, int M, int H, void* stream);
+/* h += y as amqb_add_rows, then out = RMSNorm of the updated rows as amqb_rmsnorm_rows, in one launch (the residual add
+ * after o_proj / down_proj and the norm in front of the next linears); bit-identical to the two calls.  out != h. */
+int amqb_add_rmsnorm_rows(void* h_f16, const void* y_f16, const void* gamma_f16, float eps, void* out_f16, int M, int H,
+                          void* stream);
 /* RoPE on q [B*T, Hq*D] (in place) and k [B*T, Hkv*D] for cache positions pos0 .. pos0+T-1, append k, v to the
  * static cache ([B, Hkv, max_seq, D], as amqb_attn_decode), causal attention of every prompt row over cache
  * positions [0, pos0 + t].  out: fp16 [B*T, Hq*D].  rope_cos_sin: table from amqb_rope_table (required). */

@@ -236,6 +236,34 @@ def test_speed_benchmark_protocol(tmp_path, monkeypatch):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("M,H", [(1, 256), (19, 512), (63, 4096), (40, 8192)])
+def test_add_rmsnorm_rows_equals_the_two_calls(M, H):
+    """amqb_add_rmsnorm_rows (residual add + RMSNorm of the updated rows in one launch, what follows every o_proj /
+    down_proj of the prompt pass) is bit-identical to amqb_add_rows followed by amqb_rmsnorm_rows."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import ctypes
+    from amq_b200._lib import check, cur_stream, lib, ptr
+    dev = "cuda:0"
+    torch.cuda.set_device(0)
+    g = torch.Generator(device=dev).manual_seed(M + H)
+    L, st = lib(), cur_stream()
+    h0 = torch.randn(M, H, device=dev, generator=g).half()
+    y = (0.3 * torch.randn(M, H, device=dev, generator=g)).half()
+    gamma = (1 + 0.1 * torch.randn(H, device=dev, generator=g)).half()
+    eps = ctypes.c_float(1e-5)
+    ha, xa = h0.clone(), torch.empty_like(h0)
+    check(L.amqb_add_rows(ptr(ha), ptr(y), M, H, st), "add_rows")
+    check(L.amqb_rmsnorm_rows(ptr(ha), ptr(gamma), eps, ptr(xa), M, H, st), "rmsnorm_rows")
+    hb, xb = h0.clone(), torch.empty_like(h0)
+    check(L.amqb_add_rmsnorm_rows(ptr(hb), ptr(y), ptr(gamma), eps, ptr(xb), M, H, st), "add_rmsnorm_rows")
+    torch.cuda.synchronize()
+    assert torch.equal(ha, hb) and torch.equal(xa, xb)
+    assert torch.equal(ha, (h0.float() + y.float()).half())
+    assert L.amqb_add_rmsnorm_rows(ptr(hb), ptr(y), ptr(gamma), eps, ptr(hb), M, H, st) != 0      # out must not alias h
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("D,Hq,Hkv,B,T,pos0", [(64, 4, 2, 2, 19, 0), (128, 8, 2, 1, 45, 7), (128, 4, 4, 3, 8, 33)])
 def test_prefill_row_kernels_against_torch(D, Hq, Hkv, B, T, pos0):
     """Each kernel of csrc/prefill_glue.cu against a plain PyTorch fp32 statement of the same op: row RMSNorm, SiLU*up,
