@@ -388,8 +388,11 @@ class QuantDecoder:
         row kernels of csrc/prefill_glue.cu in between.  Leaves the K/V cache filled and the position advanced; the
         hidden state of the prompt rows is not kept (the last layer stops after the cache append), so the caller feeds
         the LAST prompt token through step() to obtain the first logits.  What HF generate() does with the prompt in
-        the reference's benchmark_tps (speed.py:23-46).  The ~16 launches per layer are captured in a CUDA graph per
-        (T, start position) and replayed (a 64-token prompt is otherwise bound by the host's launch rate)."""
+        the reference's benchmark_tps (speed.py:23-46).  The ~14 launches per layer are captured in a CUDA graph per
+        (T, start position) and replayed (a 64-token prompt is otherwise bound by the host's launch rate).
+        Tensor-parallel decoders run the same pass over their shard: the partial sums of o_proj / down_proj go through
+        the attached all-reduce's rows() (tp.PeerAllReduce(..., rows_elems=...): amqb_allreduce_rows_f16); every rank
+        must call prefill() with the same ids, and the start position is taken from the host mirror of the position."""
         if self.tp_world > 1 and not getattr(self.allreduce, "has_rows", False):
             raise RuntimeError("prefill: a tensor-parallel decoder needs an all-reduce with a rows() method attached "
                                "(tp.PeerAllReduce(..., rows_elems=B * max_seq * hidden), tp.NcclAllReduce)")

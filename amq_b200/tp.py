@@ -170,6 +170,8 @@ class LocalAllReduce:
         self._rows_peers = (ctypes.c_void_p * world)(*[ctypes.c_void_p(b.data_ptr()) for b in rows_bufs]) if rows_bufs else None
 
     def rows(self, partial: torch.Tensor, h: torch.Tensor) -> None:
+        if self._rows_peers is None:
+            raise RuntimeError("LocalAllReduce: created without rows_bufs (no exchange buffers for the prompt pass)")
         _rows_call(self._rows_peers, self.rank, self.world, partial, h, self.rows_elems, self.pdl)
 
     def make_ctx(self, pos_dev: torch.Tensor, gen_dev: torch.Tensor):

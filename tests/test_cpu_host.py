@@ -168,6 +168,28 @@ part = O.gptq_forward_fp32(x[:, k0:k1], q.numpy(), s, z, bits, 128)
 dist.all_reduce(part)
 full = O.gptq_forward_fp32(x, qw.numpy(), sc, ze, bits, 128)
 assert torch.allclose(part, full, rtol=1e-5, atol=1e-5)
+# prompt pass of a sharded MLP block over M rows: column-parallel gate / up (this rank's columns), row-parallel down
+# (its k groups), ONE all-reduce of the [M, hidden] partial sums (what amqb_allreduce_rows_f16 does over peer memory)
+M, H, I = 5, 128, 512
+def lin(n, k, seed):
+    r = np.random.RandomState(seed)
+    c = r.randint(0, 8, size=(n, k))
+    return (torch.from_numpy(O.gptq_pack_codes(c, 3)), torch.from_numpy(r.uniform(0.01, 0.02, size=(k // 128, n)).astype(np.float32)),
+            torch.from_numpy(r.uniform(0.02, 0.1, size=(k // 128, n)).astype(np.float32)))
+gate, up, down = lin(I, H, 1), lin(I, H, 2), lin(H, I, 3)
+xm = torch.from_numpy(np.random.RandomState(4).randn(M, H).astype(np.float32)).half()
+fwd = lambda xx, w: O.gptq_forward_fp32(xx, w[0].numpy(), w[1], w[2], 3, 128)
+act = lambda g, u: (torch.nn.functional.silu(g) * u).half()
+want = fwd(act(fwd(xm, gate), fwd(xm, up)), down)
+plan = tp.shard_plan(tp.ModelShape("tiny", H, I, 4, 4, 1, 64, head_dim=64), world)
+assert plan["mlp.gate_proj"] == {"N": I // world, "K": H, "split": "column"} and plan["mlp.down_proj"]["split"] == "row"
+g_loc = tp.shard_gptq_buffers(*gate, 3, "column", rank, world)
+u_loc = tp.shard_gptq_buffers(*up, 3, "column", rank, world)
+d_loc = tp.shard_gptq_buffers(*down, 3, "row", rank, world)
+part = fwd(act(fwd(xm, g_loc), fwd(xm, u_loc)), d_loc)
+assert part.shape == (M, H)
+dist.all_reduce(part)
+assert torch.allclose(part, want, rtol=1e-4, atol=1e-4), float((part - want).abs().max())
 dist.destroy_process_group()
 print("ok", rank)
 '''
