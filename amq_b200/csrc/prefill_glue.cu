@@ -171,6 +171,173 @@ rope_append_kernel(__half* q, const __half* k, const __half* v,
   }
 }
 
+// ------------------------------------------------------------------ the same two row kernels, 16-byte vectors
+// The scalar kernels above walk a row in half2 steps, and in add_rmsnorm_rows_kernel / rope_append_kernel every store
+// may alias the next iteration's loads (h is updated in place, q is rotated in place), so the compiler keeps the
+// iterations' memory round trips in order: 8 - 16 dependent round trips per thread (profiles/r02_launches_prefill_summary.txt:
+// 9.3 us and 19.6 us per launch at 63 rows).  Here a thread loads ALL its 16-byte vectors first (up to kRowVecs of a row
+// of up to 8192 elements, held in registers for the second pass), then computes and stores.
+constexpr int kRowVecs = 4;
+
+__device__ __forceinline__ float sumsq8(const uint4& a, float ss) {
+  const __half2* h = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 v = __half22float2(h[i]);
+    ss = __fmaf_rn(v.x, v.x, ss);
+    ss = __fmaf_rn(v.y, v.y, ss);
+  }
+  return ss;
+}
+
+// ADD: h += y first (fp32 add, one rounding, stored), statistic and output from the rounded sum; else x = h is only read.
+// Both instantiations accumulate the statistic in the same order, so add_rows + rmsnorm_rows == add_rmsnorm_rows bit for bit.
+template <bool ADD>
+__global__ void __launch_bounds__(256)
+rmsnorm_rows_v8_kernel(__half* h, const __half* y, const __half* __restrict__ gamma, float eps, __half* out, int H) {
+  __shared__ float part[8];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int nv = H / 8;
+  uint4* hr = reinterpret_cast<uint4*>(h + (size_t)blockIdx.x * H);
+  const uint4* yr = reinterpret_cast<const uint4*>(y + (size_t)blockIdx.x * H);
+  const uint4* gr = reinterpret_cast<const uint4*>(gamma);
+  uint4* orow = reinterpret_cast<uint4*>(out + (size_t)blockIdx.x * H);
+  uint4 a[kRowVecs], b[kRowVecs], g[kRowVecs];
+#pragma unroll
+  for (int u = 0; u < kRowVecs; ++u) {
+    const int i = threadIdx.x + 256 * u;
+    if (i < nv) {
+      a[u] = hr[i];
+      if (ADD) b[u] = yr[i];
+      g[u] = gr[i];
+    }
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int u = 0; u < kRowVecs; ++u) {
+    const int i = threadIdx.x + 256 * u;
+    if (i < nv) {
+      if (ADD) {
+        __half2* ah = reinterpret_cast<__half2*>(&a[u]);
+        const __half2* bh = reinterpret_cast<const __half2*>(&b[u]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 fa = __half22float2(ah[e]), fb = __half22float2(bh[e]);
+          ah[e] = __float22half2_rn(make_float2(fa.x + fb.x, fa.y + fb.y));
+        }
+        hr[i] = a[u];
+      }
+      ss = sumsq8(a[u], ss);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tot += part[w];
+  const float rs = rsqrtf(tot / (float)H + eps);
+#pragma unroll
+  for (int u = 0; u < kRowVecs; ++u) {
+    const int i = threadIdx.x + 256 * u;
+    if (i < nv) {
+      uint4 o4;
+      __half2* oh = reinterpret_cast<__half2*>(&o4);
+      const __half2* ah = reinterpret_cast<const __half2*>(&a[u]);
+      const __half2* gh = reinterpret_cast<const __half2*>(&g[u]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 v = __half22float2(ah[e]);
+        v.x *= rs; v.y *= rs;
+        oh[e] = __hmul2(gh[e], __float22half2_rn(v));
+      }
+      orow[i] = o4;
+    }
+  }
+}
+
+// RoPE + KV append, eight rotation pairs per item: item = (head, chunk c of D/16) rotates elements [8c, 8c+8) of the
+// first half against their partners in the second half.  A thread loads up to kRopeItems items before it stores any.
+constexpr int kRopeItems = 4;
+template <int D>
+__global__ void __launch_bounds__(256)
+rope_append_v8_kernel(__half* q, const __half* k, const __half* v, __half* kc, __half* vc,
+                      const float2* __restrict__ rope_tab, int pos0, int T, int Hq, int Hkv, int max_seq) {
+  constexpr int C = D / 16;                 // chunks per head
+  pdl_launch_dependents();
+  pdl_wait();
+  const int t = blockIdx.x, b = blockIdx.y;
+  const size_t row = (size_t)b * T + t;
+  const int pos = pos0 + t;
+  __half* qr = q + row * (size_t)Hq * D;
+  const __half* kr = k + row * (size_t)Hkv * D;
+  const __half* vr = v + row * (size_t)Hkv * D;
+  const float4* tab = reinterpret_cast<const float4*>(rope_tab + (size_t)pos * (D / 2));   // (cos, sin) x 2 per float4
+  const int n_items = (Hq + Hkv) * C;
+  for (int base = 0; base < n_items; base += 256 * kRopeItems) {
+    uint4 lo[kRopeItems], hi[kRopeItems];
+    float4 cs4[kRopeItems][4];
+#pragma unroll
+    for (int u = 0; u < kRopeItems; ++u) {
+      const int idx = base + threadIdx.x + 256 * u;
+      if (idx < n_items) {
+        const int head = idx / C, c = idx % C;
+        const __half* p = head < Hq ? qr + head * D : kr + (head - Hq) * D;
+        lo[u] = *reinterpret_cast<const uint4*>(p + 8 * c);
+        hi[u] = *reinterpret_cast<const uint4*>(p + D / 2 + 8 * c);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) cs4[u][e] = tab[4 * c + e];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kRopeItems; ++u) {
+      const int idx = base + threadIdx.x + 256 * u;
+      if (idx < n_items) {
+        const int head = idx / C, c = idx % C;
+        uint4 olo, ohi;
+        __half* ol = reinterpret_cast<__half*>(&olo);
+        __half* oh = reinterpret_cast<__half*>(&ohi);
+        const __half* il = reinterpret_cast<const __half*>(&lo[u]);
+        const __half* ih = reinterpret_cast<const __half*>(&hi[u]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float4 t4 = cs4[u][e >> 1];
+          // fp16-rounded cos / sin as HF (LlamaRotaryEmbedding casts them to the activation dtype)
+          const float cs = __half2float(__float2half_rn((e & 1) ? t4.z : t4.x));
+          const float sn = __half2float(__float2half_rn((e & 1) ? t4.w : t4.y));
+          const float a = __half2float(il[e]), cc = __half2float(ih[e]);
+          ol[e] = __float2half_rn(a * cs - cc * sn);
+          oh[e] = __float2half_rn(cc * cs + a * sn);
+        }
+        __half* dst = head < Hq ? qr + head * D
+                                : kc + (((size_t)b * Hkv + (head - Hq)) * max_seq + pos) * D;
+        *reinterpret_cast<uint4*>(dst + 8 * c) = olo;
+        *reinterpret_cast<uint4*>(dst + D / 2 + 8 * c) = ohi;
+      }
+    }
+  }
+  constexpr int VD = D / 8;                 // 16-byte vectors per head row
+  const int n_v = Hkv * VD;
+  for (int base = 0; base < n_v; base += 256 * kRopeItems) {
+    uint4 vv[kRopeItems];
+#pragma unroll
+    for (int u = 0; u < kRopeItems; ++u) {
+      const int idx = base + threadIdx.x + 256 * u;
+      if (idx < n_v) vv[u] = reinterpret_cast<const uint4*>(vr)[idx];
+    }
+#pragma unroll
+    for (int u = 0; u < kRopeItems; ++u) {
+      const int idx = base + threadIdx.x + 256 * u;
+      if (idx < n_v) {
+        const int hk = idx / VD, c = idx % VD;
+        reinterpret_cast<uint4*>(vc + (((size_t)b * Hkv + hk) * max_seq + pos) * D)[c] = vv[u];
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ causal attention over the cache
 // grid (ceil(T / 8), Hq, B), 8 warps: warp w owns query t0 + w (cache position pos0 + t0 + w) of head h.  The cached
 // K / V rows are staged 32 positions at a time in shared memory (each row is read from L2 once per 8 queries); inside
@@ -258,6 +425,12 @@ attn_prefill_kernel(const __half* q, const __half* kc, const __half* vc,
   }
 }
 
+// the 16-byte-vector row kernels: rows of up to 256 * kRowVecs vectors, every operand 16-byte aligned
+static bool rows_v8_ok(int H, const void* a, const void* b, const void* c, const void* d) {
+  return H % 8 == 0 && H / 8 <= 256 * kRowVecs &&
+         ((((uintptr_t)a) | ((uintptr_t)b) | ((uintptr_t)c) | ((uintptr_t)d)) & 15) == 0;
+}
+
 static int ew_grid(size_t n2) {
   size_t g = (n2 + 255) / 256;
   return (int)(g < 148 * 8 ? (g ? g : 1) : 148 * 8);
@@ -271,6 +444,9 @@ extern "C" {
 
 int amqb_rmsnorm_rows(const void* x_f16, const void* gamma_f16, float eps, void* out_f16, int M, int H, void* stream) {
   if (!x_f16 || !gamma_f16 || !out_f16 || M < 1 || H < 2 || H % 2) return fail(AMQB_ERR_BAD_ARG, "rmsnorm_rows: bad argument");
+  if (rows_v8_ok(H, x_f16, gamma_f16, out_f16, x_f16))
+    return pf_launch(rmsnorm_rows_v8_kernel<false>, dim3(M), dim3(256), (cudaStream_t)stream, "rmsnorm_rows",
+                     (__half*)const_cast<void*>(x_f16), (const __half*)x_f16, (const __half*)gamma_f16, eps, (__half*)out_f16, H);
   return pf_launch(rmsnorm_rows_kernel, dim3(M), dim3(256), (cudaStream_t)stream, "rmsnorm_rows", (const __half*)x_f16,
                    (const __half*)gamma_f16, eps, (__half*)out_f16, H);
 }
@@ -293,6 +469,9 @@ int amqb_add_rmsnorm_rows(void* h_f16, const void* y_f16, const void* gamma_f16,
                           void* stream) {
   if (!h_f16 || !y_f16 || !gamma_f16 || !out_f16 || M < 1 || H < 2 || H % 2 || out_f16 == h_f16)
     return fail(AMQB_ERR_BAD_ARG, "add_rmsnorm_rows: bad argument");
+  if (rows_v8_ok(H, h_f16, gamma_f16, out_f16, y_f16))
+    return pf_launch(rmsnorm_rows_v8_kernel<true>, dim3(M), dim3(256), (cudaStream_t)stream, "add_rmsnorm_rows", (__half*)h_f16,
+                     (const __half*)y_f16, (const __half*)gamma_f16, eps, (__half*)out_f16, H);
   return pf_launch(add_rmsnorm_rows_kernel, dim3(M), dim3(256), (cudaStream_t)stream, "add_rmsnorm_rows", (__half*)h_f16,
                    (const __half*)y_f16, (const __half*)gamma_f16, eps, (__half*)out_f16, H);
 }
@@ -305,9 +484,21 @@ int amqb_attn_prefill(void* q_f16, const void* k_f16, const void* v_f16, void* k
     return fail(AMQB_ERR_BAD_ARG, "attn_prefill: bad argument (pos0 + T <= max_seq, Hq % Hkv == 0, rope table required)");
   if (D != 64 && D != 128) return fail(AMQB_ERR_UNSUPPORTED_SHAPE, "attn_prefill: head_dim must be 64 or 128");
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = pf_launch(rope_append_kernel, dim3(T, B), dim3(256), st, "attn_prefill (rope + append)", (__half*)q_f16,
-                     (const __half*)k_f16, (const __half*)v_f16, (__half*)k_cache, (__half*)v_cache,
-                     (const float2*)rope_cos_sin, pos0, T, Hq, Hkv, D, max_seq);
+  int rc;
+  const bool v8 = (((uintptr_t)q_f16 | (uintptr_t)k_f16 | (uintptr_t)v_f16 | (uintptr_t)k_cache | (uintptr_t)v_cache |
+                    (uintptr_t)rope_cos_sin) & 15) == 0;
+  if (v8 && D == 128)
+    rc = pf_launch(rope_append_v8_kernel<128>, dim3(T, B), dim3(256), st, "attn_prefill (rope + append)", (__half*)q_f16,
+                   (const __half*)k_f16, (const __half*)v_f16, (__half*)k_cache, (__half*)v_cache,
+                   (const float2*)rope_cos_sin, pos0, T, Hq, Hkv, max_seq);
+  else if (v8)
+    rc = pf_launch(rope_append_v8_kernel<64>, dim3(T, B), dim3(256), st, "attn_prefill (rope + append)", (__half*)q_f16,
+                   (const __half*)k_f16, (const __half*)v_f16, (__half*)k_cache, (__half*)v_cache,
+                   (const float2*)rope_cos_sin, pos0, T, Hq, Hkv, max_seq);
+  else
+    rc = pf_launch(rope_append_kernel, dim3(T, B), dim3(256), st, "attn_prefill (rope + append)", (__half*)q_f16,
+                   (const __half*)k_f16, (const __half*)v_f16, (__half*)k_cache, (__half*)v_cache,
+                   (const float2*)rope_cos_sin, pos0, T, Hq, Hkv, D, max_seq);
   if (rc) return rc;
   const dim3 grid((T + kPfWarps - 1) / kPfWarps, Hq, B);
   if (D == 128)
