@@ -139,6 +139,43 @@ def cpu_reference_sample(arch, shape, threads: int, tensors=None):
                                     "extrapolated by N*K over the 224 quantized linears")
 
 
+def cpu_reference_block(arch, shape, threads: int):
+    """The reference's own CPU path on a bounded sample of this workload: ONE decoder block (block 0 of the arch: its
+    seven quantized linears with their own bit widths and the shapes of amq/configs/llama.json), batch 1, through the
+    oracle port of GPTQLinear.forward's torch branch (autogptq.py:245-283: shift-unpack -> fp16 scales*q - zeros ->
+    matmul).  A token is n_block such blocks (attention, norms and lm_head are not counted, which favours the CPU arm).
+    Returns (seconds for the block, description)."""
+    import numpy as np
+    import torch
+    from oracle import amq_oracle as O
+    from amq_b200.arch import LINEARS
+    from amq_b200.model import _SCALE_RANGE
+    torch.set_num_threads(threads)
+    G = 128
+    if "block" not in _CPU_CACHE:
+        # same recipe as the GPU arm's synthetic layers (amq_b200/model.py synthetic_native): uniform random codes, the
+        # realistic fp16 scale range of the bit width, fractional zero, packed into the reference's GPTQ layout
+        rs = np.random.RandomState(0)
+        layers = []
+        for name in LINEARS:
+            bits = int(arch[name][0])
+            N, K = shape.linear_shape[name]
+            qweight = O.gptq_pack_codes(rs.randint(0, 2 ** bits, size=(N, K)).astype(np.int64), bits)
+            lo, hi = _SCALE_RANGE[bits]
+            scale = torch.from_numpy(rs.uniform(lo, hi, size=(K // G, N)).astype(np.float32)).half()
+            zero = torch.from_numpy(rs.uniform(0.5, 2 ** bits - 1.5, size=(K // G, N)).astype(np.float32)).half()
+            layers.append((name, bits, torch.randn(1, K).half(), qweight, scale.float(), (zero * scale).float()))
+        _CPU_CACHE["block"] = layers
+    layers = _CPU_CACHE["block"]
+    t0 = time.perf_counter()
+    for _, bits, x, q, sc, z in layers:
+        O.gptq_forward_torch(x, q, sc, z, bits, G)
+    dt = time.perf_counter() - t0
+    desc = ("one decoder block of the workload (" + ", ".join(f"{n.split('.')[-1]} {b}b" for n, b, *_ in layers) +
+            f"; 1/{shape.n_block} of a token), batch 1, torch dequant+matmul")
+    return dt, desc
+
+
 def run_reference(args, shape, arch):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -147,17 +184,19 @@ def run_reference(args, shape, arch):
     threads = os.cpu_count() or 1
     times = []
     for i in range(args.warmup + args.steps):
-        t, desc = cpu_reference_sample(arch, shape, threads)
+        t, desc = cpu_reference_block(arch, shape, threads)
         if i >= args.warmup:
             times.append(t)
-    tok_time = sum(times) / len(times)
-    tok_s = 1.0 / tok_time
+    step_time = sum(times) / len(times)            # one block = 1 / n_block of a token
+    tok_s = 1.0 / (step_time * shape.n_block)
     line = {
         "impl": "reference", "metric": "batch-1 decode tok/s, Llama-2 7B AMQ 3-bit avg", "value": tok_s, "unit": "tok/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tok_time * 1e3,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_time * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
         "config": {"workload": f"{shape.name} random-init, AMQ mixed 2/3/4-bit avg 3.0 (synthetic arch, seed 0), batch-1 decode",
-                   "timing": "host wall clock; each step = one 4096x4096 3-bit linear on the CPU, token time extrapolated by N*K"},
+                   "timing": f"host wall clock; each step = ONE of the {shape.n_block} decoder blocks (its 7 quantized linears) on the "
+                             f"CPU = 1/{shape.n_block} token; value = 1 / ({shape.n_block} x step time), extrapolated over the identical blocks",
+                   "tokens_per_step": 1.0 / shape.n_block},
         "cpu_baseline": {"value": tok_s, "unit": "tok/s", "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": tok_s, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }

@@ -248,3 +248,7 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "tok/s" and d["higher_is_better"] is True
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["value"] > 0
+    # a step is one decoder block = 1 / 32 of a token, timed for real: the line's ms_per_step is the measured step, and
+    # value is tokens per step over the step time
+    assert abs(d["value"] - d["config"]["tokens_per_step"] / (d["ms_per_step"] * 1e-3)) <= 1e-9 * d["value"]
+    assert d["config"]["tokens_per_step"] == 1 / 32 and "q_proj" in d["cpu_baseline"]["sample"]
